@@ -1,0 +1,19 @@
+"""sloika_b200: the raw-signal basecall hot path of nanoporetech/sloika on B200 (sm_100a).
+
+Modules mirror the reference's names for this path (`layers`, `activation`, `conv`, `decode`,
+`basecall`, `helpers`, `bio`, `maths`, `variables`, `module_tools`) so a caller swaps
+`import sloika.X` for `import sloika_b200.X`; `sloika_b200.install_as_sloika()` does that swap
+in `sys.modules` for unmodified model scripts and pickles.
+"""
+__version__ = '0.1.0'
+
+
+def install_as_sloika():
+    """Alias this package as `sloika` so `models/*.py` (`import sloika.module_tools as smt`) run as is."""
+    import importlib
+    import sys
+    sys.modules.setdefault('sloika', sys.modules[__name__])
+    for sub in ('config', 'variables', 'activation', 'conv', 'layers', 'module_tools', 'decode',
+                'bio', 'maths', 'basecall', 'helpers'):
+        mod = importlib.import_module('sloika_b200.' + sub)
+        sys.modules.setdefault('sloika.' + sub, mod)
