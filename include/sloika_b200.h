@@ -1,0 +1,125 @@
+/*
+ * sloika_b200.h -- C ABI of the B200 (sm_100a) implementation of Sloika's raw basecall hot path.
+ *
+ * The reference (nanoporetech/sloika) has no native interface on this path: the network is a Theano
+ * graph (`sloika/layers.py`) and the decoder is NumPy (`sloika/decode.py`).  Each entry point below
+ * replaces one of those Python-level operators; the citation on each function is the reference code
+ * whose result it must reproduce.  A maintainer binds them with ctypes.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless stated otherwise; nothing is allocated, freed or kept
+ *     by the library, and no call synchronises the device: work is enqueued on `stream`
+ *     (a `cudaStream_t` passed as void*, NULL = legacy default stream) of the CURRENT device
+ *   - tensors are float32, `[time, batch, feature]` row-major (`sloika/layers.py:13`); a "row" is one
+ *     (time, batch) pair and `ld*` is the distance in floats between consecutive rows
+ *     (= feature count when dense), which lets Parallel/birnn outputs be written in place
+ *   - `lengths` (nullable, int32[B]) gives the number of valid time steps of each sequence of a padded
+ *     ragged batch; NULL means every sequence has the full length
+ *   - return value: 0 on success, a negative SLOIKA_ERR_* for rejected arguments, or a positive
+ *     `cudaError_t` if the launch failed; `sloika_b200_strerror` describes either
+ *   - the functions are re-entrant across streams and devices
+ */
+#ifndef SLOIKA_B200_H
+#define SLOIKA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SLOIKA_B200_ABI_VERSION 1
+
+#define SLOIKA_OK               0
+#define SLOIKA_ERR_ARG         -1   /* NULL pointer / non-positive size / inconsistent shape      */
+#define SLOIKA_ERR_UNSUPPORTED -2   /* valid request with no kernel (e.g. unknown activation)     */
+#define SLOIKA_ERR_WORKSPACE   -3   /* workspace pointer missing or too small                     */
+
+/* activation codes: sloika/activation.py:8 (linear), :52 (tanh), :56 (sigmoid), :38-42 (elu) */
+#define SLOIKA_ACT_LINEAR  0
+#define SLOIKA_ACT_TANH    1
+#define SLOIKA_ACT_SIGMOID 2
+#define SLOIKA_ACT_ELU     3
+
+int sloika_b200_abi_version(void);
+const char *sloika_b200_strerror(int code);
+
+/* Number of SMs / compute capability of the current device (host call, no kernel). */
+int sloika_b200_device_info(int *sm_count, int *cc_major, int *cc_minor);
+
+/*
+ * Convolution.run  -- sloika/layers.py:417-419, sloika/conv.py:66-111
+ *   y[t,b,o] = act( bias[o] + sum_i sum_k W[o,i,k] * xpad[t*stride + k, b, i] )
+ * cross-correlation (filter_flip=False) over the time axis zero-padded by (pad_l, pad_r);
+ * T_out = (T + pad_l + pad_r - winlen) / stride + 1.
+ *   x [T,B,Cin] dense; W [Cout,Cin,winlen]; bias [Cout]; y rows of ldy floats, T_out*B rows.
+ * With `lengths`, samples t >= lengths[b] of sequence b read as zero (each read is padded with
+ * zeros exactly as if it had been convolved on its own).
+ */
+int sloika_conv1d_fwd(const float *x, const float *W, const float *bias, float *y, long ldy,
+                      const int32_t *lengths, int T, int B, int Cin, int Cout, int winlen, int stride,
+                      int pad_l, int pad_r, int act, void *stream);
+
+/*
+ * FeedForward.run -- sloika/layers.py:157-158:  y = act( x . W' + bias )
+ *   x: M rows of K floats (row distance ldx); W [N,K]; bias [N] (NULL = zeros); y: M rows (ldy).
+ * Also the GRU input projection `vI = x iW' + b` (layers.py:1011) for all time steps at once.
+ */
+int sloika_linear_fwd(const float *x, long ldx, const float *W, const float *bias, float *y, long ldy,
+                      long M, int K, int N, int act, void *stream);
+
+/*
+ * Softmax.run -- sloika/layers.py:309-314:
+ *   t = x . W' + bias ; post = exp(t - max_j t) / sum_j exp(t - max_j t)     (row-wise over N)
+ *   post: M rows of N floats (row distance ldp >= N).
+ */
+int sloika_softmax_fwd(const float *x, long ldx, const float *W, const float *bias, float *post, long ldp,
+                       long M, int K, int N, void *stream);
+
+/*
+ * Gru.step scanned over time by RNN.run -- sloika/layers.py:1010-1021, :85-88 (h0 = 0); with
+ * `reverse` != 0 it is Reverse(Gru).run (layers.py:1449-1450): each sequence is walked from its own
+ * last valid step down to 0 and outputs land at their original time index.
+ *   vI = x_t iW' + b ; vS = h sW' ; z = gate(vI[:H]+vS[:H]) ; r = gate(vI[H:2H]+vS[H:])
+ *   hbar = act(vI[2H:] + (r*h) sW2') ; h' = z*h + (1-z)*hbar
+ *   x: T*B rows of I floats (ldx); iW [3H,I]; sW [2H,H]; sW2 [H,H]; b [3H]; y: T*B rows of H (ldy).
+ *   ws: workspace of sloika_gru_workspace_bytes(T,B,H) bytes (holds vI for all steps).
+ * Outputs at steps >= lengths[b] are written as zero.
+ */
+size_t sloika_gru_workspace_bytes(int T, int B, int H);
+int sloika_gru_fwd(const float *x, long ldx, const float *iW, const float *sW, const float *sW2,
+                   const float *b, float *y, long ldy, void *ws, size_t ws_bytes, const int32_t *lengths,
+                   int T, int B, int I, int H, int reverse, int act, int gate_act, void *stream);
+
+/* The recurrence alone, given vI [T,B,3H] dense (what sloika_gru_fwd runs after the projection). */
+int sloika_gru_recurrence_fwd(const float *vI, const float *sW, const float *sW2, float *y, long ldy,
+                              const int32_t *lengths, int T, int B, int H, int reverse, int act,
+                              int gate_act, void *stream);
+
+/*
+ * decode.prepare_post + decode.viterbi -- sloika/decode.py:21-36, :39-93 (called from
+ * sloika/basecall.py:44-46), batched: one CTA per read.
+ *   post: [T,B,S] with S = nbase^klen + 1, element (t,b,s) at post[t*ld_t + b*ld_b + s]
+ *   mode: SLOIKA_VIT_POST     post are probabilities; the kernel applies
+ *                                 lpost = log( (min_prob + (1-min_prob)*post) + 1e-10 )   (float32)
+ *         SLOIKA_VIT_LOG      post are already log-probabilities (`log=True`, decode.py:56)
+ *   tb_ws: workspace of sloika_viterbi_workspace_bytes(T,B,nbase,klen) bytes (uint8 traceback)
+ *   path_out int32 [B,T]: k-mer states of the best path with stays removed, left-aligned;
+ *   path_len int32 [B]; score_out float32 [B] (= max_j v_T[j]).
+ * skip_pen and min_prob are the reference's python floats (double); they are cast to float32 where
+ * NumPy casts them.  Tie rules follow decode.py exactly: first maximum over predecessors, skip beats step on a tie,
+ * stay beats move on a tie.  A sequence with lengths[b] < 1 yields path_len 0 and score 0.
+ */
+#define SLOIKA_VIT_POST 0
+#define SLOIKA_VIT_LOG  1
+size_t sloika_viterbi_workspace_bytes(int T, int B, int nbase, int klen);
+int sloika_viterbi_fwd(const float *post, long ld_t, long ld_b, const int32_t *lengths, int T, int B,
+                       int nbase, int klen, double skip_pen, double min_prob, int mode, void *tb_ws,
+                       size_t ws_bytes, int32_t *path_out, int32_t *path_len, float *score_out,
+                       void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SLOIKA_B200_H */

@@ -1,0 +1,167 @@
+"""Basecall workers (reference `sloika/basecall.py`).
+
+Drop-in surface: `init_worker(model)`, `decode_post(...)`, `raw_worker(fast5_file_name, ...)`,
+`SeqPrinter` keep the reference's names, arguments, return tuples and error behaviour
+(`basecall.py:12-23, 26-51, 88-121, 124-163`).  On top of that `basecall_signals` / `raw_batch` run a
+*batch* of whole reads through the device in one go (ragged batch, reads stay independent exactly as
+with the reference's batch-of-one calls), which is how the GPU is actually fed.
+"""
+import sys
+
+import numpy as np
+
+from sloika_b200 import bio, decode, util
+from sloika_b200.config import sloika_dtype
+from sloika_b200.maths import mad
+from sloika_b200.variables import nstate, DEFAULT_ALPHABET
+
+calc_post = None
+
+
+def init_worker(model, device=None):
+    """ Worker init function: load the model once per process into the global `calc_post`
+    (`basecall.py:12-23`).  `model` is a Sloika model pickle or a file from `helpers.compile_model`.
+    """
+    from sloika_b200 import helpers
+    global calc_post
+    calc_post = helpers.load_calc_post(model, device=device)
+
+
+def decode_post(post, kmer_len, transducer, bad, min_prob, skip=5.0, trans=None, nbase=4, eta=1e-10):
+    """ Decode Viterbi state sequence from a posterior matrix `[T, 1, S]` (`basecall.py:26-51`)
+
+    :returns: score, Viterbi path
+    """
+    assert post.shape[2] == nstate(kmer_len, transducer=transducer, bad_state=bad, nbase=nbase)
+    if not transducer:
+        raise NotImplementedError("the non-transducer decoder (sloika/olddecode.py) is not on the "
+                                  "B200 raw basecall path; all raw models are transducers")
+    assert post.shape[1] == 1, "decode_post decodes one read; use decode.viterbi_batch for batches"
+    score, paths = decode.viterbi_batch(post, None, klen=kmer_len, skip_pen=skip, min_prob=min_prob,
+                                        nbase=nbase)
+    return score[0], paths[0]
+
+
+def prepare_signal(signal, trim, open_pore_fraction):
+    """Trim and normalise one raw signal (`basecall.py:111-118`); None when nothing is left."""
+    from sloika_b200 import batch
+    signal = batch.trim_open_pore(signal, open_pore_fraction)
+    signal = util.trim_array(signal, *trim)
+    if signal.size == 0:
+        return None
+    return ((signal - np.median(signal)) / mad(signal)).astype(sloika_dtype)
+
+
+def basecall_signals(signals, kmer_len=5, min_prob=1e-5, skip=0.0, nbase=4, network=None):
+    """Forward + Viterbi for a batch of normalised whole-read signals (list of 1-D float32 arrays).
+
+    Reads are packed into one padded `[Tmax, B, 1]` batch with per-read lengths; every kernel honours
+    the lengths, so each read sees exactly the computation it would see alone (`basecall.py:117-119`
+    feeds one read per call).  Returns a list of `(score, path)`.
+    """
+    import torch
+    net = network if network is not None else calc_post
+    if net is None:
+        raise RuntimeError("init_worker() has not been called")
+    if not signals:
+        return []
+    dev = net.device
+    lens = np.array([len(s) for s in signals], dtype=np.int32)
+    host = torch.zeros((int(lens.max()), len(signals)), dtype=torch.float32).pin_memory()
+    for b, s in enumerate(signals):
+        host[:len(s), b] = torch.from_numpy(np.ascontiguousarray(s, dtype=np.float32))
+    x = host.to(dev, non_blocking=True).unsqueeze(2)
+    out = net.forward_device(x, torch.from_numpy(lens).to(dev))
+    score, paths = decode.viterbi_batch(out.data, out.lengths, klen=kmer_len, skip_pen=skip,
+                                        min_prob=min_prob, nbase=nbase)
+    return list(zip(score.tolist(), paths))
+
+
+def _read_raw(fast5_file_name):
+    from sloika_b200.fast5 import Fast5
+    with Fast5(fast5_file_name) as f5:
+        return f5.get_read(raw=True), f5.filename_short
+
+
+def raw_worker(fast5_file_name, trim, open_pore_fraction, kmer_len, transducer, bad, min_prob,
+               alphabet=DEFAULT_ALPHABET, skip=5.0, trans=None):
+    """ Worker function for basecalling one fast5 file from raw data (`basecall.py:88-121`)
+
+    :returns: (read name, score, path of k-mer states, number of samples) or None for unreadable /
+        too-short reads (message on stderr, as the reference)
+    """
+    try:
+        signal, sn = _read_raw(fast5_file_name)
+    except Exception as e:
+        sys.stderr.write("Error getting raw data for file {}\n{!r}\n".format(fast5_file_name, e))
+        return None
+    inMat = prepare_signal(signal, trim, open_pore_fraction)
+    if inMat is None:
+        sys.stderr.write("Read too short in file {}\n".format(fast5_file_name))
+        return None
+    inMat = inMat[:, None, None]
+    post = calc_post.forward_device(_to_device(inMat))
+    score, call = decode_post(post.data, kmer_len, transducer, bad, min_prob, skip, trans, nbase=len(alphabet))
+    return sn, score, call, inMat.shape[0]
+
+
+def raw_batch(fast5_file_names, trim=(200, 10), open_pore_fraction=0, kmer_len=5, transducer=True,
+              bad=True, min_prob=1e-5, alphabet=DEFAULT_ALPHABET, skip=0.0, trans=None):
+    """`raw_worker` over many files in one device batch; same result tuples, None for bad reads."""
+    assert transducer, "only transducer models are supported"
+    names, signals, slots = [], [], []
+    results = [None] * len(fast5_file_names)
+    for i, fn in enumerate(fast5_file_names):
+        try:
+            signal, sn = _read_raw(fn)
+        except Exception as e:
+            sys.stderr.write("Error getting raw data for file {}\n{!r}\n".format(fn, e))
+            continue
+        sig = prepare_signal(signal, trim, open_pore_fraction)
+        if sig is None:
+            sys.stderr.write("Read too short in file {}\n".format(fn))
+            continue
+        names.append(sn)
+        signals.append(sig)
+        slots.append(i)
+    calls = basecall_signals(signals, kmer_len=kmer_len, min_prob=min_prob, skip=skip, nbase=len(alphabet))
+    for i, sn, sig, (score, path) in zip(slots, names, signals, calls):
+        results[i] = (sn, np.float32(score), path, len(sig))
+    return results
+
+
+def _to_device(inMat):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(inMat)).to(calc_post.device)
+
+
+class SeqPrinter(object):
+    """ Formats fasta records and writes them to stdout or a file (`basecall.py:124-163`)
+
+    :param kmer_len: length of kmer to use for converting states to kmers
+    :param datatype: collective noun for the model input, e.g. "events" or "samples"
+    :param transducer: if True, a kmer followed by itself is a move, not a stay
+    :param fname: name of output file or None to use sys.stdout
+    """
+
+    def __init__(self, kmer_len, datatype="events", transducer=False, fname=None, alphabet=DEFAULT_ALPHABET):
+        if isinstance(alphabet, bytes):
+            alphabet = alphabet.decode('ascii')
+        self.kmer_len = kmer_len
+        self.alphabet = alphabet
+        self.kmers = bio.all_kmers(kmer_len, alphabet=alphabet)
+        self.transducer = transducer
+        self.datatype = datatype
+        self.close_fh = fname is not None
+        self.fh = open(fname, 'w') if self.close_fh else sys.stdout
+
+    def __del__(self):
+        if getattr(self, 'close_fh', False):
+            self.fh.close()
+
+    def write(self, read_name, score, call, nev):
+        seq = bio.states_to_sequence(call, self.kmer_len, self.alphabet, always_move=self.transducer)
+        self.fh.write(">{} score {:.0f}, {} {} to {} bases\n".format(read_name, score,
+                                                                     nev, self.datatype, len(seq)))
+        self.fh.write(seq + '\n')
+        return len(seq)

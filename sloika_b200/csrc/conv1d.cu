@@ -1,0 +1,152 @@
+// Strided 1-D convolution over the time axis with fused bias + activation.
+//
+// Reference semantics: Convolution.run (sloika/layers.py:417-419) -> conv.conv_1d
+// (sloika/conv.py:90-111): zero-pad time by (pad_l, pad_r), valid cross-correlation
+// (filter_flip=False) with step `stride`, add bias, activation.  Theano materialises the padded copy,
+// two transposes and an im2col GEMM; here padding is a predicate on the load and the layout
+// [time, batch, feature] is consumed and produced in place.
+//
+// HBM-bound: 4*Cin bytes in and 4*Cout/stride bytes out per raw sample (Cin = 1 for raw signal).
+#include "common.cuh"
+
+namespace sloika {
+
+// Raw-signal case Cin == 1, Cout % 4 == 0.  One CTA handles TT output steps x BT sequences.
+//   smem xs[(TT-1)*stride + WIN][BT]  input window, zero filled outside [0, len_b)
+//   thread = (c4, bq): fixed group of 4 output channels (weights + bias live in registers for the
+//   whole CTA), loops over (t, b) pairs; a warp writes consecutive float4 of the dense [B, Cout]
+//   slab of one time step -> fully coalesced 128-bit stores.
+template <int WIN>
+__global__ void __launch_bounds__(256, 2)
+conv1d_raw_kernel(const float *__restrict__ x, const float *__restrict__ W, const float *__restrict__ bias,
+                  float *__restrict__ y, long ldy, const int32_t *__restrict__ lengths, int T, int B, int Cout,
+                  int stride, int pad_l, int Tout, int TT, int BT, int act)
+{
+    extern __shared__ float xs[];                    // [rows][BT]
+    const int b0 = blockIdx.x * BT;
+    const int t0 = blockIdx.y * TT;
+    const int rows = (TT - 1) * stride + WIN;
+    const int nc4 = Cout >> 2;
+    const int bq = blockDim.x / nc4;                 // sequences handled per pass
+    const int c4 = threadIdx.x % nc4;
+    const int bl = threadIdx.x / nc4;
+
+    for (int e = threadIdx.x; e < rows * BT; e += blockDim.x) {
+        const int r = e / BT, b = e - r * BT;
+        const int tin = t0 * stride - pad_l + r;
+        const int bg = b0 + b;
+        float v = 0.0f;
+        if (bg < B && tin >= 0 && tin < T) {
+            const int len = lengths ? lengths[bg] : T;
+            if (tin < len) v = __ldg(x + (long)tin * B + bg);
+        }
+        xs[e] = v;
+    }
+
+    float4 w[WIN];
+    float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (bl < bq) {
+#pragma unroll
+        for (int k = 0; k < WIN; k++) {
+            w[k].x = __ldg(W + (4 * c4 + 0) * WIN + k);
+            w[k].y = __ldg(W + (4 * c4 + 1) * WIN + k);
+            w[k].z = __ldg(W + (4 * c4 + 2) * WIN + k);
+            w[k].w = __ldg(W + (4 * c4 + 3) * WIN + k);
+        }
+        bv = __ldg(reinterpret_cast<const float4 *>(bias) + c4);
+    }
+    __syncthreads();
+    if (bl >= bq) return;
+
+    for (int tl = 0; tl < TT; tl++) {
+        const int t = t0 + tl;
+        if (t >= Tout) break;
+        for (int b = bl; b < BT; b += bq) {
+            const int bg = b0 + b;
+            if (bg >= B) break;
+            float4 acc = bv;
+            const float *xp = xs + (tl * stride) * BT + b;
+#pragma unroll
+            for (int k = 0; k < WIN; k++) {
+                const float xv = xp[k * BT];
+                acc.x = fmaf(w[k].x, xv, acc.x);
+                acc.y = fmaf(w[k].y, xv, acc.y);
+                acc.z = fmaf(w[k].z, xv, acc.z);
+                acc.w = fmaf(w[k].w, xv, acc.w);
+            }
+            acc.x = apply_act(acc.x, act);
+            acc.y = apply_act(acc.y, act);
+            acc.z = apply_act(acc.z, act);
+            acc.w = apply_act(acc.w, act);
+            float *yp = y + ((long)t * B + bg) * ldy + 4 * c4;
+            __stcs(reinterpret_cast<float4 *>(yp), acc);     // streamed once, read by the next layer
+        }
+    }
+}
+
+// General case (any Cin / winlen / Cout): one thread per output element, operands through L1/L2.
+// Not on the raw-signal hot path; kept so the operator covers the reference's full signature.
+__global__ void conv1d_generic_kernel(const float *__restrict__ x, const float *__restrict__ W,
+                                      const float *__restrict__ bias, float *__restrict__ y, long ldy,
+                                      const int32_t *__restrict__ lengths, int T, int B, int Cin, int Cout,
+                                      int winlen, int stride, int pad_l, int Tout, int act)
+{
+    const long total = (long)Tout * B * Cout;
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+        const int o = (int)(e % Cout);
+        const long tb = e / Cout;
+        const int b = (int)(tb % B);
+        const int t = (int)(tb / B);
+        const int len = lengths ? lengths[b] : T;
+        float acc = bias[o];
+        for (int i = 0; i < Cin; i++) {
+            for (int k = 0; k < winlen; k++) {
+                const int tin = t * stride - pad_l + k;
+                if (tin >= 0 && tin < T && tin < len)
+                    acc = fmaf(W[((long)o * Cin + i) * winlen + k], x[((long)tin * B + b) * Cin + i], acc);
+            }
+        }
+        y[tb * ldy + o] = apply_act(acc, act);
+    }
+}
+
+}  // namespace sloika
+
+using namespace sloika;
+
+extern "C" int sloika_conv1d_fwd(const float *x, const float *W, const float *bias, float *y, long ldy,
+                                 const int32_t *lengths, int T, int B, int Cin, int Cout, int winlen, int stride,
+                                 int pad_l, int pad_r, int act, void *stream)
+{
+    if (!x || !W || !bias || !y) return SLOIKA_ERR_ARG;
+    if (T < 0 || B <= 0 || Cin <= 0 || Cout <= 0 || winlen <= 0 || stride <= 0 || pad_l < 0 || pad_r < 0 ||
+        ldy < Cout)
+        return SLOIKA_ERR_ARG;
+    if (!act_known(act)) return SLOIKA_ERR_UNSUPPORTED;
+    const long span = (long)T + pad_l + pad_r - winlen;
+    const int Tout = span < 0 ? 0 : (int)(span / stride + 1);
+    if (Tout == 0) return SLOIKA_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+
+    const bool aligned = (Cout % 4 == 0) && (ldy % 4 == 0) && (((uintptr_t)y & 15) == 0) &&
+                         (((uintptr_t)bias & 15) == 0) && (Cout / 4 <= 256);
+    if (Cin == 1 && winlen == 11 && aligned) {
+        const int BT = 32, TT = 16;
+        const int nc4 = Cout / 4;
+        const int threads = (256 / nc4) * nc4;
+        dim3 grid((unsigned)ceil_div(B, BT), (unsigned)ceil_div(Tout, TT));
+        const size_t smem = sizeof(float) * ((size_t)(TT - 1) * stride + winlen) * BT;
+        if (smem <= 48 * 1024) {
+            conv1d_raw_kernel<11><<<grid, threads, smem, st>>>(x, W, bias, y, ldy, lengths, T, B, Cout, stride,
+                                                               pad_l, Tout, TT, BT, act);
+            SLOIKA_RETURN_LAUNCH_STATUS();
+        }
+    }
+    const long total = (long)Tout * B * Cout;
+    const int threads = 256;
+    long blocks = ceil_div(total, threads);
+    if (blocks > 148L * 32) blocks = 148L * 32;
+    conv1d_generic_kernel<<<(unsigned)blocks, threads, 0, st>>>(x, W, bias, y, ldy, lengths, T, B, Cin, Cout,
+                                                               winlen, stride, pad_l, Tout, act);
+    SLOIKA_RETURN_LAUNCH_STATUS();
+}

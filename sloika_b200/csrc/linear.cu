@@ -1,0 +1,176 @@
+// y = act(x . W' + bias): FeedForward.run (sloika/layers.py:157-158), the GRU input projection
+// vI = x iW' + b (layers.py:1011) for all time steps at once, and the logits of Softmax.run
+// (layers.py:310) followed by the row softmax (layers.py:311-314).
+//
+// Round-1 implementation: fp32 SIMT GEMM (128x64 tile, 8x4 per thread) with fused bias/activation
+// epilogue.  M = T*B rows is huge (819 200), K and N are small (<= 256 / <= 1025), so both operands'
+// K extent is streamed in 16-wide slabs through shared memory.  This is the kernel the tcgen05
+// (3xTF32) projection replaces; it stays as the exact-fp32 fallback for odd shapes.
+#include "common.cuh"
+
+namespace sloika {
+
+constexpr int BM = 128, BN = 64, BK = 16, LIN_THREADS = 256;
+
+__global__ void __launch_bounds__(LIN_THREADS, 2)
+linear_kernel(const float *__restrict__ x, long ldx, const float *__restrict__ W, const float *__restrict__ bias,
+              float *__restrict__ y, long ldy, long M, int K, int N, int act, int vec_in, int vec_out)
+{
+    __shared__ __align__(16) float As[BK][BM + 4];
+    __shared__ __align__(16) float Bs[BK][BN + 4];
+    const int tid = threadIdx.x;
+    const long m0 = (long)blockIdx.x * BM;
+    const int n0 = blockIdx.y * BN;
+    const int tx = tid & 15, ty = tid >> 4;          // 16 x 16 threads: n = tx*4.., m = ty*8..
+    const int lrow = tid >> 2, lkq = tid & 3;         // loader mapping: row, k-quad
+
+    float acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = 0.0f;
+
+    for (int k0 = 0; k0 < K; k0 += BK) {
+        const int k = k0 + lkq * 4;
+        // A slab: 128 rows x 16 k (two rows per thread)
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int r = lrow + 64 * h;
+            const long m = m0 + r;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (m < M) {
+                const float *p = x + m * ldx + k;
+                if (vec_in && k + 3 < K) {
+                    v = __ldg(reinterpret_cast<const float4 *>(p));
+                } else {
+                    if (k + 0 < K) v.x = __ldg(p + 0);
+                    if (k + 1 < K) v.y = __ldg(p + 1);
+                    if (k + 2 < K) v.z = __ldg(p + 2);
+                    if (k + 3 < K) v.w = __ldg(p + 3);
+                }
+            }
+            As[lkq * 4 + 0][r] = v.x; As[lkq * 4 + 1][r] = v.y;
+            As[lkq * 4 + 2][r] = v.z; As[lkq * 4 + 3][r] = v.w;
+        }
+        {   // B slab: 64 rows of W x 16 k
+            const int n = n0 + lrow;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (n < N) {
+                const float *p = W + (long)n * K + k;
+                if ((K & 3) == 0 && k + 3 < K) {
+                    v = __ldg(reinterpret_cast<const float4 *>(p));
+                } else {
+                    if (k + 0 < K) v.x = __ldg(p + 0);
+                    if (k + 1 < K) v.y = __ldg(p + 1);
+                    if (k + 2 < K) v.z = __ldg(p + 2);
+                    if (k + 3 < K) v.w = __ldg(p + 3);
+                }
+            }
+            Bs[lkq * 4 + 0][lrow] = v.x; Bs[lkq * 4 + 1][lrow] = v.y;
+            Bs[lkq * 4 + 2][lrow] = v.z; Bs[lkq * 4 + 3][lrow] = v.w;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BK; kk++) {
+            const float4 a0 = *reinterpret_cast<const float4 *>(&As[kk][ty * 8]);
+            const float4 a1 = *reinterpret_cast<const float4 *>(&As[kk][ty * 8 + 4]);
+            const float4 b = *reinterpret_cast<const float4 *>(&Bs[kk][tx * 4]);
+            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                acc[i][0] = fmaf(a[i], b.x, acc[i][0]);
+                acc[i][1] = fmaf(a[i], b.y, acc[i][1]);
+                acc[i][2] = fmaf(a[i], b.z, acc[i][2]);
+                acc[i][3] = fmaf(a[i], b.w, acc[i][3]);
+            }
+        }
+        __syncthreads();
+    }
+
+    const int n = n0 + tx * 4;
+    float bv[4] = {0.f, 0.f, 0.f, 0.f};
+    if (bias) {
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (n + j < N) bv[j] = __ldg(bias + n + j);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const long m = m0 + ty * 8 + i;
+        if (m >= M) break;
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) o[j] = apply_act(acc[i][j] + bv[j], act);
+        float *p = y + m * ldy + n;
+        if (vec_out && n + 3 < N) {
+            *reinterpret_cast<float4 *>(p) = make_float4(o[0], o[1], o[2], o[3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (n + j < N) p[j] = o[j];
+        }
+    }
+}
+
+// Row softmax in place, one warp per row: m = max; e = exp(t - m); e / sum(e)  (layers.py:311-314).
+__global__ void __launch_bounds__(256)
+softmax_rows_kernel(float *__restrict__ post, long ldp, long M, int N)
+{
+    const int lane = threadIdx.x & 31;
+    const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= M) return;
+    float *p = post + row * ldp;
+    float m = -INFINITY;
+    for (int j = lane; j < N; j += 32) m = fmaxf(m, p[j]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float s = 0.0f;
+    for (int j = lane; j < N; j += 32) {
+        const float e = expf(p[j] - m);
+        p[j] = e;
+        s += e;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    for (int j = lane; j < N; j += 32) p[j] = p[j] / s;
+}
+
+static int launch_linear(const float *x, long ldx, const float *W, const float *bias, float *y, long ldy, long M,
+                         int K, int N, int act, cudaStream_t st)
+{
+    const int vec_in = ((ldx & 3) == 0) && ((K & 3) == 0) && (((uintptr_t)x & 15) == 0);
+    const int vec_out = ((ldy & 3) == 0) && (((uintptr_t)y & 15) == 0);
+    const long mt = ceil_div(M, BM);
+    if (mt > 0x7fffffffL) return SLOIKA_ERR_ARG;
+    dim3 grid((unsigned)mt, (unsigned)ceil_div(N, BN));
+    linear_kernel<<<grid, LIN_THREADS, 0, st>>>(x, ldx, W, bias, y, ldy, M, K, N, act, vec_in, vec_out);
+    SLOIKA_RETURN_LAUNCH_STATUS();
+}
+
+}  // namespace sloika
+
+using namespace sloika;
+
+extern "C" int sloika_linear_fwd(const float *x, long ldx, const float *W, const float *bias, float *y, long ldy,
+                                 long M, int K, int N, int act, void *stream)
+{
+    if (!x || !W || !y || M < 0 || K <= 0 || N <= 0 || ldx < K || ldy < N) return SLOIKA_ERR_ARG;
+    if (!act_known(act)) return SLOIKA_ERR_UNSUPPORTED;
+    if (M == 0) return SLOIKA_OK;
+    return launch_linear(x, ldx, W, bias, y, ldy, M, K, N, act, (cudaStream_t)stream);
+}
+
+extern "C" int sloika_softmax_fwd(const float *x, long ldx, const float *W, const float *bias, float *post,
+                                  long ldp, long M, int K, int N, void *stream)
+{
+    if (!x || !W || !post || M < 0 || K <= 0 || N <= 0 || ldx < K || ldp < N) return SLOIKA_ERR_ARG;
+    if (M == 0) return SLOIKA_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = launch_linear(x, ldx, W, bias, post, ldp, M, K, N, SLOIKA_ACT_LINEAR, st);
+    if (rc != SLOIKA_OK) return rc;
+    const int warps = 8;
+    const long blocks = ceil_div(M, warps);
+    if (blocks > 0x7fffffffL) return SLOIKA_ERR_ARG;
+    softmax_rows_kernel<<<(unsigned)blocks, warps * 32, 0, st>>>(post, ldp, M, N);
+    SLOIKA_RETURN_LAUNCH_STATUS();
+}

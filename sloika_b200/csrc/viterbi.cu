@@ -1,0 +1,223 @@
+// Transducer Viterbi best-path decode, batched: one CTA per read.
+//
+// Reference semantics: decode.prepare_post (sloika/decode.py:21-36) + decode.viterbi (:39-93), called
+// per read from basecall.decode_post (sloika/basecall.py:44-46).  The reference is a Python loop over
+// events with ~15 NumPy calls over the 1024 k-mer states and an int32 traceback matrix.
+//
+// State j in [0,K) is k-mer j (posterior column j+1); column 0 is "stay".  With p = v_{i-1}:
+//     step[j] = max_{a<nb}   p[a*K/nb   + j/nb  ]              (first maximum)
+//     skip[j] = max_{a<nb^2} p[a*K/nb^2 + j/nb^2] - skip_pen   (first maximum)
+//     move[j] = lpost[i][1+j] + max(step, skip)     from: step if step > skip else skip
+//     stay[j] = p[j] + lpost[i][0]                  v[j] = max(move, stay), traceback stay unless move > stay
+// All nb states 'nb*r .. nb*r+nb-1' share the same step predecessor set (index r) so thread r owns
+// them: the step max stays in registers, the skip max is nb^2 conflict-free shared loads, v_{i-1} and
+// v_i ping-pong in shared memory (one __syncthreads per event).  Only 1 + nb + nb^2 traceback outcomes
+// exist per state, so the traceback is ONE BYTE per state per event (code 0 = stay, 1+a = step from a,
+// 1+nb+a = skip from a) in global memory -- 1 KB/event instead of the reference's 4 KB -- written as
+// coalesced words.  Arithmetic is float32 add/max in the reference's order, so given identical
+// log-posteriors scores and paths are bit-identical.
+//
+// HBM-bound: 4*(K+1) bytes of posterior read + K bytes of traceback written per event.
+#include "common.cuh"
+
+namespace sloika {
+
+constexpr float VIT_ETA = 1e-10f;
+
+// lpost = log((min_prob + (1 - min_prob) * post) + 1e-10), each operation rounded to float32 exactly as
+// NumPy evaluates decode.py:36 and :56 (no FMA contraction).
+__device__ __forceinline__ float to_lpost(float v, int mode, float c0, float c1)
+{
+    if (mode == SLOIKA_VIT_LOG) return v;
+    const float p = __fadd_rn(c0, __fmul_rn(c1, v));
+    return logf(__fadd_rn(p, VIT_ETA));
+}
+
+template <int NB>
+__global__ void __launch_bounds__(256)
+viterbi_kernel(const float *__restrict__ post, long ld_t, long ld_b, const int32_t *__restrict__ lengths, int T, int B,
+               int K, float skip_pen, float c0, float c1, int mode, uint8_t *__restrict__ tb, int32_t *__restrict__ path_out,
+               int32_t *__restrict__ path_len, float *__restrict__ score_out)
+{
+    constexpr int NS = NB * NB;
+    extern __shared__ __align__(16) float vbuf[];       // [2][K]
+    __shared__ float red_v[32];
+    __shared__ int red_i[32];
+    __shared__ int s_best;
+
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int nev = lengths ? min(lengths[b], T) : T;
+    if (nev < 1) {
+        if (tid == 0) { path_len[b] = 0; score_out[b] = 0.0f; }
+        return;
+    }
+    const int rstep = K / NB, rskip = K / NS;
+    const float *pb = post + (long)b * ld_b;
+    uint8_t *tbb = tb + (size_t)b * (size_t)T * (size_t)K;
+
+    // v_0 = lpost[0][1:]   (decode.py:57)
+    for (int j = tid; j < K; j += nthr) vbuf[j] = to_lpost(__ldg(pb + 1 + j), mode, c0, c1);
+    __syncthreads();
+
+    int cur = 0;
+    for (int i = 1; i < nev; i++) {
+        const float *row = pb + (long)i * ld_t;
+        const float *p = vbuf + cur * K;
+        float *vn = vbuf + (cur ^ 1) * K;
+        const float lp0 = to_lpost(__ldg(row), mode, c0, c1);
+        for (int r = tid; r < rstep; r += nthr) {
+            float lp[NB];
+#pragma unroll
+            for (int c = 0; c < NB; c++) lp[c] = __ldg(row + 1 + NB * r + c);
+            // step: first maximum over a of p[a*rstep + r]
+            float ss = p[r];
+            int as = 0;
+#pragma unroll
+            for (int a = 1; a < NB; a++) {
+                const float c = p[a * rstep + r];
+                if (c > ss) { ss = c; as = a; }
+            }
+            // skip: first maximum over a of p[a*rskip + q], q = r / NB
+            const int q = r / NB;
+            float sk = p[q];
+            int ak = 0;
+#pragma unroll
+            for (int a = 1; a < NS; a++) {
+                const float c = p[a * rskip + q];
+                if (c > sk) { sk = c; ak = a; }
+            }
+            sk = __fsub_rn(sk, skip_pen);
+            const bool use_step = ss > sk;                       // tie -> skip (decode.py:76)
+            const float best = use_step ? ss : sk;
+            const unsigned code = use_step ? (1u + as) : (1u + NB + ak);
+            unsigned packed = 0;
+#pragma unroll
+            for (int c = 0; c < NB; c++) {
+                const int j = NB * r + c;
+                const float move = __fadd_rn(to_lpost(lp[c], mode, c0, c1), best);
+                const float stay = __fadd_rn(p[j], lp0);
+                const bool mv = move > stay;                     // tie -> stay (decode.py:81)
+                vn[j] = mv ? move : stay;
+                const unsigned cd = mv ? code : 0u;
+                if (NB == 4) packed |= cd << (8 * c);
+                else tbb[(size_t)i * K + j] = (uint8_t)cd;
+            }
+            if (NB == 4) reinterpret_cast<unsigned *>(tbb + (size_t)i * K)[r] = packed;
+        }
+        cur ^= 1;
+        __syncthreads();
+    }
+
+    // ---- argmax of v_T (first maximum) ----
+    const float *v = vbuf + cur * K;
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int j = tid; j < K; j += nthr) {
+        const float c = v[j];
+        if (c > bv || (c == bv && j < bi)) { bv = c; bi = j; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if ((tid & 31) == 0) { red_v[tid >> 5] = bv; red_i[tid >> 5] = bi; }
+    __syncthreads();
+    if (tid == 0) {
+        const int nw = (nthr + 31) >> 5;
+        for (int w = 1; w < nw; w++)
+            if (red_v[w] > bv || (red_v[w] == bv && red_i[w] < bi)) { bv = red_v[w]; bi = red_i[w]; }
+        score_out[b] = bv;
+        // ---- backtrace (decode.py:84-91): states with stays removed, written right-aligned ----
+        int32_t *out = path_out + (size_t)b * T;
+        int pos = nev - 1;
+        int state = bi;
+        out[pos] = state;
+        for (int i = nev - 1; i > 0; i--) {
+            const unsigned cd = tbb[(size_t)i * K + state];
+            if (cd != 0) {
+                if (cd <= (unsigned)NB) state = (int)(cd - 1) * rstep + state / NB;
+                else state = (int)(cd - 1 - NB) * rskip + state / NS;
+                out[--pos] = state;
+            }
+        }
+        path_len[b] = nev - pos;
+        s_best = pos;
+    }
+    __syncthreads();
+    // ---- left-align the path ----
+    const int off = s_best;
+    const int n = nev - off;
+    if (off > 0) {
+        int32_t *out = path_out + (size_t)b * T;
+        for (int base = 0; base < n; base += nthr) {
+            const int idx = base + tid;
+            int32_t val = 0;
+            if (idx < n) val = out[off + idx];
+            __syncthreads();
+            if (idx < n) out[idx] = val;
+            __syncthreads();
+        }
+    }
+}
+
+static bool ipow_ok(int nbase, int klen, long *K)
+{
+    long k = 1;
+    for (int i = 0; i < klen; i++) {
+        k *= nbase;
+        if (k > (1L << 20)) return false;
+    }
+    *K = k;
+    return true;
+}
+
+}  // namespace sloika
+
+using namespace sloika;
+
+extern "C" size_t sloika_viterbi_workspace_bytes(int T, int B, int nbase, int klen)
+{
+    long K;
+    if (T < 0 || B < 0 || nbase < 2 || klen < 1 || !ipow_ok(nbase, klen, &K)) return 0;
+    return (size_t)T * (size_t)B * (size_t)K;
+}
+
+extern "C" int sloika_viterbi_fwd(const float *post, long ld_t, long ld_b, const int32_t *lengths, int T, int B,
+                                  int nbase, int klen, double skip_pen, double min_prob, int mode, void *tb_ws,
+                                  size_t ws_bytes, int32_t *path_out, int32_t *path_len, float *score_out,
+                                  void *stream)
+{
+    if (!post || !path_out || !path_len || !score_out || T < 0 || B <= 0) return SLOIKA_ERR_ARG;
+    if (klen < 3) return SLOIKA_ERR_ARG;                 // decode.py:50
+    long K;
+    if (nbase < 2 || !ipow_ok(nbase, klen, &K)) return SLOIKA_ERR_ARG;
+    if (mode != SLOIKA_VIT_POST && mode != SLOIKA_VIT_LOG) return SLOIKA_ERR_ARG;
+    if (nbase != 4 && nbase != 5) return SLOIKA_ERR_UNSUPPORTED;
+    if (2 * K * sizeof(float) > 200 * 1024) return SLOIKA_ERR_UNSUPPORTED;
+    if (!tb_ws || ws_bytes < sloika_viterbi_workspace_bytes(T, B, nbase, klen)) return SLOIKA_ERR_WORKSPACE;
+    if (T == 0) return SLOIKA_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t smem = 2 * (size_t)K * sizeof(float);
+    // python-float constants enter the float32 arithmetic exactly as NumPy casts them (decode.py:36, :72)
+    const float c0 = (float)min_prob, c1 = (float)(1.0 - min_prob), sp = (float)skip_pen;
+    long threads = K / nbase;
+    threads = threads > 256 ? 256 : (threads < 32 ? 32 : ceil_div(threads, 32) * 32);
+    cudaError_t err;
+    if (nbase == 4) {
+        err = cudaFuncSetAttribute(viterbi_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return (int)err;
+        viterbi_kernel<4><<<B, (unsigned)threads, smem, st>>>(post, ld_t, ld_b, lengths, T, B, (int)K, sp,
+                                                             c0, c1, mode, (uint8_t *)tb_ws, path_out, path_len,
+                                                             score_out);
+    } else {
+        err = cudaFuncSetAttribute(viterbi_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return (int)err;
+        viterbi_kernel<5><<<B, (unsigned)threads, smem, st>>>(post, ld_t, ld_b, lengths, T, B, (int)K, sp,
+                                                             c0, c1, mode, (uint8_t *)tb_ws, path_out, path_len,
+                                                             score_out);
+    }
+    SLOIKA_RETURN_LAUNCH_STATUS();
+}

@@ -1,0 +1,107 @@
+"""Transducer Viterbi decode on the B200 (reference `sloika/decode.py:21-93`).
+
+`prepare_post` and `viterbi` keep the reference signatures so `basecall.decode_post` reads the same;
+`viterbi_batch` is the batched device entry (one CTA per read) that the GPU basecall path uses --
+it fuses `prepare_post` (the min_prob floor) and the `log(post + 1e-10)` of `decode.py:56` into the
+kernel and never materialises the int32 traceback of the reference.
+
+All dynamic programming happens in `sloika_viterbi_fwd` (csrc/viterbi.cu); there is no host
+implementation here.  Arithmetic is float32 (the dtype of real posteriors); float64 input, which the
+reference would decode in float64, is cast to float32.
+"""
+import numpy as np
+
+from sloika_b200 import cabi
+from sloika_b200 import variables as sv
+
+_ETA = 1e-10
+
+
+def prepare_post(post, min_prob=1e-5, drop_bad=False):
+    """ Sanitised posterior matrix for decoding (`decode.py:21-36`)
+
+    Host/NumPy or torch input `[T, 1, S]`; returns `[T, S]` (`[T', S-1]` renormalised when
+    `drop_bad`).  The device basecall path does not call this: `viterbi_batch(min_prob=...)` applies
+    the same floor inside the kernel.
+    """
+    is_np = isinstance(post, np.ndarray)
+    post = post.squeeze(1)
+    if drop_bad:
+        keep = post.argmax(1) > 0
+        post = post[keep][:, 1:]
+        post = post / post.sum(1, keepdims=True) if is_np else post / post.sum(1, keepdim=True)
+    return min_prob + (1.0 - min_prob) * post
+
+
+def _as_device(post, device=None):
+    import torch
+    if isinstance(post, np.ndarray):
+        if not torch.cuda.is_available():
+            raise cabi.SloikaB200Error("no CUDA device: the B200 decode has no CPU fallback")
+        dev = device or torch.device('cuda', torch.cuda.current_device())
+        return torch.from_numpy(np.ascontiguousarray(post, dtype=np.float32)).to(dev)
+    if post.dtype != torch.float32:
+        post = post.float()
+    return post
+
+
+def viterbi_batch(post, lengths=None, klen=5, skip_pen=0.0, min_prob=1e-5, nbase=4, log=False,
+                  return_device=False):
+    """Best paths of a batch of reads.
+
+    :param post: `[T, B, S]` float32 posteriors (torch CUDA tensor, any row strides, or ndarray);
+        raw network output -- the min_prob floor of `prepare_post` is applied in the kernel
+    :param lengths: events per read (None = T for all)
+    :param min_prob: floor; pass 0.0 if `post` already went through `prepare_post`
+    :param log: `post` holds log-probabilities (`decode.py:56` `log=True`); min_prob is ignored
+
+    :returns: (scores float32[B], list of B lists of k-mer states) -- or the device tensors
+        `(scores, paths[B, T], path_len[B])` when `return_device`
+    """
+    import torch
+    lib = cabi.load()
+    post = _as_device(post)
+    assert post.dim() == 3, "post must be [time, batch, state]"
+    T, B, S = post.shape
+    assert klen >= 3, "Kmer not long enough to apply Viterbi with skips"
+    assert sv.nstate(klen, transducer=True, nbase=nbase) == S
+    if post.stride(2) != 1:
+        post = post.contiguous()
+    dev = post.device
+    lens = None
+    if lengths is not None:
+        lens = torch.as_tensor(lengths, dtype=torch.int32, device=dev).contiguous()
+    with torch.cuda.device(dev):
+        nbytes = lib.sloika_viterbi_workspace_bytes(T, B, nbase, klen)
+        tb = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=dev)
+        paths = torch.empty((B, max(T, 1)), dtype=torch.int32, device=dev)
+        plen = torch.empty(B, dtype=torch.int32, device=dev)
+        score = torch.empty(B, dtype=torch.float32, device=dev)
+        cabi.check(lib.sloika_viterbi_fwd(
+            cabi.ptr(post), post.stride(0), post.stride(1), cabi.ptr(lens), T, B, nbase, klen,
+            float(skip_pen), float(min_prob), cabi.SLOIKA_VIT_LOG if log else cabi.SLOIKA_VIT_POST,
+            cabi.ptr(tb), nbytes, cabi.ptr(paths), cabi.ptr(plen), cabi.ptr(score),
+            cabi.stream_ptr(dev)), 'sloika_viterbi_fwd')
+    if return_device:
+        return score, paths, plen
+    score_h = score.cpu().numpy()
+    plen_h = plen.cpu().numpy()
+    paths_h = paths.cpu().numpy()
+    return score_h, [paths_h[b, :plen_h[b]].tolist() for b in range(B)]
+
+
+def viterbi(post, klen, skip_pen=0.0, log=False, nbase=4):
+    """  Viterbi decoding of a kmer transducer (`decode.py:39-93`)
+
+    :param post: A 2d array `[events, states]`, already through `prepare_post`
+    :param klen: Length of kmer
+    :param log: post array is in log space
+
+    :returns: (score, list of k-mer states)
+    """
+    if isinstance(post, np.ndarray):
+        post3 = post[:, None, :]
+    else:
+        post3 = post.unsqueeze(1)
+    score, paths = viterbi_batch(post3, None, klen=klen, skip_pen=skip_pen, min_prob=0.0, nbase=nbase, log=log)
+    return score[0], paths[0]

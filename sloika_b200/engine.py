@@ -1,0 +1,219 @@
+"""Execution of a layer tree on one B200: device activations and the per-layer kernel launches.
+
+This replaces what Theano does for the reference (`Layer.compile`, `sloika/layers.py:34-36`:
+`th.function([x], self.run(x))`): `CompiledNetwork` is the `calc_post` callable of
+`sloika/basecall.py:12-23, 119`, and the `run_*` functions are the bodies of the layers' `run`
+methods.  Every operator goes through the C ABI (`cabi`), on the current torch stream; torch is
+used for device memory, streams and nothing else.
+"""
+import ctypes
+
+import numpy as np
+
+from sloika_b200 import cabi
+from sloika_b200.activation import code_of
+from sloika_b200.config import sloika_dtype
+from sloika_b200.conv import output_length
+
+
+class Act(object):
+    """A device activation `[T, B, F]` (float32), possibly a column slice of a wider buffer.
+
+    data     torch CUDA tensor of shape [T, B, F]; rows (t, b) are `ld` floats apart
+    lengths  optional int32 CUDA tensor [B]: valid steps per sequence (ragged whole-read batch)
+    reverse  time direction flag toggled by `Reverse` (nothing is ever flipped in memory)
+    """
+
+    def __init__(self, data, lengths=None, reverse=False):
+        assert data.dim() == 3 and data.stride(2) == 1 and data.stride(0) == data.shape[1] * data.stride(1)
+        self.data = data
+        self.lengths = lengths
+        self.reverse = reverse
+
+    @property
+    def T(self):
+        return self.data.shape[0]
+
+    @property
+    def B(self):
+        return self.data.shape[1]
+
+    @property
+    def F(self):
+        return self.data.shape[2]
+
+    @property
+    def ld(self):
+        return self.data.stride(1)
+
+    @property
+    def device(self):
+        return self.data.device
+
+    def flipped(self):
+        return Act(self.data, self.lengths, not self.reverse)
+
+    def like(self, data, lengths='same'):
+        return Act(data, self.lengths if lengths == 'same' else lengths, self.reverse)
+
+
+def _empty(shape, device):
+    import torch
+    return torch.empty(shape, dtype=torch.float32, device=device)
+
+
+def _out_buffer(act, T, F, out):
+    """Output activation: a fresh dense buffer, or the caller's column slice (Parallel)."""
+    if out is not None:
+        assert out.shape == (T, act.B, F)
+        return out
+    return _empty((T, act.B, F), act.device)
+
+
+def run_convolution(layer, act, out=None):
+    lib = cabi.load()
+    assert act.F == layer.insize, "Convolution input has {} features, expected {}".format(act.F, layer.insize)
+    if act.ld != act.F:
+        raise ValueError("Convolution needs a dense input")
+    Tout = output_length(act.T, layer.winlen, layer.stride, layer.padding)
+    y = _out_buffer(act, Tout, layer.size, out)
+    dev = act.device
+    cabi.check(lib.sloika_conv1d_fwd(
+        cabi.ptr(act.data), cabi.ptr(layer.W.device(dev)), cabi.ptr(layer.b.device(dev)), cabi.ptr(y),
+        y.stride(1), cabi.ptr(act.lengths), act.T, act.B, layer.insize, layer.size, layer.winlen,
+        layer.stride, layer.padding[0], layer.padding[1], code_of(layer.fun), cabi.stream_ptr(dev)),
+        'sloika_conv1d_fwd')
+    lengths = None
+    if act.lengths is not None:
+        # per-read output length: each read is padded/convolved on its own (conv.py:66-111)
+        span = act.lengths + (layer.padding[0] + layer.padding[1] - layer.winlen)
+        lengths = (span.clamp(min=-layer.stride) // layer.stride + 1).clamp(min=0).to(act.lengths.dtype)
+    return act.like(y, lengths)
+
+
+def run_feedforward(layer, act, out=None):
+    lib = cabi.load()
+    assert act.F == layer.insize
+    y = _out_buffer(act, act.T, layer.size, out)
+    dev = act.device
+    cabi.check(lib.sloika_linear_fwd(
+        cabi.ptr(act.data), act.ld, cabi.ptr(layer.W.device(dev)), cabi.ptr(layer.b.device(dev)),
+        cabi.ptr(y), y.stride(1), act.T * act.B, layer.insize, layer.size, code_of(layer.fun),
+        cabi.stream_ptr(dev)), 'sloika_linear_fwd')
+    return act.like(y)
+
+
+def run_softmax(layer, act, out=None):
+    lib = cabi.load()
+    assert act.F == layer.insize
+    y = _out_buffer(act, act.T, layer.size, out)
+    dev = act.device
+    cabi.check(lib.sloika_softmax_fwd(
+        cabi.ptr(act.data), act.ld, cabi.ptr(layer.W.device(dev)), cabi.ptr(layer.b.device(dev)),
+        cabi.ptr(y), y.stride(1), act.T * act.B, layer.insize, layer.size, cabi.stream_ptr(dev)),
+        'sloika_softmax_fwd')
+    return act.like(y)
+
+
+def run_gru(layer, act, out=None):
+    import torch
+    lib = cabi.load()
+    assert act.F == layer.insize
+    y = _out_buffer(act, act.T, layer.size, out)
+    dev = act.device
+    nbytes = lib.sloika_gru_workspace_bytes(act.T, act.B, layer.size)
+    ws = torch.empty((max(nbytes, 4) + 3) // 4, dtype=torch.float32, device=dev)
+    cabi.check(lib.sloika_gru_fwd(
+        cabi.ptr(act.data), act.ld, cabi.ptr(layer.iW.device(dev)), cabi.ptr(layer.sW.device(dev)),
+        cabi.ptr(layer.sW2.device(dev)), cabi.ptr(layer.b.device(dev)), cabi.ptr(y), y.stride(1),
+        cabi.ptr(ws), nbytes, cabi.ptr(act.lengths), act.T, act.B, layer.insize, layer.size,
+        1 if act.reverse else 0, code_of(layer.fun), code_of(layer.gatefun), cabi.stream_ptr(dev)),
+        'sloika_gru_fwd')
+    return act.like(y)
+
+
+_SLICE_WRITERS = {}
+
+
+def run_parallel(layer, act, out=None):
+    """Parallel.run (`layers.py:1486-1487`): sub-layers write their column slice of one buffer."""
+    from sloika_b200 import layers as L
+    y = _out_buffer(act, act.T, layer.size, out)
+    col = 0
+    result = None
+    for sub in layer.layers:
+        view = y[:, :, col:col + sub.size]
+        inner, flips = sub, 0
+        while isinstance(inner, L.Reverse):
+            inner, flips = inner.layer, flips + 1
+        src = act.flipped() if flips % 2 else act
+        if isinstance(inner, L.Gru):
+            res = run_gru(inner, src, out=view)
+        elif isinstance(inner, L.FeedForward):
+            res = run_feedforward(inner, src, out=view)
+        elif isinstance(inner, L.Softmax):
+            res = run_softmax(inner, src, out=view)
+        else:
+            res = sub.run(act)                  # nested containers: run, then place
+            view.copy_(res.data)
+            res = act.like(view, res.lengths)
+            flips = 0
+        if result is None:
+            result = res.flipped() if flips % 2 else res
+        col += sub.size
+    return Act(y, result.lengths, act.reverse)
+
+
+class CompiledNetwork(object):
+    """`calc_post`: the callable `Layer.compile()` returns (`layers.py:34-36`, used at
+    `basecall.py:119`).
+
+    NumPy in -> NumPy out (drop-in for the reference: float32 `[T, B, F]` C-contiguous, anything
+    else raises TypeError like a Theano function does); torch CUDA tensor in -> torch CUDA tensor
+    out (device path, no host copies).  `lengths` enables the ragged whole-read batch.
+    """
+
+    def __init__(self, network, device=None):
+        self.network = network
+        self._device = device
+
+    @property
+    def device(self):
+        import torch
+        if self._device is None:
+            if not torch.cuda.is_available():
+                raise cabi.SloikaB200Error("no CUDA device: the B200 path has no CPU fallback")
+            self._device = torch.device('cuda', torch.cuda.current_device())
+        return self._device
+
+    def to(self, device):
+        import torch
+        self._device = torch.device(device)
+        return self
+
+    def forward_device(self, x, lengths=None):
+        """x: float32 CUDA tensor [T, B, F] (dense); lengths: optional int32 CUDA tensor [B]."""
+        import torch
+        cabi.load()
+        if x.dtype != torch.float32 or x.dim() != 3:
+            raise TypeError("calc_post expects a float32 [time, batch, feature] tensor")
+        x = x.contiguous()
+        if lengths is not None:
+            lengths = lengths.to(device=x.device, dtype=torch.int32).contiguous()
+        with torch.cuda.device(x.device):
+            out = self.network.run(Act(x, lengths))
+        return out
+
+    def __call__(self, inMat, lengths=None):
+        import torch
+        if isinstance(inMat, np.ndarray):
+            if inMat.dtype != np.dtype(sloika_dtype) or inMat.ndim != 3:
+                raise TypeError("calc_post expects a float32 ndarray of shape [time, batch, feature], "
+                                "got {} {}".format(inMat.dtype, inMat.shape))
+            dev = self.device
+            x = torch.from_numpy(np.ascontiguousarray(inMat)).to(dev)
+            lens = None if lengths is None else torch.as_tensor(np.asarray(lengths), dtype=torch.int32, device=dev)
+            out = self.forward_device(x, lens)
+            return out.data.contiguous().cpu().numpy()
+        out = self.forward_device(inMat, lengths)
+        return out.data
