@@ -1,0 +1,384 @@
+#!/usr/bin/env python3
+"""Benchmark of the raw basecall hot path (forward + Viterbi) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload raw_rgrgr|raw_rGr|bigger_raw_gru|pretrained_like]
+    python bench.py --impl reference ...        # the CPU arm: oracle port on the host cores
+
+A step = one pass of the hot path over one batch of synthetic raw-signal chunks
+(x ~ N(0,1) float32 [4000, 1024, 1] per GPU, seeded; weights truncated-normal sd 0.5, seeded):
+conv -> GRU stack (projection + recurrence per layer) -> softmax -> Viterbi incl. backtrace.
+metric = raw samples/s basecalled, whole job over all ranks (read sharding, weak scaling: every rank
+owns its own 1024 chunks; no data-path collective).  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "raw_samples_per_s_basecalled_fwd_viterbi"
+UNIT = "samples/s"
+CHUNK_LEN = 4000
+BATCH_PER_GPU = 1024
+WEIGHT_SEED = 0xdeadbeef & 0x7fffffff
+INPUT_SEED = 20261017
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--workload', default='raw_rgrgr')
+    ap.add_argument('--batch', type=int, default=BATCH_PER_GPU, help='chunks per GPU')
+    ap.add_argument('--chunk', type=int, default=CHUNK_LEN, help='raw samples per chunk')
+    ap.add_argument('--cpu-sample-chunks', type=int, default=32, help='chunks in the bounded CPU-baseline sample')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    return ap.parse_args()
+
+
+def build_network(workload):
+    from sloika_b200 import zoo
+    np.random.seed(WEIGHT_SEED)
+    return getattr(zoo, workload)()
+
+
+def stride_of(net):
+    return net.layers[0].stride
+
+
+def flops_per_sample(net):
+    """Algorithmic FLOP per raw sample from the layer shapes."""
+    from sloika_b200 import layers as L
+
+    def per_step(layer):
+        if isinstance(layer, L.Convolution):
+            return 2 * layer.insize * layer.winlen * layer.size
+        if isinstance(layer, L.Gru):
+            return 2 * (3 * layer.size * layer.insize + 3 * layer.size * layer.size)
+        if isinstance(layer, (L.FeedForward, L.Softmax)):
+            return 2 * layer.insize * layer.size
+        if isinstance(layer, L.Reverse):
+            return per_step(layer.layer)
+        return sum(per_step(sub) for sub in layer.layers)
+    return per_step(net) / float(stride_of(net))
+
+
+# ---------------------------------------------------------------------------------------------
+# algorithmic HBM bytes per raw sample of each kernel class (every activation
+# written once / read once, fp32, weights resident, vI not materialised, uint8 traceback)
+def algorithmic_bytes_per_sample(net):
+    from sloika_b200 import layers as L
+    s = float(stride_of(net))
+    out = {}
+
+    def add(name, nbytes):
+        out[name] = out.get(name, 0.0) + nbytes / s
+
+    def walk(layer, first=False):
+        if isinstance(layer, L.Convolution):
+            out['conv1d'] = 4.0 * layer.insize + 4.0 * layer.size / s
+        elif isinstance(layer, L.Gru):
+            add('gru_layer', 4.0 * layer.insize + 4.0 * layer.size)
+        elif isinstance(layer, L.FeedForward):
+            add('feedforward', 4.0 * layer.insize + 4.0 * layer.size)
+        elif isinstance(layer, L.Softmax):
+            add('softmax', 4.0 * layer.insize + 4.0 * layer.size)
+            add('viterbi', 4.0 * layer.size + (layer.size - 1))
+        elif isinstance(layer, L.Reverse):
+            walk(layer.layer)
+        else:
+            for sub in layer.layers:
+                walk(sub)
+    walk(net)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    FIELDS = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+              'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+              'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu_index), '--query-gpu=' + self.FIELDS,
+                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(',')]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax.append(float(parts[2]))
+                power.append(float(parts[3]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------
+def cpu_reference_step(desc, x, klen=5, min_prob=1e-5, skip=0.0, pool=None):
+    """One bounded CPU sample: oracle forward (NumPy/BLAS, all host threads) + the reference-semantics
+    NumPy Viterbi per chunk, chunks spread over `pool` processes (mirrors --jobs, iterators.py:343-351)."""
+    from oracle import forward_ref
+    post = forward_ref.run(desc, x)
+    cols = [np.ascontiguousarray(post[:, b:b + 1]) for b in range(post.shape[1])]
+    args = [(c, klen, min_prob, skip) for c in cols]
+    if pool is None:
+        res = [_decode_one(a) for a in args]
+    else:
+        res = pool.map(_decode_one, args)
+    return res
+
+
+def _decode_one(arg):
+    from oracle import decode_ref
+    post, klen, min_prob, skip = arg
+    return decode_ref.decode_post(post, klen, min_prob, skip=skip)
+
+
+def time_cpu_reference(net, chunk, nchunks, steps, warmup):
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    desc = net.json(params=True)
+    rng = np.random.default_rng(INPUT_SEED)
+    x = rng.standard_normal((chunk, nchunks, 1)).astype(np.float32)
+    ctx = mp.get_context('fork')
+    with ctx.Pool(min(cores, nchunks)) as pool:
+        for _ in range(warmup):
+            cpu_reference_step(desc, x, pool=pool)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            cpu_reference_step(desc, x, pool=pool)
+        dt = time.perf_counter() - t0
+    return chunk * nchunks * steps / dt, dt / steps, cores
+
+
+# ---------------------------------------------------------------------------------------------
+def run_reference_arm(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    net = build_network(args.workload)
+    nchunks = args.cpu_sample_chunks
+    value, sec_per_step, cores = time_cpu_reference(net, args.chunk, nchunks, args.steps, args.warmup)
+    sample = "{} chunks x {} samples per step (of {} per GPU), oracle NumPy forward + NumPy Viterbi over {} processes".format(
+        nchunks, args.chunk, args.batch, min(cores, nchunks))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args), "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "Theano 0.8.2 is not installable in this image; the CPU arm is the reference-semantics port (oracle/)",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(args):
+    return "{}: {} chunks x {} raw samples per GPU, fwd+Viterbi".format(args.workload, args.batch, args.chunk)
+
+
+def run_b200_arm(args):
+    import torch
+    import torch.distributed as dist
+    from sloika_b200 import basecall, cabi, decode, engine
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    cabi.load()
+
+    net = build_network(args.workload)
+    calc_post = net.compile().to(dev)
+    T, B = args.chunk, args.batch
+    gen = torch.Generator().manual_seed(INPUT_SEED + rank)
+    x_host = torch.randn((T, B, 1), generator=gen, dtype=torch.float32).pin_memory()
+    x_dev = x_host.to(dev)
+    samples_per_step = T * B
+
+    def step_device():
+        out = calc_post.forward_device(x_dev)
+        return decode.viterbi_batch(out.data, None, klen=5, skip_pen=0.0, min_prob=1e-5, return_device=True)
+
+    def step_e2e():
+        return basecall.basecall_chunks(x_host, kmer_len=5, min_prob=1e-5, skip=0.0, network=calc_post)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(step_fn, steps):
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        wall0 = time.perf_counter()
+        start.record()
+        for _ in range(steps):
+            res = step_fn()
+        end.record()
+        barrier()
+        wall = (time.perf_counter() - wall0) * 1e3
+        return start.elapsed_time(end), wall, res
+
+    # ---- warm-up ----
+    for _ in range(max(args.warmup, 3)):
+        res = step_device()
+    barrier()
+
+    # ---- device-resident timing (value) with per-kernel events ----
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    engine.TIMER.reset()
+    engine.TIMER.enabled = True
+    ms_dev, _, res = timed(step_device, args.steps)
+    engine.TIMER.enabled = False
+    launches = engine.TIMER.launches
+    kernel_ms = engine.TIMER.totals_ms()
+    ms_dev = max_over_ranks(ms_dev)
+
+    # ---- end-to-end timing through the host-buffer API (e2e): H2D + D2H inside, wall clock on host ----
+    for _ in range(2):
+        step_e2e()
+    _, wall_e2e, res_e2e = timed(step_e2e, args.steps)
+    wall_e2e = max_over_ranks(wall_e2e)
+    clocks = sampler.stop() if sampler else None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    value = samples_per_step * world * args.steps / (ms_dev * 1e-3)
+    e2e_value = samples_per_step * world * args.steps / (wall_e2e * 1e-3)
+    scores, paths, plen = res_e2e
+    d2h = scores.nbytes + paths.nbytes + plen.nbytes
+
+    # ---- roofline of the dominant kernel ----
+    peaks = {}
+    peaks_src = "fallback"
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as fh:
+            peaks = json.load(fh)
+        peaks_src = "measured"
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
+    alg = algorithmic_bytes_per_sample(net)
+    # a GRU layer's algorithmic bytes (x read once, h written once) are charged to its recurrence kernel;
+    # the projection kernel's vI round trip is extra (non-algorithmic) traffic by SURVEY section 8d
+    alg_by_kernel = {'conv1d': alg.get('conv1d', 0.0), 'gru_recurrence': alg.get('gru_layer', 0.0),
+                     'gru_projection': 0.0, 'feedforward': alg.get('feedforward', 0.0),
+                     'softmax': alg.get('softmax', 0.0), 'viterbi': alg.get('viterbi', 0.0)}
+    breakdown = {}
+    for name, (ms, calls) in kernel_ms.items():
+        nbytes = alg_by_kernel.get(name, 0.0) * samples_per_step * args.steps
+        breakdown[name] = {"ms_per_step": ms / args.steps, "calls_per_step": calls / args.steps,
+                           "algorithmic_GBps": (nbytes / (ms * 1e-3) / 1e9) if ms > 0 else None}
+    dominant = max(kernel_ms, key=lambda k: kernel_ms[k][0])
+    dom_ms, dom_calls = kernel_ms[dominant]
+    dom_bytes_per_launch = alg_by_kernel.get(dominant, 0.0) * samples_per_step * args.steps / dom_calls
+    achieved = dom_bytes_per_launch / (dom_ms / dom_calls * 1e-3) / 1e9
+    roofline = {"kernel": dominant, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                "frac": achieved / hbm_peak, "traffic": None, "peak_source": peaks_src,
+                "algorithmic_bytes_per_launch": dom_bytes_per_launch,
+                "avg_launch_ms": dom_ms / dom_calls, "share_of_step": dom_ms / (ms_dev if world == 1 else sum(v[0] for v in kernel_ms.values()))}
+    total_alg = sum(alg.values())
+    paper = min(hbm_peak * 1e9 / total_alg, float(peaks.get('bf16_tflops_sustained', 1400.0)) * 1e12 / flops_per_sample(net))
+
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        nchunks = args.cpu_sample_chunks
+        cpu_value, sec_per_step, cores = time_cpu_reference(net, T, nchunks, steps=1, warmup=0)
+        cpu_baseline = {"value": cpu_value, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": "{} chunks x {} samples once: oracle NumPy forward (BLAS threads) + NumPy Viterbi over {} processes, {:.1f} s".format(
+                            nchunks, T, min(cores, nchunks), sec_per_step)}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args), "chunks_per_gpu": B, "chunk_len": T, "stride": stride_of(net),
+                   "sharding": "reads x{} (no collective)".format(world),
+                   "l2": "working set per step (posteriors {:.2f} GB) exceeds L2; no flush needed".format(
+                       4.0 * net.size * (T // stride_of(net)) * B / 1e9)},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(x_host.numel() * 4),
+                "d2h_bytes_per_step": int(d2h), "ms_per_step": wall_e2e / args.steps},
+        "gpu_launches": launches,
+        "roofline": roofline,
+        "kernels": breakdown,
+        "paper_roofline_samples_per_s": paper,
+        "frac_of_paper_roofline": value / world / paper,
+        "cpu_baseline": cpu_baseline,
+        "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == 'reference':
+        run_reference_arm(args)
+    else:
+        run_b200_arm(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -77,6 +77,26 @@ def basecall_signals(signals, kmer_len=5, min_prob=1e-5, skip=0.0, nbase=4, netw
     return list(zip(score.tolist(), paths))
 
 
+def basecall_chunks(x_host, kmer_len=5, min_prob=1e-5, skip=0.0, nbase=4, network=None):
+    """Forward + Viterbi for a dense batch of equal-length chunks held in HOST memory.
+
+    :param x_host: float32 torch CPU tensor `[T, B]` or `[T, B, 1]` (pinned memory makes the copy
+        asynchronous); the synthetic-chunk shape of the throughput configs (4000 x 1024)
+    :returns: (scores float32[B], paths int32[B, T'], path_len int32[B]) as NumPy arrays on the host
+    """
+    import torch
+    net = network if network is not None else calc_post
+    if net is None:
+        raise RuntimeError("init_worker() has not been called")
+    if x_host.dim() == 2:
+        x_host = x_host.unsqueeze(2)
+    x = x_host.to(net.device, non_blocking=True)
+    out = net.forward_device(x)
+    score, paths, plen = decode.viterbi_batch(out.data, None, klen=kmer_len, skip_pen=skip, min_prob=min_prob,
+                                              nbase=nbase, return_device=True)
+    return score.cpu().numpy(), paths.cpu().numpy(), plen.cpu().numpy()
+
+
 def _read_raw(fast5_file_name):
     from sloika_b200.fast5 import Fast5
     with Fast5(fast5_file_name) as f5:

@@ -65,8 +65,11 @@ def viterbi_batch(post, lengths=None, klen=5, skip_pen=0.0, min_prob=1e-5, nbase
     T, B, S = post.shape
     assert klen >= 3, "Kmer not long enough to apply Viterbi with skips"
     assert sv.nstate(klen, transducer=True, nbase=nbase) == S
-    if post.stride(2) != 1:
+    if post.stride(2) != 1 and S > 1:
         post = post.contiguous()
+    # strides of size-1 dimensions are arbitrary in torch: only pass strides that are stepped over
+    ld_t = post.stride(0) if T > 1 else B * S
+    ld_b = post.stride(1) if B > 1 else S
     dev = post.device
     lens = None
     if lengths is not None:
@@ -77,11 +80,12 @@ def viterbi_batch(post, lengths=None, klen=5, skip_pen=0.0, min_prob=1e-5, nbase
         paths = torch.empty((B, max(T, 1)), dtype=torch.int32, device=dev)
         plen = torch.empty(B, dtype=torch.int32, device=dev)
         score = torch.empty(B, dtype=torch.float32, device=dev)
-        cabi.check(lib.sloika_viterbi_fwd(
-            cabi.ptr(post), post.stride(0), post.stride(1), cabi.ptr(lens), T, B, nbase, klen,
-            float(skip_pen), float(min_prob), cabi.SLOIKA_VIT_LOG if log else cabi.SLOIKA_VIT_POST,
-            cabi.ptr(tb), nbytes, cabi.ptr(paths), cabi.ptr(plen), cabi.ptr(score),
-            cabi.stream_ptr(dev)), 'sloika_viterbi_fwd')
+        from sloika_b200.engine import launch
+        launch('viterbi', 1, lib.sloika_viterbi_fwd,
+               cabi.ptr(post), ld_t, ld_b, cabi.ptr(lens), T, B, nbase, klen,
+               float(skip_pen), float(min_prob), cabi.SLOIKA_VIT_LOG if log else cabi.SLOIKA_VIT_POST,
+               cabi.ptr(tb), nbytes, cabi.ptr(paths), cabi.ptr(plen), cabi.ptr(score),
+               cabi.stream_ptr(dev))
     if return_device:
         return score, paths, plen
     score_h = score.cpu().numpy()

@@ -25,8 +25,20 @@ class Act(object):
     """
 
     def __init__(self, data, lengths=None, reverse=False):
-        assert data.dim() == 3 and data.stride(2) == 1 and data.stride(0) == data.shape[1] * data.stride(1)
+        assert data.dim() == 3
+        T, B, F = data.shape
+        # strides of size-1 dimensions are meaningless in torch; derive the row distance from a
+        # dimension that is really stepped over
+        if B > 1:
+            ld = data.stride(1)
+            assert T == 1 or data.stride(0) == B * ld, "time-major [T, B, F] layout expected"
+        elif T > 1:
+            ld = data.stride(0)
+        else:
+            ld = F
+        assert (F == 1 or data.stride(2) == 1) and ld >= F, "feature axis must be contiguous"
         self.data = data
+        self._ld = ld
         self.lengths = lengths
         self.reverse = reverse
 
@@ -44,7 +56,7 @@ class Act(object):
 
     @property
     def ld(self):
-        return self.data.stride(1)
+        return self._ld
 
     @property
     def device(self):
@@ -55,6 +67,50 @@ class Act(object):
 
     def like(self, data, lengths='same'):
         return Act(data, self.lengths if lengths == 'same' else lengths, self.reverse)
+
+
+class KernelTimer(object):
+    """Optional per-kernel device timing: CUDA events recorded on the launching stream around each
+    C-ABI call (used by bench.py for the roofline object; off by default)."""
+
+    def __init__(self):
+        self.spans = {}       # kernel name -> [(start_event, end_event)]
+        self.launches = 0     # kernels enqueued since reset (counted even when timing is off)
+        self.enabled = False
+
+    def reset(self):
+        self.spans = {}
+        self.launches = 0
+
+    def totals_ms(self):
+        """name -> (total ms, number of calls); call after synchronising."""
+        return {k: (sum(a.elapsed_time(b) for a, b in v), len(v)) for k, v in self.spans.items()}
+
+
+TIMER = KernelTimer()
+
+
+def launch(name, nkernels, fn, *args):
+    """Enqueue one C-ABI call, bracketed by events when profiling is on."""
+    import torch
+    TIMER.launches += nkernels
+    if TIMER.enabled:
+        start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        code = fn(*args)
+        end.record()
+        TIMER.spans.setdefault(name, []).append((start, end))
+    else:
+        code = fn(*args)
+    cabi.check(code, name)
+
+
+def _row_stride(t):
+    """Distance in floats between consecutive (time, batch) rows of a [T, B, F] tensor."""
+    T, B, F = t.shape
+    if B > 1:
+        return t.stride(1)
+    return t.stride(0) if T > 1 else F
 
 
 def _empty(shape, device):
@@ -78,11 +134,10 @@ def run_convolution(layer, act, out=None):
     Tout = output_length(act.T, layer.winlen, layer.stride, layer.padding)
     y = _out_buffer(act, Tout, layer.size, out)
     dev = act.device
-    cabi.check(lib.sloika_conv1d_fwd(
-        cabi.ptr(act.data), cabi.ptr(layer.W.device(dev)), cabi.ptr(layer.b.device(dev)), cabi.ptr(y),
-        y.stride(1), cabi.ptr(act.lengths), act.T, act.B, layer.insize, layer.size, layer.winlen,
-        layer.stride, layer.padding[0], layer.padding[1], code_of(layer.fun), cabi.stream_ptr(dev)),
-        'sloika_conv1d_fwd')
+    launch('conv1d', 1, lib.sloika_conv1d_fwd,
+           cabi.ptr(act.data), cabi.ptr(layer.W.device(dev)), cabi.ptr(layer.b.device(dev)), cabi.ptr(y),
+           _row_stride(y), cabi.ptr(act.lengths), act.T, act.B, layer.insize, layer.size, layer.winlen,
+           layer.stride, layer.padding[0], layer.padding[1], code_of(layer.fun), cabi.stream_ptr(dev))
     lengths = None
     if act.lengths is not None:
         # per-read output length: each read is padded/convolved on its own (conv.py:66-111)
@@ -96,10 +151,10 @@ def run_feedforward(layer, act, out=None):
     assert act.F == layer.insize
     y = _out_buffer(act, act.T, layer.size, out)
     dev = act.device
-    cabi.check(lib.sloika_linear_fwd(
-        cabi.ptr(act.data), act.ld, cabi.ptr(layer.W.device(dev)), cabi.ptr(layer.b.device(dev)),
-        cabi.ptr(y), y.stride(1), act.T * act.B, layer.insize, layer.size, code_of(layer.fun),
-        cabi.stream_ptr(dev)), 'sloika_linear_fwd')
+    launch('feedforward', 1, lib.sloika_linear_fwd,
+           cabi.ptr(act.data), act.ld, cabi.ptr(layer.W.device(dev)), cabi.ptr(layer.b.device(dev)),
+           cabi.ptr(y), _row_stride(y), act.T * act.B, layer.insize, layer.size, code_of(layer.fun),
+           cabi.stream_ptr(dev))
     return act.like(y)
 
 
@@ -108,27 +163,29 @@ def run_softmax(layer, act, out=None):
     assert act.F == layer.insize
     y = _out_buffer(act, act.T, layer.size, out)
     dev = act.device
-    cabi.check(lib.sloika_softmax_fwd(
-        cabi.ptr(act.data), act.ld, cabi.ptr(layer.W.device(dev)), cabi.ptr(layer.b.device(dev)),
-        cabi.ptr(y), y.stride(1), act.T * act.B, layer.insize, layer.size, cabi.stream_ptr(dev)),
-        'sloika_softmax_fwd')
+    launch('softmax', 2, lib.sloika_softmax_fwd,
+           cabi.ptr(act.data), act.ld, cabi.ptr(layer.W.device(dev)), cabi.ptr(layer.b.device(dev)),
+           cabi.ptr(y), _row_stride(y), act.T * act.B, layer.insize, layer.size, cabi.stream_ptr(dev))
     return act.like(y)
 
 
 def run_gru(layer, act, out=None):
-    import torch
     lib = cabi.load()
     assert act.F == layer.insize
     y = _out_buffer(act, act.T, layer.size, out)
     dev = act.device
-    nbytes = lib.sloika_gru_workspace_bytes(act.T, act.B, layer.size)
-    ws = torch.empty((max(nbytes, 4) + 3) // 4, dtype=torch.float32, device=dev)
-    cabi.check(lib.sloika_gru_fwd(
-        cabi.ptr(act.data), act.ld, cabi.ptr(layer.iW.device(dev)), cabi.ptr(layer.sW.device(dev)),
-        cabi.ptr(layer.sW2.device(dev)), cabi.ptr(layer.b.device(dev)), cabi.ptr(y), y.stride(1),
-        cabi.ptr(ws), nbytes, cabi.ptr(act.lengths), act.T, act.B, layer.insize, layer.size,
-        1 if act.reverse else 0, code_of(layer.fun), code_of(layer.gatefun), cabi.stream_ptr(dev)),
-        'sloika_gru_fwd')
+    # sloika_gru_fwd == input projection for all steps + recurrence; issued as its two halves so
+    # that each kernel can be timed on its own
+    H = layer.size
+    vI = _empty((act.T, act.B, 3 * H), dev)
+    st = cabi.stream_ptr(dev)
+    launch('gru_projection', 1, lib.sloika_linear_fwd,
+           cabi.ptr(act.data), act.ld, cabi.ptr(layer.iW.device(dev)), cabi.ptr(layer.b.device(dev)),
+           cabi.ptr(vI), 3 * H, act.T * act.B, layer.insize, 3 * H, 0, st)
+    launch('gru_recurrence', 1, lib.sloika_gru_recurrence_fwd,
+           cabi.ptr(vI), cabi.ptr(layer.sW.device(dev)), cabi.ptr(layer.sW2.device(dev)), cabi.ptr(y),
+           _row_stride(y), cabi.ptr(act.lengths), act.T, act.B, H, 1 if act.reverse else 0,
+           code_of(layer.fun), code_of(layer.gatefun), st)
     return act.like(y)
 
 

@@ -1,0 +1,88 @@
+"""GPU: the north-star path end to end on the bundled reads (config 1): pretrained network forward +
+Viterbi + sequence assembly against the golden basecalls made with the reference's decode.py/bio.py
+on the oracle's float32 posteriors (tools/make_golden.py)."""
+import io
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import scaled_signal
+from oracle import decode_ref, forward_ref, host_ref
+from sloika_b200 import basecall, decode
+
+pytestmark = pytest.mark.gpu
+NAMES = ['read{}'.format(i) for i in range(1, 9)]
+
+
+def _edit_distance(a, b):
+    prev = list(range(len(b) + 1))
+    for i, ca in enumerate(a, 1):
+        cur = [i]
+        for j, cb in enumerate(b, 1):
+            cur.append(min(prev[j] + 1, cur[j - 1] + 1, prev[j - 1] + (ca != cb)))
+        prev = cur
+    return prev[-1]
+
+
+@pytest.fixture(scope='module')
+def calls(pretrained, reads_daq):
+    net = pretrained.compile()
+    signals = [basecall.prepare_signal(scaled_signal(reads_daq, n), (200, 10), 0) for n in NAMES]
+    batch = basecall.basecall_signals(signals, kmer_len=5, min_prob=1e-5, skip=0.0, network=net)
+    return net, signals, batch
+
+
+def test_ragged_batch_basecalls_match_golden(calls, read_basecalls):
+    """All 8 reads in ONE ragged device batch: paths/FASTA identical to the golden records (score to
+    0.05 -- the header prints it with %.0f)."""
+    net, signals, batch = calls
+    printer_out = io.StringIO()
+    printer = basecall.SeqPrinter(5, datatype='samples', transducer=True)
+    printer.fh = printer_out
+    mismatched = []
+    for name, sig, (score, path) in zip(NAMES, signals, batch):
+        gold = read_basecalls[name]
+        assert len(sig) == gold['nsamples']
+        assert abs(score - gold['score']) < 0.05, name
+        if path != gold['path']:
+            mismatched.append((name, _edit_distance(path, gold['path'])))
+        printer.write(name, score, path, len(sig))
+    assert not mismatched, "paths differ from golden (edit distances): {}".format(mismatched)
+    expect = ''.join(read_basecalls[n]['header'] + '\n' + read_basecalls[n]['seq'] + '\n' for n in NAMES)
+    assert printer_out.getvalue() == expect
+
+
+def test_single_read_call_equals_batched_call(calls):
+    """Batch-of-one (the reference's calling convention, basecall.py:117-119) == ragged batch."""
+    net, signals, batch = calls
+    for idx in (6, 4):
+        one = basecall.basecall_signals([signals[idx]], network=net)[0]
+        assert one[1] == batch[idx][1] and one[0] == batch[idx][0]
+
+
+def test_posteriors_of_real_read_within_bound(calls, golden_dir, pretrained):
+    net, signals, _ = calls
+    slices = np.load(os.path.join(golden_dir, 'reads_post_slices.npz'))
+    for name in ('read5', 'read8'):
+        sig = signals[NAMES.index(name)]
+        post = net(sig[:, None, None])
+        assert np.abs(post[:8, 0] - slices[name + '_head']).max() < 1e-4
+        assert np.abs(post[-8:, 0] - slices[name + '_tail']).max() < 1e-4
+        assert np.abs(post[:, 0].max(1) - slices[name + '_rowmax']).max() < 1e-4
+    # full-matrix check against the live oracle on the shortest real read
+    sig = signals[NAMES.index('read7')]
+    post = net(sig[:, None, None])
+    ref = forward_ref.run(pretrained.json(params=True), sig[:, None, None])
+    assert np.abs(post - ref).max() < 1e-4
+
+
+def test_decode_post_dropin(calls, read_basecalls, pretrained):
+    """basecall.decode_post on a [T, 1, S] posterior (the reference call at basecall.py:119)."""
+    net, signals, _ = calls
+    sig = signals[NAMES.index('read7')]
+    ref_post = forward_ref.run(pretrained.json(params=True), sig[:, None, None])
+    score, path = basecall.decode_post(ref_post, 5, True, True, 1e-5, 0.0, None, nbase=4)
+    s_ref, p_ref = decode_ref.decode_post(ref_post, 5, 1e-5, skip=0.0)
+    assert path == p_ref and abs(score - s_ref) < 1e-2

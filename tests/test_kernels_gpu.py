@@ -1,0 +1,262 @@
+"""GPU: every kernel behind the C ABI against the CPU oracle on the same seeded inputs.
+
+Tolerances: forward kernels are float32 with a different summation order than BLAS -> 2e-5 on
+pre-softmax activations in [-1, 1] (elu outputs: relative), 1e-4 max-abs on posteriors (the
+north-star bound); Viterbi is float32 add/max only -> scores and paths are compared EXACTLY when both
+sides get identical log-posteriors.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import cbind, decode_ref, forward_ref
+from sloika_b200 import activation as act
+from sloika_b200 import cabi, decode, engine, layers, zoo
+from sloika_b200 import module_tools as smt
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+
+
+def _init():
+    return smt.partial(smt.truncated_normal, sd=0.5)
+
+
+def _run(layer, x, lengths=None, reverse=False):
+    a = engine.Act(torch.from_numpy(x).to(DEV), None if lengths is None else torch.as_tensor(lengths, dtype=torch.int32, device=DEV), reverse)
+    out = layer.run(a)
+    torch.cuda.synchronize()
+    return out.data.cpu().numpy(), out
+
+
+def _oracle(layer, x):
+    return forward_ref.run(layer.json(params=True), x)
+
+
+# ------------------------------------------------------------------ convolution
+@pytest.mark.parametrize('C,stride,fun,T,B', [(96, 5, act.elu, 403, 37), (128, 2, act.tanh, 250, 5),
+                                               (32, 2, act.tanh, 64, 33), (128, 5, act.elu, 1, 1),
+                                               (96, 5, act.elu, 4000, 16)])
+def test_conv_raw(C, stride, fun, T, B):
+    np.random.seed(C + T)
+    layer = layers.Convolution(1, C, 11, stride, init=_init(), has_bias=True, fun=fun)
+    x = (3 * np.random.standard_normal((T, B, 1))).astype(np.float32)
+    got, _ = _run(layer, x)
+    ref = _oracle(layer, x)
+    assert got.shape == ref.shape == (-(-T // stride), B, C)
+    np.testing.assert_allclose(got, ref, atol=2e-5, rtol=2e-5)
+
+
+def test_conv_generic_signature():
+    """The reference's own layer test shape: Convolution(12, 32, 11, 5) on [100, 20, 12] (test_layers.py:454-459)."""
+    np.random.seed(3)
+    for mode in ('same', 'valid', 'full', (2, 7)):
+        layer = layers.Convolution(12, 32, 11, 5, init=_init(), has_bias=True, padding_mode=mode)
+        x = np.random.standard_normal((100, 20, 12)).astype(np.float32)
+        got, _ = _run(layer, x)
+        ref = _oracle(layer, x)
+        assert got.shape == ref.shape
+        np.testing.assert_allclose(got, ref, atol=2e-5, rtol=2e-5)
+    # even window, no bias, Cout not a multiple of 4
+    layer = layers.Convolution(1, 30, 4, 3, init=_init(), has_bias=False, fun=act.linear)
+    x = np.random.standard_normal((50, 3, 1)).astype(np.float32)
+    np.testing.assert_allclose(_run(layer, x)[0], _oracle(layer, x), atol=2e-5, rtol=2e-5)
+
+
+def test_conv_ragged_equals_per_read():
+    np.random.seed(4)
+    layer = layers.Convolution(1, 96, 11, 5, init=_init(), has_bias=True, fun=act.elu)
+    lengths = [503, 1, 250, 499, 7]
+    x = np.zeros((503, 5, 1), dtype=np.float32)
+    for b, n in enumerate(lengths):
+        x[:n, b, 0] = np.random.standard_normal(n)
+    x_dirty = x.copy()
+    for b, n in enumerate(lengths):
+        x_dirty[n:, b, 0] = 99.0                     # garbage past the end must not be read
+    got, out = _run(layer, x_dirty, lengths)
+    assert out.lengths.cpu().tolist() == [-(-n // 5) for n in lengths]
+    for b, n in enumerate(lengths):
+        ref = _oracle(layer, x[:n, b:b + 1])
+        np.testing.assert_allclose(got[:ref.shape[0], b], ref[:, 0], atol=2e-5, rtol=2e-5)
+
+
+# ------------------------------------------------------------------ feed-forward / softmax
+@pytest.mark.parametrize('I,O,fun', [(192, 128, act.tanh), (12, 8, act.linear), (110, 37, act.sigmoid), (5, 130, act.elu)])
+def test_feedforward(I, O, fun):
+    np.random.seed(I)
+    layer = layers.FeedForward(I, O, init=_init(), has_bias=True, fun=fun)
+    x = np.random.standard_normal((33, 7, I)).astype(np.float32)
+    np.testing.assert_allclose(_run(layer, x)[0], _oracle(layer, x), atol=2e-5, rtol=2e-5)
+
+
+@pytest.mark.parametrize('I', [96, 110, 112, 128])
+def test_softmax(I):
+    np.random.seed(I)
+    layer = layers.Softmax(I, 1025, init=_init(), has_bias=True)
+    layer.W.set_value(layer.W.get_value() * 6)       # trained-model-like magnitudes -> peaky rows
+    x = np.tanh(np.random.standard_normal((40, 9, I))).astype(np.float32)
+    got = _run(layer, x)[0]
+    ref = _oracle(layer, x)
+    assert np.abs(got - ref).max() < 2e-5
+    np.testing.assert_allclose(got.sum(2), 1.0, rtol=1e-5)
+
+
+# ------------------------------------------------------------------ GRU
+@pytest.mark.parametrize('I,H,T,B,reverse', [(96, 96, 120, 19, False), (96, 96, 120, 8, True),
+                                             (128, 112, 80, 5, True), (112, 144, 80, 9, False),
+                                             (128, 110, 60, 3, True), (110, 142, 60, 4, False),
+                                             (32, 96, 50, 1, False), (12, 64, 10, 20, False),
+                                             (7, 5, 30, 2, True), (40, 128, 40, 11, False),
+                                             (3, 33, 25, 17, True), (16, 80, 25, 8, False), (16, 16, 25, 8, True)])
+def test_gru(I, H, T, B, reverse):
+    np.random.seed(I * 1000 + H)
+    g = layers.Gru(I, H, init=_init(), has_bias=True)
+    # trained-model-like magnitudes (|w| up to ~4): gates saturate, errors would compound if wrong
+    g.sW.set_value(g.sW.get_value() * 6)
+    g.sW2.set_value(g.sW2.get_value() * 6)
+    layer = layers.Reverse(g) if reverse else g
+    x = np.tanh(np.random.standard_normal((T, B, I))).astype(np.float32)
+    got = _run(layer, x)[0]
+    ref = _oracle(layer, x)
+    assert got.shape == ref.shape
+    assert np.abs(got - ref).max() < 5e-5
+
+
+def test_gru_ragged_equals_per_read():
+    np.random.seed(11)
+    for reverse in (False, True):
+        g = layers.Gru(24, 96, init=_init(), has_bias=True)
+        layer = layers.Reverse(g) if reverse else g
+        lengths = [70, 1, 33, 69, 70, 2, 50, 64, 8, 41]
+        x = np.tanh(np.random.standard_normal((70, len(lengths), 24))).astype(np.float32)
+        got, _ = _run(layer, x, lengths)
+        for b, n in enumerate(lengths):
+            ref = _oracle(layer, x[:n, b:b + 1])
+            assert np.abs(got[:n, b] - ref[:, 0]).max() < 5e-5, (reverse, b)
+            assert np.all(got[n:, b] == 0)
+
+
+def test_birnn_parallel_writes_in_place():
+    np.random.seed(12)
+    init = _init()
+    net = layers.Serial([layers.birnn(layers.Gru(20, 48, init=init, has_bias=True), layers.Gru(20, 48, init=init, has_bias=True)),
+                         layers.FeedForward(96, 40, init=init, has_bias=True),
+                         layers.Parallel([layers.FeedForward(40, 8, init=init, has_bias=True),
+                                          layers.Reverse(layers.Gru(40, 16, init=init, has_bias=True))])])
+    x = np.tanh(np.random.standard_normal((45, 6, 20))).astype(np.float32)
+    got = _run(net, x)[0]
+    ref = _oracle(net, x)
+    assert got.shape == ref.shape == (45, 6, 24)
+    assert np.abs(got - ref).max() < 5e-5
+
+
+# ------------------------------------------------------------------ whole networks
+@pytest.mark.parametrize('name,T,B', [('raw_rgrgr', 1000, 6), ('raw_rGr', 400, 5), ('bigger_raw_gru', 300, 4),
+                                      ('pretrained_like', 900, 3)])
+def test_network_posteriors(name, T, B):
+    np.random.seed(len(name))
+    net = getattr(zoo, name)()
+    x = np.random.standard_normal((T, B, 1)).astype(np.float32)
+    post = net.compile()(x)
+    ref = _oracle(net, x)
+    assert post.shape == ref.shape and post.dtype == np.float32
+    assert np.abs(post - ref).max() < 1e-4            # north-star bound
+    with pytest.raises(TypeError):
+        net.compile()(x.astype(np.float64))           # Theano function rejects the wrong dtype too
+
+
+# ------------------------------------------------------------------ Viterbi
+def _kernel_vs_golden(case, data, **kw):
+    name = case['name']
+    if name + '/post' in data:
+        post = data[name + '/post']
+    else:
+        post = decode_ref.prepare_post(data[name + '/raw'], min_prob=1e-5)
+    return post
+
+
+def test_viterbi_reference_known_answers(decode_cases):
+    """test/unit/test_decode.py:233-256 through the device kernel (float64 inputs are decoded in
+    float32: paths identical, score to 1e-5)."""
+    meta, data = decode_cases
+    score, path = decode.viterbi(data['kat_post3/post'], 3)
+    assert path == [49, 7, 63, 63] and abs(score - (-11.130084569094556)) < 1e-5
+    score, path = decode.viterbi(data['kat_post3/post'], 3, skip_pen=3.0)
+    assert path == [49, 7, 31, 63, 63] and abs(score - (-11.936803444063674)) < 1e-5
+    score, path = decode.viterbi(data['kat_modbase/post'], 3, skip_pen=5.0, nbase=5)
+    assert path == data['kat_modbase/path'].tolist()
+
+
+def test_viterbi_golden_vectors_bit_exact(decode_cases):
+    """Identical float32 log-posteriors in -> identical score bits and path out."""
+    meta, data = decode_cases
+    for case in meta:
+        post = _kernel_vs_golden(case, data)
+        if post.dtype != np.float32:
+            continue
+        lp = post if case['log'] else decode_ref.log_post(post)
+        score, path = decode.viterbi(lp, case['klen'], skip_pen=case['skip_pen'], log=True, nbase=case['nbase'])
+        assert path == data[case['name'] + '/path'].tolist(), case['name']
+        assert score == data[case['name'] + '/score'], case['name']
+
+
+def test_viterbi_fused_prepare_and_log(decode_cases):
+    """Raw posteriors in, min_prob floor + log done in the kernel (device logf vs NumPy log may differ
+    by an ulp, so the score is compared to 1e-3 and the path must still match on these cases)."""
+    meta, data = decode_cases
+    for case in meta:
+        name = case['name']
+        if name + '/raw' not in data:
+            continue
+        score, paths = decode.viterbi_batch(data[name + '/raw'], None, klen=case['klen'], skip_pen=case['skip_pen'],
+                                            min_prob=1e-5, nbase=case['nbase'])
+        assert paths[0] == data[name + '/path'].tolist(), name
+        assert abs(score[0] - float(data[name + '/score'])) < 1e-3 * max(1.0, abs(float(data[name + '/score']))), name
+
+
+def test_viterbi_ragged_batch_bit_exact():
+    rng = np.random.default_rng(9)
+    T, B, S = 257, 21, 1025
+    logits = 3 * rng.standard_normal((T, B, S))
+    logits[:, :, 0] += 6
+    post = np.exp(logits - logits.max(2, keepdims=True))
+    post = (post / post.sum(2, keepdims=True)).astype(np.float32)
+    lp = decode_ref.log_post(decode_ref.prepare_post(post.reshape(T * B, 1, S)).reshape(T, B, S)).astype(np.float32)
+    lengths = rng.integers(1, T + 1, size=B).astype(np.int32)
+    lengths[:4] = [T, 1, 2, 0]
+    for skip in (0.0, 2.5):
+        score, paths = decode.viterbi_batch(lp, lengths, skip_pen=skip, log=True)
+        ok = lengths > 0
+        ref_score, ref_paths = cbind.viterbi_batch(lp[:, ok], lengths[ok], skip_pen=skip)
+        got_paths = [p for p, k in zip(paths, ok) if k]
+        assert got_paths == ref_paths
+        assert np.array_equal(score[ok], ref_score)
+        assert paths[3] == [] and score[3] == 0.0
+
+
+def test_viterbi_strided_posteriors_view():
+    """The decoder reads the network's output in place, including a column-padded buffer."""
+    rng = np.random.default_rng(10)
+    T, B, S = 60, 3, 1025
+    buf = torch.rand((T, B, 1032), device=DEV)
+    view = buf[:, :, :S]
+    lp = torch.log_softmax(view * 4, dim=2)
+    padded = torch.full((T, B, 1032), -1.0, device=DEV)
+    padded[:, :, :S] = lp
+    s1, p1 = decode.viterbi_batch(padded[:, :, :S], None, log=True)
+    s2, p2 = decode.viterbi_batch(lp.contiguous(), None, log=True)
+    assert p1 == p2 and np.array_equal(s1, s2)
+    ref_s, ref_p = cbind.viterbi_batch(lp.cpu().numpy(), None)
+    assert p1 == ref_p and np.array_equal(s1, ref_s)
+
+
+def test_error_codes_surface_as_exceptions():
+    with pytest.raises(AssertionError):
+        decode.viterbi(np.zeros((4, 17), dtype=np.float32), 2)             # klen >= 3 (decode.py:50)
+    with pytest.raises(AssertionError):
+        decode.viterbi(np.zeros((4, 66), dtype=np.float32), 3)             # nstate mismatch (decode.py:52)
+    g = layers.Gru(8, 200, has_bias=True)                                   # H > 144: no kernel yet
+    with pytest.raises(cabi.SloikaB200Error):
+        _run(g, np.zeros((4, 2, 8), dtype=np.float32))
