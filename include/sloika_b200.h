@@ -69,6 +69,16 @@ int sloika_conv1d_fwd(const float *x, const float *W, const float *bias, float *
 int sloika_linear_fwd(const float *x, long ldx, const float *W, const float *bias, float *y, long ldy,
                       long M, int K, int N, int act, void *stream);
 
+/* Same, with an explicit kernel choice: AUTO = tcgen05 tensor-core kernel (3xTF32 split, fp32-equivalent
+ * accuracy, TMA fed) when shape/alignment allow, else the fp32 SIMT kernel; SIMT / TC force one
+ * (TC returns SLOIKA_ERR_UNSUPPORTED when it cannot run: ldx % 4 != 0, x not 16-byte aligned, K > 256,
+ * M < 128). */
+#define SLOIKA_GEMM_AUTO 0
+#define SLOIKA_GEMM_SIMT 1
+#define SLOIKA_GEMM_TC   2
+int sloika_linear_fwd_ex(const float *x, long ldx, const float *W, const float *bias, float *y, long ldy,
+                         long M, int K, int N, int act, int algo, void *stream);
+
 /*
  * Softmax.run -- sloika/layers.py:309-314:
  *   t = x . W' + bias ; post = exp(t - max_j t) / sum_j exp(t - max_j t)     (row-wise over N)

@@ -24,6 +24,7 @@ EXPORTS = {
     'sloika_b200_device_info': (_i, [_p, _p, _p]),
     'sloika_conv1d_fwd': (_i, [_p, _p, _p, _p, _l, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     'sloika_linear_fwd': (_i, [_p, _l, _p, _p, _p, _l, _l, _i, _i, _i, _p]),
+    'sloika_linear_fwd_ex': (_i, [_p, _l, _p, _p, _p, _l, _l, _i, _i, _i, _i, _p]),
     'sloika_softmax_fwd': (_i, [_p, _l, _p, _p, _p, _l, _l, _i, _i, _p]),
     'sloika_gru_workspace_bytes': (_z, [_i, _i, _i]),
     'sloika_gru_fwd': (_i, [_p, _l, _p, _p, _p, _p, _p, _l, _p, _z, _p, _i, _i, _i, _i, _i, _i, _i, _p]),

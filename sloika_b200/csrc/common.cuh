@@ -35,6 +35,16 @@ __device__ __forceinline__ float apply_act(float x, int act) {
     }
 }
 
+// Compile-time selected activation: keeps unrolled epilogues branch-free and small (a runtime switch
+// inlined 32x blew the instruction cache of the GEMM epilogue).
+template <int ACT>
+__device__ __forceinline__ float apply_act_t(float x) {
+    if constexpr (ACT == SLOIKA_ACT_TANH) return tanhf(x);
+    else if constexpr (ACT == SLOIKA_ACT_SIGMOID) return sigmoid_ref(x);
+    else if constexpr (ACT == SLOIKA_ACT_ELU) return elu_ref(x);
+    else return x;
+}
+
 __host__ inline bool act_known(int act) { return act >= SLOIKA_ACT_LINEAR && act <= SLOIKA_ACT_ELU; }
 
 __host__ __device__ __forceinline__ long ceil_div(long a, long b) { return (a + b - 1) / b; }

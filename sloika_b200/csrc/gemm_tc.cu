@@ -1,0 +1,361 @@
+// y = act(x . W' + bias) on the 5th-generation tensor cores with fp32-equivalent accuracy (3xTF32).
+//
+// Used for the GRU input projection over all time steps (sloika/layers.py:1011: vI = x iW' + b),
+// FeedForward.run (layers.py:157-158) and the logits of Softmax.run (layers.py:310).
+// M = T*B rows is huge (819 200), K <= 256 and N <= ~1100 are small: the weights are tiny and stay
+// resident on chip, x is streamed exactly once per N slice, y is written once.  HBM-bound by design.
+//
+// Accuracy: the reference multiplies in float32.  Plain TF32 (10-bit mantissa) would put ~1e-3 of
+// error into the gate pre-activations, so every operand is split on chip into hi = top 19 bits and
+// lo = x - hi (exact), and three MMAs  hi.hi + lo.hi + hi.lo  are accumulated in fp32 in TMEM; the
+// dropped lo.lo term is 2^-22 relative.
+//
+// Structure (one persistent CTA per SM, 320 threads, warp specialised):
+//   grid = n_slices x ctas_per_slice; a CTA owns output columns [n0, n0 + BN) and walks m-tiles.
+//   prologue   all warps: W slice -> smem as W_hi / W_lo in the UMMA K-major SWIZZLE_128B layout
+//   warp 4     TMA producer: x tile [128 rows x 32 k] per stage (cp.async.bulk.tensor, SWIZZLE_128B)
+//   warps 6-9  transform: raw fp32 tile -> hi (in place) + lo, fence.proxy.async, signal
+//   warp 5     MMA issuer: 4 K-steps x 3 tcgen05.mma (M=128, N=BN, K=8) per stage, accumulators in
+//              TMEM (2 stages x BN columns); tcgen05.commit frees the smem stage / publishes the tile
+//   warps 0-3  epilogue: tcgen05.ld (thread = row), + bias, activation, transpose through smem,
+//              coalesced 128-byte row stores
+#include <cstdlib>
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace sloika {
+
+namespace gemm_tc {
+
+constexpr int BM = 128;            // rows per tile (UMMA M)
+constexpr int KB = 32;             // k elements per K block (one 128-byte swizzle row)
+constexpr int MAX_STAGES = 8;      // smem stages of (hi, lo) x-tiles (as many as fit)
+constexpr int NACC = 2;            // TMEM accumulator stages
+constexpr int THREADS = 320;
+constexpr int A_TILE_BYTES = BM * KB * 4;        // 16 KB
+constexpr int TMEM_COLS = 512;
+constexpr int STG_LD = 36;           // staging row pitch (floats): 16-byte aligned rows, conflict-free float4 phases
+
+struct Params {
+    const float *W;
+    const float *bias;
+    float *y;
+    long ldy;
+    long M;
+    int K, N, act;
+    int BN, n_slices, ctas_per_slice, nkb;
+    int stages;       // smem pipeline depth
+    int vec_out;      // rows of y are 16-byte aligned: 128-bit stores
+    int dbg;          // timing experiments only (SLOIKA_B200_GEMM_DBG): 1 no split math, 2 no stores, 4 no MMA
+};
+
+__host__ __device__ inline size_t smem_bytes(int BN, int nkb, int stages)
+{
+    size_t w = (size_t)2 * nkb * BN * 128;                 // W_hi + W_lo
+    size_t a = (size_t)stages * 2 * A_TILE_BYTES;          // (hi, lo) per stage
+    size_t stg = (size_t)4 * 32 * STG_LD * 4;              // epilogue transpose buffers
+    size_t misc = (size_t)BN * 4 + 512;                    // bias slice + barriers
+    return w + a + stg + misc + 1024;                      // + alignment slack
+}
+
+template <int ACT>
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params p)
+{
+    extern __shared__ uint8_t smem_raw[];
+    // 1024-byte alignment for the 128-byte swizzle; plain pointer arithmetic keeps the shared address space
+    uint8_t *smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
+    const int BN = p.BN, nkb = p.nkb, STAGES = p.stages;
+    uint8_t *Whi = smem;
+    uint8_t *Wlo = Whi + (size_t)nkb * BN * 128;
+    uint8_t *Abase = Wlo + (size_t)nkb * BN * 128;                        // stage s: hi at 2s, lo at 2s+1
+    float *stg_all = reinterpret_cast<float *>(Abase + (size_t)STAGES * 2 * A_TILE_BYTES);
+    float *bias_s = stg_all + 4 * 32 * STG_LD;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(bias_s + BN);
+    uint64_t *full_raw = bars;                     // [STAGES] TMA -> transform
+    uint64_t *full_split = bars + MAX_STAGES;      // [STAGES] transform -> MMA
+    uint64_t *empty = bars + 2 * MAX_STAGES;       // [STAGES] MMA -> TMA
+    uint64_t *tmem_full = bars + 3 * MAX_STAGES;   // [NACC]   MMA -> epilogue
+    uint64_t *tmem_empty = tmem_full + NACC;       // [NACC]   epilogue -> MMA
+    uint32_t *tmem_base_s = reinterpret_cast<uint32_t *>(tmem_empty + NACC);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int slice = blockIdx.x % p.n_slices;
+    const int cta_in_slice = blockIdx.x / p.n_slices;
+    const int n0 = slice * BN;
+    const long m_tiles = (p.M + BM - 1) / BM;
+
+    // ---------------- prologue ----------------
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; s++) { tc::mbar_init(&full_raw[s], 1); tc::mbar_init(&full_split[s], 128); tc::mbar_init(&empty[s], 1); }
+        for (int a = 0; a < NACC; a++) { tc::mbar_init(&tmem_full[a], 1); tc::mbar_init(&tmem_empty[a], 128); }
+        tc::mbar_fence_init();
+    }
+    if (warp == 4 && lane == 0) tc::tma_prefetch_desc(&tmap_x);
+    if (warp == 5) tc::tmem_alloc(tmem_base_s, TMEM_COLS);
+    // weights of this slice: split into hi / lo and stored K-major, 128-byte swizzled, zero padded
+    for (int e = tid; e < BN * nkb * KB; e += THREADS) {
+        const int k = e % (nkb * KB), n = e / (nkb * KB);
+        float w = 0.0f;
+        if (n0 + n < p.N && k < p.K) w = __ldg(p.W + (long)(n0 + n) * p.K + k);
+        const float hi = __uint_as_float(__float_as_uint(w) & 0xffffe000u);
+        const uint32_t off = (uint32_t)(k / KB) * (uint32_t)(BN * 128) + tc::sw128_offset(n, k % KB);
+        *reinterpret_cast<float *>(Whi + off) = hi;
+        *reinterpret_cast<float *>(Wlo + off) = w - hi;
+    }
+    for (int n = tid; n < BN; n += THREADS) bias_s[n] = (p.bias && n0 + n < p.N) ? __ldg(p.bias + n0 + n) : 0.0f;
+    tc::fence_proxy_async();
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_base_s;
+
+    if (warp == 4) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (long mt = cta_in_slice; mt < m_tiles; mt += p.ctas_per_slice) {
+                for (int kb = 0; kb < nkb; kb++, it++) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    tc::mbar_wait(&empty[s], ph ^ 1);
+                    tc::mbar_arrive_expect_tx(&full_raw[s], A_TILE_BYTES);
+                    tc::tma_load_2d(Abase + (size_t)(2 * s) * A_TILE_BYTES, &tmap_x, &full_raw[s], kb * KB, (int)(mt * BM));
+                }
+            }
+        }
+    } else if (warp == 5) {
+        // ================= MMA issuer =================
+        if (lane == 0) {
+            const uint32_t idesc = tc::umma_idesc_tf32_m128(BN);
+            uint32_t it = 0, tile = 0;
+            for (long mt = cta_in_slice; mt < m_tiles; mt += p.ctas_per_slice, tile++) {
+                const int a = tile % NACC;
+                const uint32_t aph = (tile / NACC) & 1;
+                tc::mbar_wait(&tmem_empty[a], aph ^ 1);
+                tc::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(a * BN);
+                for (int kb = 0; kb < nkb; kb++, it++) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    tc::mbar_wait(&full_split[s], ph);
+                    tc::tc_fence_after();
+                    const uint32_t a_hi = tc::smem_u32(Abase + (size_t)(2 * s) * A_TILE_BYTES);
+                    const uint32_t a_lo = a_hi + A_TILE_BYTES;
+                    const uint32_t b_hi = tc::smem_u32(Whi) + (uint32_t)kb * (uint32_t)(BN * 128);
+                    const uint32_t b_lo = tc::smem_u32(Wlo) + (uint32_t)kb * (uint32_t)(BN * 128);
+                    const int krem = p.K - kb * KB;
+                    const int ksteps = krem >= KB ? 4 : (krem + 7) / 8;
+#pragma unroll 1
+                    for (int ks = 0; ks < ksteps; ks++) {
+                        const uint64_t dah = tc::umma_desc_sw128_kmajor(a_hi + ks * 32);
+                        const uint64_t dal = tc::umma_desc_sw128_kmajor(a_lo + ks * 32);
+                        const uint64_t dbh = tc::umma_desc_sw128_kmajor(b_hi + ks * 32);
+                        const uint64_t dbl = tc::umma_desc_sw128_kmajor(b_lo + ks * 32);
+                        if (p.dbg & 4) continue;
+                        tc::umma_tf32_ss(d_tmem, dah, dbh, idesc, (kb | ks) != 0);
+                        tc::umma_tf32_ss(d_tmem, dal, dbh, idesc, true);
+                        tc::umma_tf32_ss(d_tmem, dah, dbl, idesc, true);
+                    }
+                    tc::umma_commit(&empty[s]);                 // smem stage reusable once these MMAs retire
+                }
+                tc::umma_commit(&tmem_full[a]);                 // accumulator tile complete
+            }
+        }
+    } else if (warp >= 6) {
+        // ================= transform: fp32 -> (hi, lo) =================
+        const int tt = tid - 6 * 32;                            // 0..127
+        uint32_t it = 0;
+        for (long mt = cta_in_slice; mt < m_tiles; mt += p.ctas_per_slice) {
+            for (int kb = 0; kb < nkb; kb++, it++) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                tc::mbar_wait(&full_raw[s], ph);
+                float4 *hi = reinterpret_cast<float4 *>(Abase + (size_t)(2 * s) * A_TILE_BYTES);
+                float4 *lo = reinterpret_cast<float4 *>(Abase + (size_t)(2 * s + 1) * A_TILE_BYTES);
+#pragma unroll
+                for (int i = 0; i < ((p.dbg & 1) ? 0 : A_TILE_BYTES / 16 / 128); i++) {
+                    const int c = tt + 128 * i;
+                    const float4 v = hi[c];
+                    float4 h, l;
+                    h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); l.x = v.x - h.x;
+                    h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); l.y = v.y - h.y;
+                    h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); l.z = v.z - h.z;
+                    h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); l.w = v.w - h.w;
+                    hi[c] = h;
+                    lo[c] = l;
+                }
+                tc::fence_proxy_async();                        // generic-proxy writes -> visible to the tensor core
+                tc::mbar_arrive(&full_split[s]);
+            }
+        }
+    } else {
+        // ================= epilogue (warps 0-3: TMEM lanes 32*warp .. +31) =================
+        float *stg = stg_all + warp * 32 * STG_LD;
+        uint32_t tile = 0;
+        for (long mt = cta_in_slice; mt < m_tiles; mt += p.ctas_per_slice, tile++) {
+            const int a = tile % NACC;
+            const uint32_t aph = (tile / NACC) & 1;
+            tc::mbar_wait(&tmem_full[a], aph);
+            tc::tc_fence_after();
+            const long row0 = mt * BM + warp * 32;
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                const int width = (BN - c0) >= 32 ? 32 : 16;
+                uint32_t v[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * BN + c0);
+                if (width == 32) tc::tmem_ld_32x32b_x32(taddr, v);
+                else tc::tmem_ld_32x32b_x16(taddr, v);
+                tc::tmem_ld_wait();
+                if (c0 + 32 >= BN) {                             // last read of this accumulator: hand it back
+                    tc::tc_fence_before();
+                    tc::mbar_arrive(&tmem_empty[a]);
+                }
+                // thread = row: bias + activation, then 8 x 128-bit writes into the staging tile
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    if (i < width) {
+                        float4 o;
+                        o.x = apply_act_t<ACT>(__uint_as_float(v[i + 0]) + bias_s[c0 + i + 0]);
+                        o.y = apply_act_t<ACT>(__uint_as_float(v[i + 1]) + bias_s[c0 + i + 1]);
+                        o.z = apply_act_t<ACT>(__uint_as_float(v[i + 2]) + bias_s[c0 + i + 2]);
+                        o.w = apply_act_t<ACT>(__uint_as_float(v[i + 3]) + bias_s[c0 + i + 3]);
+                        *reinterpret_cast<float4 *>(&stg[lane * STG_LD + i]) = o;
+                    }
+                }
+                __syncwarp();
+                if (!(p.dbg & 2)) {
+                    if (p.vec_out) {
+                        // 8 lanes x float4 cover the 32 columns of one row: 4 rows (4 x 128 B) per instruction
+                        const int cq = (lane & 7) * 4, rsub = lane >> 3;
+                        const int n = n0 + c0 + cq;
+                        if (cq < width && n < p.N) {
+#pragma unroll
+                            for (int r4 = 0; r4 < 8; r4++) {
+                                const int r = r4 * 4 + rsub;
+                                const long m = row0 + r;
+                                if (m < p.M) {
+                                    const float4 o = *reinterpret_cast<const float4 *>(&stg[r * STG_LD + cq]);
+                                    float *dst = p.y + m * p.ldy + n;
+                                    if (n + 3 < p.N) {
+                                        *reinterpret_cast<float4 *>(dst) = o;
+                                    } else {
+                                        dst[0] = o.x;
+                                        if (n + 1 < p.N) dst[1] = o.y;
+                                        if (n + 2 < p.N) dst[2] = o.z;
+                                    }
+                                }
+                            }
+                        }
+                    } else {
+                        const int n = n0 + c0 + lane;
+                        if (lane < width && n < p.N) {
+#pragma unroll 8
+                            for (int r = 0; r < 32; r++) {
+                                const long m = row0 + r;
+                                if (m < p.M) p.y[m * p.ldy + n] = stg[r * STG_LD + lane];
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    }
+
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 5) {
+        tc::tc_fence_after();
+        tc::tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// ---- host side ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+// Returns SLOIKA_ERR_UNSUPPORTED when the shape/alignment cannot use the tensor path (caller falls back).
+int launch(const float *x, long ldx, const float *W, const float *bias, float *y, long ldy, long M, int K, int N,
+           int act, cudaStream_t st)
+{
+    if ((ldx & 3) != 0 || ((uintptr_t)x & 15) != 0 || K > 256 || M < BM || M > 0x7fffffffL) return SLOIKA_ERR_UNSUPPORTED;
+    EncodeTiledFn enc = encode_fn();
+    if (!enc) return SLOIKA_ERR_UNSUPPORTED;
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return SLOIKA_ERR_UNSUPPORTED;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) return SLOIKA_ERR_UNSUPPORTED;
+
+    const int nkb = (K + KB - 1) / KB;
+    // widest slice whose (hi, lo) weights fit beside (at least) 3 x stages in 227 KB of shared memory
+    int bn_max = 256;
+    const char *bn_env = getenv("SLOIKA_B200_GEMM_BN");
+    if (bn_env && atoi(bn_env) >= 16) bn_max = atoi(bn_env) / 16 * 16;
+    while (bn_max >= 16 && smem_bytes(bn_max, nkb, 3) > 227 * 1024) bn_max -= 16;
+    if (bn_max < 16) return SLOIKA_ERR_UNSUPPORTED;
+    const int n_slices = (N + bn_max - 1) / bn_max;
+    int BN = ((N + n_slices - 1) / n_slices + 15) / 16 * 16;
+    if (n_slices > sms) return SLOIKA_ERR_UNSUPPORTED;
+
+    CUtensorMap tmap;
+    const cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)M};
+    const cuuint64_t gstride[1] = {(cuuint64_t)ldx * 4};
+    const cuuint32_t box[2] = {(cuuint32_t)KB, (cuuint32_t)BM};
+    const cuuint32_t estr[2] = {1, 1};
+    if (enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(x), gdim, gstride, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return SLOIKA_ERR_UNSUPPORTED;
+
+    Params p;
+    p.W = W; p.bias = bias; p.y = y; p.ldy = ldy; p.M = M; p.K = K; p.N = N; p.act = act;
+    p.BN = BN; p.n_slices = n_slices; p.nkb = nkb;
+    p.vec_out = ((ldy & 3) == 0) && (((uintptr_t)y & 15) == 0);
+    const char *dbg = getenv("SLOIKA_B200_GEMM_DBG");
+    p.dbg = dbg ? atoi(dbg) : 0;
+    const long m_tiles = (M + BM - 1) / BM;
+    long per = sms / n_slices;
+    if (per > m_tiles) per = m_tiles;
+    p.ctas_per_slice = (int)per;
+    int stages = 3;
+    while (stages < MAX_STAGES && smem_bytes(BN, nkb, stages + 1) <= 227 * 1024) stages++;
+    p.stages = stages;
+    const size_t smem = smem_bytes(BN, nkb, stages);
+    const unsigned grid = (unsigned)(n_slices * p.ctas_per_slice);
+#define LAUNCH_ACT(A)                                                                                              \
+    case A: {                                                                                                      \
+        cudaError_t err = cudaFuncSetAttribute(gemm_tf32x3_kernel<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                               (int)smem);                                                         \
+        if (err != cudaSuccess) return (int)err;                                                                   \
+        gemm_tf32x3_kernel<A><<<grid, THREADS, smem, st>>>(tmap, p);                                               \
+        break;                                                                                                     \
+    }
+    switch (act) {
+        LAUNCH_ACT(SLOIKA_ACT_LINEAR)
+        LAUNCH_ACT(SLOIKA_ACT_TANH)
+        LAUNCH_ACT(SLOIKA_ACT_SIGMOID)
+        LAUNCH_ACT(SLOIKA_ACT_ELU)
+        default: return SLOIKA_ERR_UNSUPPORTED;
+    }
+#undef LAUNCH_ACT
+    SLOIKA_RETURN_LAUNCH_STATUS();
+}
+
+}  // namespace gemm_tc
+}  // namespace sloika

@@ -20,6 +20,7 @@
 //     step t+6 is prefetched into L2.
 //
 // Latency-bound by design (T dependent steps); per step a CTA issues 6*H^2*BT FMAs.
+#include <cstdlib>
 #include "common.cuh"
 
 namespace sloika {
@@ -309,6 +310,11 @@ static int launch_gru(const float *vI, const float *sW, const float *sW2, float 
     SLOIKA_RETURN_LAUNCH_STATUS();
 }
 
+namespace gru2 {
+int dispatch(const float *vI, const float *sW, const float *sW2, float *y, long ldy, const int32_t *lengths, int T, int B,
+             int H, int reverse, int act, int gate_act, cudaStream_t st);
+}
+
 }  // namespace sloika
 
 using namespace sloika;
@@ -321,6 +327,13 @@ extern "C" int sloika_gru_recurrence_fwd(const float *vI, const float *sW, const
     if (!act_known(act) || !act_known(gate_act)) return SLOIKA_ERR_UNSUPPORTED;
     if (T == 0) return SLOIKA_OK;
     cudaStream_t st = (cudaStream_t)stream;
+    {   // register-resident kernel (gru_v2.cu) where it covers the size; SLOIKA_B200_GRU=v1 forces the first kernel
+        const char *sel = getenv("SLOIKA_B200_GRU");
+        if (!(sel && sel[0] == 'v' && sel[1] == '1')) {
+            const int rc = gru2::dispatch(vI, sW, sW2, y, ldy, lengths, T, B, H, reverse, act, gate_act, st);
+            if (rc != SLOIKA_ERR_UNSUPPORTED) return rc;
+        }
+    }
 #define GRU_CASE(HP_, S_, W2R_) \
     return launch_gru<HP_, S_, W2R_>(vI, sW, sW2, y, ldy, lengths, T, B, H, reverse, act, gate_act, st)
     if (H <= 16) GRU_CASE(16, 4, 0);

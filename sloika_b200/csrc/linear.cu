@@ -147,9 +147,36 @@ static int launch_linear(const float *x, long ldx, const float *W, const float *
     SLOIKA_RETURN_LAUNCH_STATUS();
 }
 
+namespace gemm_tc {
+int launch(const float *x, long ldx, const float *W, const float *bias, float *y, long ldy, long M, int K, int N,
+           int act, cudaStream_t st);
+}
+
+// algo: SLOIKA_GEMM_AUTO tries the tcgen05 3xTF32 kernel and falls back to the fp32 SIMT kernel when the
+// shape or alignment rules it out; SLOIKA_GEMM_SIMT / SLOIKA_GEMM_TC force one of them.
+static int dispatch_linear(const float *x, long ldx, const float *W, const float *bias, float *y, long ldy, long M,
+                           int K, int N, int act, int algo, cudaStream_t st)
+{
+    if (algo != SLOIKA_GEMM_SIMT) {
+        const int rc = gemm_tc::launch(x, ldx, W, bias, y, ldy, M, K, N, act, st);
+        if (rc != SLOIKA_ERR_UNSUPPORTED || algo == SLOIKA_GEMM_TC) return rc;
+    }
+    return launch_linear(x, ldx, W, bias, y, ldy, M, K, N, act, st);
+}
+
 }  // namespace sloika
 
 using namespace sloika;
+
+extern "C" int sloika_linear_fwd_ex(const float *x, long ldx, const float *W, const float *bias, float *y, long ldy,
+                                    long M, int K, int N, int act, int algo, void *stream)
+{
+    if (!x || !W || !y || M < 0 || K <= 0 || N <= 0 || ldx < K || ldy < N) return SLOIKA_ERR_ARG;
+    if (algo < SLOIKA_GEMM_AUTO || algo > SLOIKA_GEMM_TC) return SLOIKA_ERR_ARG;
+    if (!act_known(act)) return SLOIKA_ERR_UNSUPPORTED;
+    if (M == 0) return SLOIKA_OK;
+    return dispatch_linear(x, ldx, W, bias, y, ldy, M, K, N, act, algo, (cudaStream_t)stream);
+}
 
 extern "C" int sloika_linear_fwd(const float *x, long ldx, const float *W, const float *bias, float *y, long ldy,
                                  long M, int K, int N, int act, void *stream)
@@ -157,7 +184,7 @@ extern "C" int sloika_linear_fwd(const float *x, long ldx, const float *W, const
     if (!x || !W || !y || M < 0 || K <= 0 || N <= 0 || ldx < K || ldy < N) return SLOIKA_ERR_ARG;
     if (!act_known(act)) return SLOIKA_ERR_UNSUPPORTED;
     if (M == 0) return SLOIKA_OK;
-    return launch_linear(x, ldx, W, bias, y, ldy, M, K, N, act, (cudaStream_t)stream);
+    return dispatch_linear(x, ldx, W, bias, y, ldy, M, K, N, act, SLOIKA_GEMM_AUTO, (cudaStream_t)stream);
 }
 
 extern "C" int sloika_softmax_fwd(const float *x, long ldx, const float *W, const float *bias, float *post,
@@ -166,7 +193,7 @@ extern "C" int sloika_softmax_fwd(const float *x, long ldx, const float *W, cons
     if (!x || !W || !post || M < 0 || K <= 0 || N <= 0 || ldx < K || ldp < N) return SLOIKA_ERR_ARG;
     if (M == 0) return SLOIKA_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    int rc = launch_linear(x, ldx, W, bias, post, ldp, M, K, N, SLOIKA_ACT_LINEAR, st);
+    int rc = dispatch_linear(x, ldx, W, bias, post, ldp, M, K, N, SLOIKA_ACT_LINEAR, SLOIKA_GEMM_AUTO, st);
     if (rc != SLOIKA_OK) return rc;
     const int warps = 8;
     const long blocks = ceil_div(M, warps);

@@ -260,3 +260,58 @@ def test_error_codes_surface_as_exceptions():
     g = layers.Gru(8, 200, has_bias=True)                                   # H > 144: no kernel yet
     with pytest.raises(cabi.SloikaB200Error):
         _run(g, np.zeros((4, 2, 8), dtype=np.float32))
+
+
+# ------------------------------------------------------------------ tcgen05 3xTF32 GEMM vs fp32 SIMT vs float64
+def _linear_abi(x, W, b, act_code, algo, ldy=None):
+    lib = cabi.load()
+    M, K = x.shape
+    N = W.shape[0]
+    ldy = ldy or N
+    xd, Wd = torch.from_numpy(x).to(DEV), torch.from_numpy(W).to(DEV)
+    bd = None if b is None else torch.from_numpy(b).to(DEV)
+    y = torch.full((M, ldy), -7.0, dtype=torch.float32, device=DEV)
+    rc = lib.sloika_linear_fwd_ex(cabi.ptr(xd), K, cabi.ptr(Wd), cabi.ptr(bd), cabi.ptr(y), ldy, M, K, N, act_code, algo,
+                                  cabi.stream_ptr(torch.device(DEV)))
+    torch.cuda.synchronize()
+    return rc, y.cpu().numpy()
+
+
+@pytest.mark.parametrize('M,K,N,act_code', [(4096, 96, 288, 0), (1000, 96, 288, 1), (128, 96, 96, 0), (777, 128, 336, 0),
+                                            (3000, 112, 432, 0), (2500, 144, 336, 2), (2048, 96, 1025, 0),
+                                            (640, 32, 96, 3), (513, 40, 50, 0), (300, 8, 16, 0), (20000, 192, 128, 1),
+                                            (1500, 256, 300, 0)])
+def test_tensor_core_gemm_matches_fp32(M, K, N, act_code):
+    rng = np.random.default_rng(M + K + N)
+    x = np.tanh(rng.standard_normal((M, K))).astype(np.float32)
+    W = (rng.standard_normal((N, K)) * 1.5).astype(np.float32)          # trained-model-like magnitudes
+    b = rng.standard_normal(N).astype(np.float32)
+    rc, y_tc = _linear_abi(x, W, b, act_code, 2)
+    assert rc == 0
+    rc, y_simt = _linear_abi(x, W, b, act_code, 1)
+    assert rc == 0
+    exact = x.astype(np.float64) @ W.astype(np.float64).T + b
+    fun = {0: lambda v: v, 1: np.tanh, 2: lambda v: 1 / (1 + np.exp(-v)), 3: lambda v: np.where(v > 0, v, np.expm1(np.minimum(v, 0)))}[act_code]
+    exact = fun(exact)
+    err_tc = np.abs(y_tc - exact).max()
+    err_simt = np.abs(y_simt - exact).max()
+    scale = np.abs(exact).max()
+    # the 3xTF32 split must be as good as plain fp32 accumulation (both ~1e-6 relative to the row scale)
+    assert err_tc <= max(4 * err_simt, 4e-6 * scale), (err_tc, err_simt, scale)
+
+
+def test_tensor_core_gemm_column_slice_and_fallback():
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal((512, 64)).astype(np.float32)
+    W = rng.standard_normal((48, 64)).astype(np.float32)
+    rc, y = _linear_abi(x, W, None, 0, 2, ldy=100)                     # writes only its 48 columns of 100
+    assert rc == 0
+    np.testing.assert_allclose(y[:, :48], x @ W.T, atol=2e-4)
+    assert np.all(y[:, 48:] == -7.0)
+    xo = rng.standard_normal((512, 110)).astype(np.float32)            # ld not a multiple of 4: no TMA
+    Wo = rng.standard_normal((30, 110)).astype(np.float32)
+    rc, _ = _linear_abi(xo, Wo, None, 0, 2)
+    assert rc == -2                                                    # forced TC refuses
+    rc, y = _linear_abi(xo, Wo, None, 0, 0)                            # AUTO falls back to SIMT
+    assert rc == 0
+    np.testing.assert_allclose(y, xo @ Wo.T, atol=2e-4)
