@@ -244,8 +244,8 @@ def run_b200_arm(args):
     samples_per_step = T * B
 
     def step_device():
-        out = calc_post.forward_device(x_dev)
-        return decode.viterbi_batch(out.data, None, klen=5, skip_pen=0.0, min_prob=1e-5, return_device=True)
+        out = calc_post.forward_device(x_dev, fused_decode=True)
+        return decode.viterbi_batch(out, None, klen=5, skip_pen=0.0, min_prob=1e-5, return_device=True)
 
     def step_e2e():
         return basecall.basecall_chunks(x_host, kmer_len=5, min_prob=1e-5, skip=0.0, network=calc_post)

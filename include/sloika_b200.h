@@ -88,6 +88,22 @@ int sloika_softmax_fwd(const float *x, long ldx, const float *W, const float *bi
                        long M, int K, int N, void *stream);
 
 /*
+ * Softmax.run split for the fused basecall path (tensor-core kernel only).
+ *   sloika_softmax_slices        number of column slices S the kernel uses for (K, N); 0 = use sloika_softmax_fwd
+ *   sloika_softmax_logits_fwd    logits t = x . W' + bias (row distance ldl, ldl % 4 == 0 recommended) and
+ *                                stats[(row*S + s)*2 + {0,1}] = (max_j t_j, sum_j exp(t_j - max)) over slice s.
+ *                                stay_last != 0 writes the columns rotated by one: k-mer states first, the stay /
+ *                                blank state (reference column 0) in column N-1 -- the layout the decoder reads.
+ *   sloika_softmax_normalise_fwd logits -> posteriors in place: exp(t - M) / S_row with the row maximum M and
+ *                                row sum S_row combined from the slice pairs (layers.py:311-314)
+ */
+int sloika_softmax_slices(int K, int N);
+int sloika_softmax_logits_fwd(const float *x, long ldx, const float *W, const float *bias, float *logits, long ldl,
+                              float *stats, long M, int K, int N, int stay_last, void *stream);
+int sloika_softmax_normalise_fwd(float *logits, long ldl, const float *stats, int n_slices, long M, int N,
+                                 void *stream);
+
+/*
  * Gru.step scanned over time by RNN.run -- sloika/layers.py:1010-1021, :85-88 (h0 = 0); with
  * `reverse` != 0 it is Reverse(Gru).run (layers.py:1449-1450): each sequence is walked from its own
  * last valid step down to 0 and outputs land at their original time index.
@@ -128,6 +144,18 @@ int sloika_viterbi_fwd(const float *post, long ld_t, long ld_b, const int32_t *l
                        int nbase, int klen, double skip_pen, double min_prob, int mode, void *tb_ws,
                        size_t ws_bytes, int32_t *path_out, int32_t *path_len, float *score_out,
                        void *stream);
+
+/*
+ * Same decode fed by the un-normalised network output of sloika_softmax_logits_fwd(stay_last = 1):
+ * the softmax division (layers.py:314), the min_prob floor (decode.py:36) and the log (decode.py:56) are
+ * applied inside the kernel, so the posterior matrix never exists in HBM.  nbase = 4, klen = 5 only.
+ *   logits: element (t, b, j) at logits[t*ld_t + b*ld_b + j], j < 1024 k-mer states, j = 1024 stay;
+ *   stats: [T*B][n_slices] float pairs as written by sloika_softmax_logits_fwd.
+ */
+int sloika_viterbi_logits_fwd(const float *logits, long ld_t, long ld_b, const float *stats, int n_slices,
+                              const int32_t *lengths, int T, int B, int nbase, int klen, double skip_pen,
+                              double min_prob, void *tb_ws, size_t ws_bytes, int32_t *path_out, int32_t *path_len,
+                              float *score_out, void *stream);
 
 #ifdef __cplusplus
 }

@@ -71,9 +71,8 @@ def basecall_signals(signals, kmer_len=5, min_prob=1e-5, skip=0.0, nbase=4, netw
     for b, s in enumerate(signals):
         host[:len(s), b] = torch.from_numpy(np.ascontiguousarray(s, dtype=np.float32))
     x = host.to(dev, non_blocking=True).unsqueeze(2)
-    out = net.forward_device(x, torch.from_numpy(lens).to(dev))
-    score, paths = decode.viterbi_batch(out.data, out.lengths, klen=kmer_len, skip_pen=skip,
-                                        min_prob=min_prob, nbase=nbase)
+    out = net.forward_device(x, torch.from_numpy(lens).to(dev), fused_decode=(kmer_len == 5 and nbase == 4))
+    score, paths = decode.viterbi_batch(out, None, klen=kmer_len, skip_pen=skip, min_prob=min_prob, nbase=nbase)
     return list(zip(score.tolist(), paths))
 
 
@@ -91,8 +90,8 @@ def basecall_chunks(x_host, kmer_len=5, min_prob=1e-5, skip=0.0, nbase=4, networ
     if x_host.dim() == 2:
         x_host = x_host.unsqueeze(2)
     x = x_host.to(net.device, non_blocking=True)
-    out = net.forward_device(x)
-    score, paths, plen = decode.viterbi_batch(out.data, None, klen=kmer_len, skip_pen=skip, min_prob=min_prob,
+    out = net.forward_device(x, fused_decode=(kmer_len == 5 and nbase == 4))
+    score, paths, plen = decode.viterbi_batch(out, None, klen=kmer_len, skip_pen=skip, min_prob=min_prob,
                                               nbase=nbase, return_device=True)
     return score.cpu().numpy(), paths.cpu().numpy(), plen.cpu().numpy()
 

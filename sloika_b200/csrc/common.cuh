@@ -45,6 +45,25 @@ __device__ __forceinline__ float apply_act_t(float x) {
     else return x;
 }
 
+// Fast variants for the latency-bound recurrence epilogue: MUFU ex2 / rcp based, absolute error ~1e-7
+// (relative 2^-21 on the exponential), three orders of magnitude inside the 1e-4 posterior budget.
+__device__ __forceinline__ float sigmoid_fast(float x) {
+    float y = __fdividef(1.0f, 1.0f + __expf(-x));
+    y = x < -88.0f ? 0.0f : y;
+    return x > 15.0f ? 1.0f : y;
+}
+__device__ __forceinline__ float tanh_fast(float x) {
+    const float xc = fminf(fmaxf(x, -30.0f), 30.0f);          // keep exp finite; tanh(+-30) == +-1 in fp32
+    return 1.0f - __fdividef(2.0f, 1.0f + __expf(2.0f * xc));
+}
+template <int ACT>
+__device__ __forceinline__ float apply_act_fast(float x) {
+    if constexpr (ACT == SLOIKA_ACT_TANH) return tanh_fast(x);
+    else if constexpr (ACT == SLOIKA_ACT_SIGMOID) return sigmoid_fast(x);
+    else if constexpr (ACT == SLOIKA_ACT_ELU) return x > 0.0f ? x : (__expf(x) - 1.0f);
+    else return x;
+}
+
 __host__ inline bool act_known(int act) { return act >= SLOIKA_ACT_LINEAR && act <= SLOIKA_ACT_ELU; }
 
 __host__ __device__ __forceinline__ long ceil_div(long a, long b) { return (a + b - 1) / b; }

@@ -44,6 +44,8 @@ struct Params {
     long M;
     int K, N, act;
     int BN, n_slices, ctas_per_slice, nkb;
+    float2 *stats;    // optional [M][n_slices] (row max, sum of exp(t - max)) of each row's slice, for the softmax
+    int rot;          // output column n is computed from weight/bias row (n + rot) % N  (stay-last logits layout)
     int stages;       // smem pipeline depth
     int vec_out;      // rows of y are 16-byte aligned: 128-bit stores
     int dbg;          // timing experiments only (SLOIKA_B200_GEMM_DBG): 1 no split math, 2 no stores, 4 no MMA
@@ -58,7 +60,7 @@ __host__ __device__ inline size_t smem_bytes(int BN, int nkb, int stages)
     return w + a + stg + misc + 1024;                      // + alignment slack
 }
 
-template <int ACT>
+template <int ACT, bool STATS>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params p)
 {
@@ -97,13 +99,13 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params p)
     for (int e = tid; e < BN * nkb * KB; e += THREADS) {
         const int k = e % (nkb * KB), n = e / (nkb * KB);
         float w = 0.0f;
-        if (n0 + n < p.N && k < p.K) w = __ldg(p.W + (long)(n0 + n) * p.K + k);
+        if (n0 + n < p.N && k < p.K) w = __ldg(p.W + (long)((n0 + n + p.rot) % p.N) * p.K + k);
         const float hi = __uint_as_float(__float_as_uint(w) & 0xffffe000u);
         const uint32_t off = (uint32_t)(k / KB) * (uint32_t)(BN * 128) + tc::sw128_offset(n, k % KB);
         *reinterpret_cast<float *>(Whi + off) = hi;
         *reinterpret_cast<float *>(Wlo + off) = w - hi;
     }
-    for (int n = tid; n < BN; n += THREADS) bias_s[n] = (p.bias && n0 + n < p.N) ? __ldg(p.bias + n0 + n) : 0.0f;
+    for (int n = tid; n < BN; n += THREADS) bias_s[n] = (p.bias && n0 + n < p.N) ? __ldg(p.bias + (n0 + n + p.rot) % p.N) : 0.0f;
     tc::fence_proxy_async();
     tc::tc_fence_before();
     __syncthreads();
@@ -199,6 +201,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params p)
             tc::mbar_wait(&tmem_full[a], aph);
             tc::tc_fence_after();
             const long row0 = mt * BM + warp * 32;
+            float m_run = -INFINITY, s_run = 0.0f;              // STATS: online (max, sum exp) of this thread's row
             for (int c0 = 0; c0 < BN; c0 += 32) {
                 const int width = (BN - c0) >= 32 ? 32 : 16;
                 uint32_t v[32];
@@ -220,6 +223,26 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params p)
                         o.z = apply_act_t<ACT>(__uint_as_float(v[i + 2]) + bias_s[c0 + i + 2]);
                         o.w = apply_act_t<ACT>(__uint_as_float(v[i + 3]) + bias_s[c0 + i + 3]);
                         *reinterpret_cast<float4 *>(&stg[lane * STG_LD + i]) = o;
+                        if constexpr (STATS) {                   // park the values for the reduction below
+                            v[i + 0] = __float_as_uint(o.x); v[i + 1] = __float_as_uint(o.y);
+                            v[i + 2] = __float_as_uint(o.z); v[i + 3] = __float_as_uint(o.w);
+                        }
+                    }
+                }
+                if constexpr (STATS) {
+                    const int nvalid = min(width, p.N - (n0 + c0));      // padded columns must not enter the max
+                    float cm = -INFINITY;
+#pragma unroll
+                    for (int i = 0; i < 32; i++)
+                        if (i < nvalid) cm = fmaxf(cm, __uint_as_float(v[i]));
+                    if (nvalid > 0) {
+                        const float nm = fmaxf(m_run, cm);
+                        float acc = 0.0f;
+#pragma unroll
+                        for (int i = 0; i < 32; i++)
+                            if (i < nvalid) acc += __expf(__uint_as_float(v[i]) - nm);
+                        s_run = s_run * __expf(m_run - nm) + acc;
+                        m_run = nm;
                     }
                 }
                 __syncwarp();
@@ -259,6 +282,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params p)
                 }
                 __syncwarp();
             }
+            if constexpr (STATS) {
+                const long m = row0 + lane;
+                if (m < p.M) p.stats[m * p.n_slices + slice] = make_float2(m_run, s_run);
+            }
         }
     }
 
@@ -291,8 +318,23 @@ static EncodeTiledFn encode_fn()
 }
 
 // Returns SLOIKA_ERR_UNSUPPORTED when the shape/alignment cannot use the tensor path (caller falls back).
+// Column slices the kernel would use for (K, N) (0 = shape not supported): lets callers size `stats`.
+int plan_slices(int K, int N, int *bn_out)
+{
+    if (K <= 0 || K > 256 || N <= 0) return 0;
+    const int nkb = (K + KB - 1) / KB;
+    int bn_max = 256;
+    const char *bn_env = getenv("SLOIKA_B200_GEMM_BN");
+    if (bn_env && atoi(bn_env) >= 16) bn_max = atoi(bn_env) / 16 * 16;
+    while (bn_max >= 16 && smem_bytes(bn_max, nkb, 3) > 227 * 1024) bn_max -= 16;
+    if (bn_max < 16) return 0;
+    const int n_slices = (N + bn_max - 1) / bn_max;
+    if (bn_out) *bn_out = ((N + n_slices - 1) / n_slices + 15) / 16 * 16;
+    return n_slices;
+}
+
 int launch(const float *x, long ldx, const float *W, const float *bias, float *y, long ldy, long M, int K, int N,
-           int act, cudaStream_t st)
+           int act, float2 *stats, int rot, cudaStream_t st)
 {
     if ((ldx & 3) != 0 || ((uintptr_t)x & 15) != 0 || K > 256 || M < BM || M > 0x7fffffffL) return SLOIKA_ERR_UNSUPPORTED;
     EncodeTiledFn enc = encode_fn();
@@ -304,14 +346,10 @@ int launch(const float *x, long ldx, const float *W, const float *bias, float *y
 
     const int nkb = (K + KB - 1) / KB;
     // widest slice whose (hi, lo) weights fit beside (at least) 3 x stages in 227 KB of shared memory
-    int bn_max = 256;
-    const char *bn_env = getenv("SLOIKA_B200_GEMM_BN");
-    if (bn_env && atoi(bn_env) >= 16) bn_max = atoi(bn_env) / 16 * 16;
-    while (bn_max >= 16 && smem_bytes(bn_max, nkb, 3) > 227 * 1024) bn_max -= 16;
-    if (bn_max < 16) return SLOIKA_ERR_UNSUPPORTED;
-    const int n_slices = (N + bn_max - 1) / bn_max;
-    int BN = ((N + n_slices - 1) / n_slices + 15) / 16 * 16;
-    if (n_slices > sms) return SLOIKA_ERR_UNSUPPORTED;
+    int BN = 0;
+    const int n_slices = plan_slices(K, N, &BN);
+    if (n_slices <= 0 || n_slices > sms) return SLOIKA_ERR_UNSUPPORTED;
+    if (stats && act != SLOIKA_ACT_LINEAR) return SLOIKA_ERR_UNSUPPORTED;
 
     CUtensorMap tmap;
     const cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)M};
@@ -326,6 +364,7 @@ int launch(const float *x, long ldx, const float *W, const float *bias, float *y
     Params p;
     p.W = W; p.bias = bias; p.y = y; p.ldy = ldy; p.M = M; p.K = K; p.N = N; p.act = act;
     p.BN = BN; p.n_slices = n_slices; p.nkb = nkb;
+    p.stats = stats; p.rot = rot;
     p.vec_out = ((ldy & 3) == 0) && (((uintptr_t)y & 15) == 0);
     const char *dbg = getenv("SLOIKA_B200_GEMM_DBG");
     p.dbg = dbg ? atoi(dbg) : 0;
@@ -338,13 +377,20 @@ int launch(const float *x, long ldx, const float *W, const float *bias, float *y
     p.stages = stages;
     const size_t smem = smem_bytes(BN, nkb, stages);
     const unsigned grid = (unsigned)(n_slices * p.ctas_per_slice);
-#define LAUNCH_ACT(A)                                                                                              \
-    case A: {                                                                                                      \
-        cudaError_t err = cudaFuncSetAttribute(gemm_tf32x3_kernel<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                               (int)smem);                                                         \
-        if (err != cudaSuccess) return (int)err;                                                                   \
-        gemm_tf32x3_kernel<A><<<grid, THREADS, smem, st>>>(tmap, p);                                               \
-        break;                                                                                                     \
+#define LAUNCH_ACT(A)                                                                                         \
+    case A: {                                                                                                 \
+        cudaError_t err = cudaFuncSetAttribute(gemm_tf32x3_kernel<A, false>,                                  \
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
+        if (err != cudaSuccess) return (int)err;                                                              \
+        gemm_tf32x3_kernel<A, false><<<grid, THREADS, smem, st>>>(tmap, p);                                   \
+        break;                                                                                                \
+    }
+    if (stats) {
+        cudaError_t err = cudaFuncSetAttribute(gemm_tf32x3_kernel<SLOIKA_ACT_LINEAR, true>,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return (int)err;
+        gemm_tf32x3_kernel<SLOIKA_ACT_LINEAR, true><<<grid, THREADS, smem, st>>>(tmap, p);
+        SLOIKA_RETURN_LAUNCH_STATUS();
     }
     switch (act) {
         LAUNCH_ACT(SLOIKA_ACT_LINEAR)

@@ -80,11 +80,11 @@ struct Cfg {
 };
 
 // W1REG: sW (2H x H) register resident (else read from shared memory every step); sW2 always in registers.
-template <int HP, bool W1REG>
+template <int HP, bool W1REG, int ACT, int GATE>
 __global__ void __launch_bounds__(THREADS, 1)
 gru_recurrence_v2_kernel(const float *__restrict__ vI, const float *__restrict__ sW, const float *__restrict__ sW2,
                          float *__restrict__ y, long ldy, const int32_t *__restrict__ lengths, int T, int B, int H,
-                         int reverse, int act, int gate_act)
+                         int reverse)
 {
     using C = Cfg<HP>;
     constexpr int RPT = C::RPT, NG = C::NG, HP4 = HP / 4, VLD = C::VLD;
@@ -220,8 +220,8 @@ gru_recurrence_v2_kernel(const float *__restrict__ vI, const float *__restrict__
 #pragma unroll
         for (int i = 0; i < RPT; i++) {
             const int j = j0 + i;
-            const float z = apply_act(pre1[i] + vrow[j], gate_act);
-            const float r = apply_act(pre1[RPT + i] + vrow[H + j], gate_act);
+            const float z = apply_act_fast<GATE>(pre1[i] + vrow[j]);
+            const float r = apply_act_fast<GATE>(pre1[RPT + i] + vrow[H + j]);
             zg[i] = z;
             if (j < H) rh[b_own * HP + j] = r * h_own[i];
         }
@@ -262,7 +262,7 @@ gru_recurrence_v2_kernel(const float *__restrict__ vI, const float *__restrict__
 #pragma unroll
         for (int i = 0; i < RPT; i++) {
             const int j = j0 + i;
-            const float hbar = apply_act(pre2[i] + vrow[2 * H + j], act);
+            const float hbar = apply_act_fast<ACT>(pre2[i] + vrow[2 * H + j]);
             float hn = zg[i] * h_own[i] + (1.0f - zg[i]) * hbar;
             hn = (live && j < H) ? hn : 0.0f;
             h_own[i] = hn;
@@ -293,11 +293,13 @@ static int launch(const float *vI, const float *sW, const float *sW2, float *y, 
 {
     using C = Cfg<HP>;
     const size_t smem = sizeof(float) * ((size_t)2 * BT * HP + (size_t)2 * BT * C::VLD + (W1REG ? 0 : (size_t)2 * HP * HP));
-    auto kern = gru_recurrence_v2_kernel<HP, W1REG>;
+    // the models on the path use tanh / sigmoid (every models/*.py); other pairs go to the generic kernel
+    if (act != SLOIKA_ACT_TANH || gate_act != SLOIKA_ACT_SIGMOID) return SLOIKA_ERR_UNSUPPORTED;
+    auto kern = gru_recurrence_v2_kernel<HP, W1REG, SLOIKA_ACT_TANH, SLOIKA_ACT_SIGMOID>;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return (int)err;
     const unsigned grid = (unsigned)ceil_div(B, BT);
-    kern<<<grid, THREADS, smem, st>>>(vI, sW, sW2, y, ldy, lengths, T, B, H, reverse, act, gate_act);
+    kern<<<grid, THREADS, smem, st>>>(vI, sW, sW2, y, ldy, lengths, T, B, H, reverse);
     SLOIKA_RETURN_LAUNCH_STATUS();
 }
 

@@ -135,6 +135,39 @@ softmax_rows_kernel(float *__restrict__ post, long ldp, long M, int N)
     for (int j = lane; j < N; j += 32) p[j] = p[j] / s;
 }
 
+// post = exp(t - M) / S in place, from the per-slice (max, sum exp) pairs written by the GEMM epilogue:
+// M = max_s m_s, S = sum_s s_s * exp(m_s - M)  (layers.py:311-314 with the row reductions pre-computed).
+// One warp per row; rows are 16-byte aligned (ldp % 4 == 0) so the bulk moves as float4.
+__global__ void __launch_bounds__(256)
+softmax_normalise_kernel(float *__restrict__ post, long ldp, const float2 *__restrict__ stats, int n_slices, long M, int N)
+{
+    const int lane = threadIdx.x & 31;
+    const long row = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= M) return;
+    float m = -INFINITY, s = 0.0f;
+    if (lane < n_slices) {
+        const float2 st = __ldg(stats + row * n_slices + lane);
+        m = st.x;
+        s = st.y;
+    }
+    float mx = m;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float tot = lane < n_slices ? s * expf(m - mx) : 0.0f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+    float *p = post + row * ldp;
+    const int n4 = N >> 2;
+    float4 *p4 = reinterpret_cast<float4 *>(p);
+    for (int c = lane; c < n4; c += 32) {
+        float4 v = p4[c];
+        v.x = expf(v.x - mx) / tot; v.y = expf(v.y - mx) / tot;
+        v.z = expf(v.z - mx) / tot; v.w = expf(v.w - mx) / tot;
+        p4[c] = v;
+    }
+    for (int j = 4 * n4 + lane; j < N; j += 32) p[j] = expf(p[j] - mx) / tot;
+}
+
 static int launch_linear(const float *x, long ldx, const float *W, const float *bias, float *y, long ldy, long M,
                          int K, int N, int act, cudaStream_t st)
 {
@@ -148,8 +181,9 @@ static int launch_linear(const float *x, long ldx, const float *W, const float *
 }
 
 namespace gemm_tc {
+int plan_slices(int K, int N, int *bn_out);
 int launch(const float *x, long ldx, const float *W, const float *bias, float *y, long ldy, long M, int K, int N,
-           int act, cudaStream_t st);
+           int act, float2 *stats, int rot, cudaStream_t st);
 }
 
 // algo: SLOIKA_GEMM_AUTO tries the tcgen05 3xTF32 kernel and falls back to the fp32 SIMT kernel when the
@@ -158,7 +192,7 @@ static int dispatch_linear(const float *x, long ldx, const float *W, const float
                            int K, int N, int act, int algo, cudaStream_t st)
 {
     if (algo != SLOIKA_GEMM_SIMT) {
-        const int rc = gemm_tc::launch(x, ldx, W, bias, y, ldy, M, K, N, act, st);
+        const int rc = gemm_tc::launch(x, ldx, W, bias, y, ldy, M, K, N, act, nullptr, 0, st);
         if (rc != SLOIKA_ERR_UNSUPPORTED || algo == SLOIKA_GEMM_TC) return rc;
     }
     return launch_linear(x, ldx, W, bias, y, ldy, M, K, N, act, st);
@@ -185,6 +219,37 @@ extern "C" int sloika_linear_fwd(const float *x, long ldx, const float *W, const
     if (!act_known(act)) return SLOIKA_ERR_UNSUPPORTED;
     if (M == 0) return SLOIKA_OK;
     return dispatch_linear(x, ldx, W, bias, y, ldy, M, K, N, act, SLOIKA_GEMM_AUTO, (cudaStream_t)stream);
+}
+
+extern "C" int sloika_softmax_slices(int K, int N)
+{
+    if (N > 32 * 256) return 0;
+    const int n = gemm_tc::plan_slices(K, N, nullptr);
+    return n > 32 ? 0 : n;
+}
+
+extern "C" int sloika_softmax_logits_fwd(const float *x, long ldx, const float *W, const float *bias, float *logits,
+                                         long ldl, float *stats, long M, int K, int N, int stay_last, void *stream)
+{
+    if (!x || !W || !logits || !stats || M < 0 || K <= 0 || N <= 0 || ldx < K || ldl < N) return SLOIKA_ERR_ARG;
+    if (M == 0) return SLOIKA_OK;
+    if (sloika_softmax_slices(K, N) <= 0) return SLOIKA_ERR_UNSUPPORTED;
+    return gemm_tc::launch(x, ldx, W, bias, logits, ldl, M, K, N, SLOIKA_ACT_LINEAR, reinterpret_cast<float2 *>(stats),
+                           stay_last ? 1 : 0, (cudaStream_t)stream);
+}
+
+extern "C" int sloika_softmax_normalise_fwd(float *logits, long ldl, const float *stats, int n_slices, long M, int N,
+                                            void *stream)
+{
+    if (!logits || !stats || M < 0 || N <= 0 || ldl < N || n_slices <= 0 || n_slices > 32) return SLOIKA_ERR_ARG;
+    if ((ldl & 3) != 0 || ((uintptr_t)logits & 15) != 0) return SLOIKA_ERR_UNSUPPORTED;
+    if (M == 0) return SLOIKA_OK;
+    const int warps = 8;
+    const long blocks = ceil_div(M, warps);
+    if (blocks > 0x7fffffffL) return SLOIKA_ERR_ARG;
+    softmax_normalise_kernel<<<(unsigned)blocks, warps * 32, 0, (cudaStream_t)stream>>>(
+        logits, ldl, reinterpret_cast<const float2 *>(stats), n_slices, M, N);
+    SLOIKA_RETURN_LAUNCH_STATUS();
 }
 
 extern "C" int sloika_softmax_fwd(const float *x, long ldx, const float *W, const float *bias, float *post,

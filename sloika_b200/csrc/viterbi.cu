@@ -18,6 +18,8 @@
 // log-posteriors scores and paths are bit-identical.
 //
 // HBM-bound: 4*(K+1) bytes of posterior read + K bytes of traceback written per event.
+#include <cmath>
+#include <cstdlib>
 #include "common.cuh"
 
 namespace sloika {
@@ -163,6 +165,204 @@ viterbi_kernel(const float *__restrict__ post, long ld_t, long ld_b, const int32
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// Specialisation for the basecaller's shape: 4 bases, k = 5 -> K = 1024 states, 256 threads, thread r
+// owns states 4r..4r+3.  Compile-time strides (immediate shared-memory offsets), 128-bit accesses to
+// the own-state quads of v (the generic kernel's stride-4 scalar accesses cost 46 % of its
+// shared-memory wavefronts in bank conflicts), log-posterior row of the NEXT event fetched while the
+// current one is processed.
+//   IN_POST / IN_LOG : rows laid out [stay, kmer 0..1023] (the network's posterior layout), any stride
+//   IN_LOGITS        : rows laid out [kmer 0..1023, stay] (16-byte aligned), un-normalised logits plus
+//                      the per-slice (max, sum exp) pairs of the softmax GEMM epilogue; the softmax
+//                      division, the min_prob floor and the log are all applied here, so the
+//                      posterior matrix is never written to HBM on the fused basecall path.
+constexpr int IN_POST = 0, IN_LOG = 1, IN_LOGITS = 2;
+
+template <int MODE>
+__global__ void __launch_bounds__(256)
+viterbi_k1024_kernel(const float *__restrict__ post, long ld_t, long ld_b, const float2 *__restrict__ stats, int n_slices,
+                     const int32_t *__restrict__ lengths, int T, int B, float skip_pen, float c0, float c1,
+                     float skip_below, uint8_t *__restrict__ tb, int32_t *__restrict__ path_out,
+                     int32_t *__restrict__ path_len, float *__restrict__ score_out)
+{
+    constexpr int K = 1024, RS = 256, RK = 64;
+    __shared__ __align__(16) float vbuf[2][K];
+    __shared__ float2 ms_s[2];                       // (row max, row sum) of the softmax, double buffered
+    __shared__ float red_v[8];
+    __shared__ int red_i[8];
+    __shared__ int s_best;
+
+    const int b = blockIdx.x;
+    const int r = threadIdx.x;
+    const int nev = lengths ? min(lengths[b], T) : T;
+    if (nev < 1) {
+        if (r == 0) { path_len[b] = 0; score_out[b] = 0.0f; }
+        return;
+    }
+    const float *pb = post + (long)b * ld_b;
+    uint8_t *tbb = tb + (size_t)b * (size_t)T * (size_t)K;
+    const float lp_floor = logf(__fadd_rn(c0, VIT_ETA));
+
+    // softmax row statistics of event i -> ms_s[i & 1] (warp 0; visible after the next barrier)
+    auto row_stats = [&](int i) {
+        if (MODE != IN_LOGITS || r >= 32) return;
+        float m = -INFINITY, s = 0.0f;
+        if (r < n_slices) {
+            const float2 st = __ldg(stats + ((long)i * B + b) * n_slices + r);
+            m = st.x;
+            s = st.y;
+        }
+        float mx = m;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float tot = r < n_slices ? s * expf(m - mx) : 0.0f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+        if (r == 0) ms_s[i & 1] = make_float2(mx, tot);
+    };
+    // raw row values of event i for this thread: 4 k-mer columns + the stay column
+    auto fetch = [&](int i, float (&x)[4], float &x0) {
+        const float *row = pb + (long)i * ld_t;
+        if (MODE == IN_LOGITS) {
+            const float4 q = __ldg(reinterpret_cast<const float4 *>(row) + r);
+            x[0] = q.x; x[1] = q.y; x[2] = q.z; x[3] = q.w;
+            x0 = __ldg(row + K);
+        } else {
+            x[0] = __ldg(row + 1 + 4 * r); x[1] = __ldg(row + 2 + 4 * r);
+            x[2] = __ldg(row + 3 + 4 * r); x[3] = __ldg(row + 4 + 4 * r);
+            x0 = __ldg(row);
+        }
+    };
+    auto lpost_of = [&](float v, float2 ms) -> float {
+        if (MODE == IN_LOG) return v;
+        if (MODE == IN_LOGITS) {
+            const float d = v - ms.x;
+            if (d < skip_below) return lp_floor;                 // p below half an ulp of min_prob: exact shortcut
+            v = __fdiv_rn(expf(d), ms.y);                        // Softmax.run: exp(t - m) / rowsum
+        }
+        return logf(__fadd_rn(__fadd_rn(c0, __fmul_rn(c1, v)), VIT_ETA));
+    };
+
+    float xn[4], xn0;
+    row_stats(0);
+    fetch(0, xn, xn0);
+    __syncthreads();
+    {
+        const float2 ms = ms_s[0];
+        float4 v0;
+        v0.x = lpost_of(xn[0], ms); v0.y = lpost_of(xn[1], ms); v0.z = lpost_of(xn[2], ms); v0.w = lpost_of(xn[3], ms);
+        reinterpret_cast<float4 *>(vbuf[0])[r] = v0;             // v_0 = lpost[0][1:]   (decode.py:57)
+    }
+    if (nev > 1) { row_stats(1); fetch(1, xn, xn0); }
+    __syncthreads();
+
+    int cur = 0;
+    for (int i = 1; i < nev; i++) {
+        float x[4] = {xn[0], xn[1], xn[2], xn[3]};
+        const float x0 = xn0;
+        const float2 ms = ms_s[i & 1];
+        if (i + 1 < nev) { row_stats(i + 1); fetch(i + 1, xn, xn0); }   // next event, off the critical path
+        const float *p = vbuf[cur];
+        const float lp0 = lpost_of(x0, ms);
+        // step: first maximum over a of p[a*256 + r]
+        float ss = p[r];
+        int as = 0;
+#pragma unroll
+        for (int a = 1; a < 4; a++) {
+            const float c = p[a * RS + r];
+            if (c > ss) { ss = c; as = a; }
+        }
+        // skip: first maximum over a of p[a*64 + r/4]
+        const int q = r >> 2;
+        float sk = p[q];
+        int ak = 0;
+#pragma unroll
+        for (int a = 1; a < 16; a++) {
+            const float c = p[a * RK + q];
+            if (c > sk) { sk = c; ak = a; }
+        }
+        sk = __fsub_rn(sk, skip_pen);
+        const bool use_step = ss > sk;                               // tie -> skip (decode.py:76)
+        const float best = use_step ? ss : sk;
+        const unsigned code = use_step ? (1u + as) : (5u + ak);
+        const float4 pv = reinterpret_cast<const float4 *>(p)[r];
+        const float pj[4] = {pv.x, pv.y, pv.z, pv.w};
+        float vo[4];
+        unsigned packed = 0;
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const float move = __fadd_rn(lpost_of(x[c], ms), best);
+            const float stay = __fadd_rn(pj[c], lp0);
+            const bool mv = move > stay;                             // tie -> stay (decode.py:81)
+            vo[c] = mv ? move : stay;
+            packed |= (mv ? code : 0u) << (8 * c);
+        }
+        reinterpret_cast<float4 *>(vbuf[cur ^ 1])[r] = make_float4(vo[0], vo[1], vo[2], vo[3]);
+        reinterpret_cast<unsigned *>(tbb + (size_t)i * K)[r] = packed;
+        cur ^= 1;
+        __syncthreads();
+    }
+
+    // ---- argmax of v_T (first maximum), backtrace, left-align: as in the generic kernel ----
+    const float *v = vbuf[cur];
+    float bv = -INFINITY;
+    int bi = 0x7fffffff;
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        const float val = v[4 * r + c];
+        if (val > bv) { bv = val; bi = 4 * r + c; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    if ((r & 31) == 0) { red_v[r >> 5] = bv; red_i[r >> 5] = bi; }
+    __syncthreads();
+    if (r == 0) {
+        for (int w = 1; w < 8; w++)
+            if (red_v[w] > bv || (red_v[w] == bv && red_i[w] < bi)) { bv = red_v[w]; bi = red_i[w]; }
+        score_out[b] = bv;
+        int32_t *out = path_out + (size_t)b * T;
+        int pos = nev - 1;
+        int state = bi;
+        out[pos] = state;
+        for (int i = nev - 1; i > 0; i--) {
+            const unsigned cd = tbb[(size_t)i * K + state];
+            if (cd != 0) {
+                state = cd <= 4u ? (int)(cd - 1) * RS + (state >> 2) : (int)(cd - 5) * RK + (state >> 4);
+                out[--pos] = state;
+            }
+        }
+        path_len[b] = nev - pos;
+        s_best = pos;
+    }
+    __syncthreads();
+    const int off = s_best;
+    const int n = nev - off;
+    if (off > 0) {
+        int32_t *out = path_out + (size_t)b * T;
+        for (int base = 0; base < n; base += 256) {
+            const int idx = base + r;
+            int32_t val = 0;
+            if (idx < n) val = out[off + idx];
+            __syncthreads();
+            if (idx < n) out[idx] = val;
+            __syncthreads();
+        }
+    }
+}
+
+// d below which p = exp(d)/S (<= exp(d), S >= 1) cannot change min_prob + (1-min_prob)*p in float32
+static float logits_skip_threshold(float c0, float c1)
+{
+    if (!(c0 > 0.0f) || !(c1 > 0.0f)) return -INFINITY;
+    const float half_ulp = 0.5f * (nextafterf(c0, 2.0f * c0) - c0);
+    return logf(half_ulp / c1) - 0.5f;
+}
+
 static bool ipow_ok(int nbase, int klen, long *K)
 {
     long k = 1;
@@ -206,6 +406,15 @@ extern "C" int sloika_viterbi_fwd(const float *post, long ld_t, long ld_b, const
     long threads = K / nbase;
     threads = threads > 256 ? 256 : (threads < 32 ? 32 : ceil_div(threads, 32) * 32);
     cudaError_t err;
+    if (nbase == 4 && K == 1024 && !getenv("SLOIKA_B200_VITERBI_GENERIC")) {
+        if (mode == SLOIKA_VIT_POST)
+            viterbi_k1024_kernel<IN_POST><<<B, 256, 0, st>>>(post, ld_t, ld_b, nullptr, 0, lengths, T, B, sp, c0, c1,
+                                                              -INFINITY, (uint8_t *)tb_ws, path_out, path_len, score_out);
+        else
+            viterbi_k1024_kernel<IN_LOG><<<B, 256, 0, st>>>(post, ld_t, ld_b, nullptr, 0, lengths, T, B, sp, c0, c1,
+                                                             -INFINITY, (uint8_t *)tb_ws, path_out, path_len, score_out);
+        SLOIKA_RETURN_LAUNCH_STATUS();
+    }
     if (nbase == 4) {
         err = cudaFuncSetAttribute(viterbi_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return (int)err;
@@ -219,5 +428,22 @@ extern "C" int sloika_viterbi_fwd(const float *post, long ld_t, long ld_b, const
                                                              c0, c1, mode, (uint8_t *)tb_ws, path_out, path_len,
                                                              score_out);
     }
+    SLOIKA_RETURN_LAUNCH_STATUS();
+}
+
+extern "C" int sloika_viterbi_logits_fwd(const float *logits, long ld_t, long ld_b, const float *stats, int n_slices,
+                                         const int32_t *lengths, int T, int B, int nbase, int klen, double skip_pen,
+                                         double min_prob, void *tb_ws, size_t ws_bytes, int32_t *path_out,
+                                         int32_t *path_len, float *score_out, void *stream)
+{
+    if (!logits || !stats || !path_out || !path_len || !score_out || T <= 0 || B <= 0 || n_slices <= 0 || n_slices > 32)
+        return SLOIKA_ERR_ARG;
+    if (nbase != 4 || klen != 5) return SLOIKA_ERR_UNSUPPORTED;          // K = 1024 specialisation only
+    if ((ld_t & 3) != 0 || (ld_b & 3) != 0 || ((uintptr_t)logits & 15) != 0) return SLOIKA_ERR_UNSUPPORTED;
+    if (!tb_ws || ws_bytes < sloika_viterbi_workspace_bytes(T, B, nbase, klen)) return SLOIKA_ERR_WORKSPACE;
+    const float c0 = (float)min_prob, c1 = (float)(1.0 - min_prob), sp = (float)skip_pen;
+    viterbi_k1024_kernel<IN_LOGITS><<<B, 256, 0, (cudaStream_t)stream>>>(
+        logits, ld_t, ld_b, reinterpret_cast<const float2 *>(stats), n_slices, lengths, T, B, sp, c0, c1,
+        logits_skip_threshold(c0, c1), (uint8_t *)tb_ws, path_out, path_len, score_out);
     SLOIKA_RETURN_LAUNCH_STATUS();
 }

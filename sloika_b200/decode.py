@@ -59,7 +59,12 @@ def viterbi_batch(post, lengths=None, klen=5, skip_pen=0.0, min_prob=1e-5, nbase
         `(scores, paths[B, T], path_len[B])` when `return_device`
     """
     import torch
+    from sloika_b200 import engine
     lib = cabi.load()
+    if isinstance(post, engine.LogitsAct):
+        return _viterbi_logits(post, klen, skip_pen, min_prob, nbase, return_device)
+    if isinstance(post, engine.Act):
+        post, lengths = post.data, (post.lengths if lengths is None else lengths)
     post = _as_device(post)
     assert post.dim() == 3, "post must be [time, batch, state]"
     T, B, S = post.shape
@@ -91,6 +96,34 @@ def viterbi_batch(post, lengths=None, klen=5, skip_pen=0.0, min_prob=1e-5, nbase
     score_h = score.cpu().numpy()
     plen_h = plen.cpu().numpy()
     paths_h = paths.cpu().numpy()
+    return score_h, [paths_h[b, :plen_h[b]].tolist() for b in range(B)]
+
+
+def _viterbi_logits(la, klen, skip_pen, min_prob, nbase, return_device):
+    """Decode straight from the final layer's logits + row statistics (`engine.LogitsAct`)."""
+    import torch
+    from sloika_b200.engine import launch
+    lib = cabi.load()
+    data = la.data
+    T, B, S = data.shape
+    assert klen >= 3, "Kmer not long enough to apply Viterbi with skips"
+    assert sv.nstate(klen, transducer=True, nbase=nbase) == S
+    dev = data.device
+    ld_t = data.stride(0) if T > 1 else B * data.stride(1)
+    ld_b = data.stride(1)
+    with torch.cuda.device(dev):
+        nbytes = lib.sloika_viterbi_workspace_bytes(T, B, nbase, klen)
+        tb = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=dev)
+        paths = torch.empty((B, max(T, 1)), dtype=torch.int32, device=dev)
+        plen = torch.empty(B, dtype=torch.int32, device=dev)
+        score = torch.empty(B, dtype=torch.float32, device=dev)
+        launch('viterbi', 1, lib.sloika_viterbi_logits_fwd,
+               cabi.ptr(data), ld_t, ld_b, cabi.ptr(la.stats), la.n_slices, cabi.ptr(la.lengths), T, B, nbase, klen,
+               float(skip_pen), float(min_prob), cabi.ptr(tb), nbytes, cabi.ptr(paths), cabi.ptr(plen),
+               cabi.ptr(score), cabi.stream_ptr(dev))
+    if return_device:
+        return score, paths, plen
+    score_h, plen_h, paths_h = score.cpu().numpy(), plen.cpu().numpy(), paths.cpu().numpy()
     return score_h, [paths_h[b, :plen_h[b]].tolist() for b in range(B)]
 
 

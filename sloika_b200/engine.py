@@ -158,14 +158,67 @@ def run_feedforward(layer, act, out=None):
     return act.like(y)
 
 
-def run_softmax(layer, act, out=None):
+def _padded_rows(T, B, F, device):
+    """[T, B, F] view of a buffer whose rows are padded to a multiple of 4 floats (16-byte aligned rows
+    let the kernels use 128-bit accesses; 1025 posterior columns become a pitch of 1028)."""
+    pitch = (F + 3) // 4 * 4
+    return _empty((T, B, pitch), device)[:, :, :F]
+
+
+class LogitsAct(object):
+    """Un-normalised output of the final Softmax layer in the decoder's layout: `data[t, b, :]` holds the
+    k-mer state logits first and the stay/blank logit LAST, `stats[t*B + b, s]` the (max, sum exp) pair
+    of column slice s.  Produced by `run_softmax_logits`, consumed by `decode.viterbi_batch`; the
+    posterior matrix itself is never materialised on this path."""
+
+    def __init__(self, data, stats, n_slices, lengths):
+        self.data, self.stats, self.n_slices, self.lengths = data, stats, n_slices, lengths
+
+
+def _softmax_tc_ok(lib, layer, act):
+    return act.ld % 4 == 0 and act.data.data_ptr() % 16 == 0 and act.T * act.B >= 128 and \
+        lib.sloika_softmax_slices(layer.insize, layer.size) > 0
+
+
+def run_softmax_logits(layer, act):
+    """Final Softmax for the fused basecall path: logits + row statistics (see LogitsAct); None when the
+    tensor-core kernel cannot take this shape (caller falls back to `run_softmax`)."""
+    import torch
     lib = cabi.load()
     assert act.F == layer.insize
-    y = _out_buffer(act, act.T, layer.size, out)
+    if not _softmax_tc_ok(lib, layer, act):
+        return None
     dev = act.device
-    launch('softmax', 2, lib.sloika_softmax_fwd,
+    nsl = lib.sloika_softmax_slices(layer.insize, layer.size)
+    y = _padded_rows(act.T, act.B, layer.size, dev)
+    stats = torch.empty((act.T * act.B, nsl, 2), dtype=torch.float32, device=dev)
+    launch('softmax', 1, lib.sloika_softmax_logits_fwd,
            cabi.ptr(act.data), act.ld, cabi.ptr(layer.W.device(dev)), cabi.ptr(layer.b.device(dev)),
-           cabi.ptr(y), _row_stride(y), act.T * act.B, layer.insize, layer.size, cabi.stream_ptr(dev))
+           cabi.ptr(y), _row_stride(y), cabi.ptr(stats), act.T * act.B, layer.insize, layer.size, 1,
+           cabi.stream_ptr(dev))
+    return LogitsAct(y, stats, nsl, act.lengths)
+
+
+def run_softmax(layer, act, out=None):
+    import torch
+    lib = cabi.load()
+    assert act.F == layer.insize
+    dev = act.device
+    y = out if out is not None else _padded_rows(act.T, act.B, layer.size, dev)
+    ldy = _row_stride(y)
+    if _softmax_tc_ok(lib, layer, act) and ldy % 4 == 0 and y.data_ptr() % 16 == 0:
+        # tensor-core logits + per-slice row statistics, then one normalising pass (read + write)
+        nsl = lib.sloika_softmax_slices(layer.insize, layer.size)
+        stats = torch.empty((act.T * act.B, nsl, 2), dtype=torch.float32, device=dev)
+        launch('softmax', 1, lib.sloika_softmax_logits_fwd,
+               cabi.ptr(act.data), act.ld, cabi.ptr(layer.W.device(dev)), cabi.ptr(layer.b.device(dev)),
+               cabi.ptr(y), ldy, cabi.ptr(stats), act.T * act.B, layer.insize, layer.size, 0, cabi.stream_ptr(dev))
+        launch('softmax_normalise', 1, lib.sloika_softmax_normalise_fwd,
+               cabi.ptr(y), ldy, cabi.ptr(stats), nsl, act.T * act.B, layer.size, cabi.stream_ptr(dev))
+    else:
+        launch('softmax', 2, lib.sloika_softmax_fwd,
+               cabi.ptr(act.data), act.ld, cabi.ptr(layer.W.device(dev)), cabi.ptr(layer.b.device(dev)),
+               cabi.ptr(y), ldy, act.T * act.B, layer.insize, layer.size, cabi.stream_ptr(dev))
     return act.like(y)
 
 
@@ -248,9 +301,14 @@ class CompiledNetwork(object):
         self._device = torch.device(device)
         return self
 
-    def forward_device(self, x, lengths=None):
-        """x: float32 CUDA tensor [T, B, F] (dense); lengths: optional int32 CUDA tensor [B]."""
+    def forward_device(self, x, lengths=None, fused_decode=False):
+        """x: float32 CUDA tensor [T, B, F] (dense); lengths: optional int32 CUDA tensor [B].
+
+        With `fused_decode` the final Softmax layer hands un-normalised logits + row statistics to the
+        decoder (`LogitsAct`) instead of writing posteriors; only `decode.viterbi_batch` understands
+        that form.  Falls back to posteriors when the network or shape does not allow it."""
         import torch
+        from sloika_b200 import layers as L
         cabi.load()
         if x.dtype != torch.float32 or x.dim() != 3:
             raise TypeError("calc_post expects a float32 [time, batch, feature] tensor")
@@ -258,7 +316,16 @@ class CompiledNetwork(object):
         if lengths is not None:
             lengths = lengths.to(device=x.device, dtype=torch.int32).contiguous()
         with torch.cuda.device(x.device):
-            out = self.network.run(Act(x, lengths))
+            net = self.network
+            if fused_decode and isinstance(net, L.Serial) and isinstance(net.layers[-1], L.Softmax):
+                act = Act(x, lengths)
+                for layer in net.layers[:-1]:
+                    act = layer.run(act)
+                out = run_softmax_logits(net.layers[-1], act)
+                if out is None:
+                    out = net.layers[-1].run(act)
+            else:
+                out = net.run(Act(x, lengths))
         return out
 
     def __call__(self, inMat, lengths=None):

@@ -315,3 +315,57 @@ def test_tensor_core_gemm_column_slice_and_fallback():
     rc, y = _linear_abi(xo, Wo, None, 0, 0)                            # AUTO falls back to SIMT
     assert rc == 0
     np.testing.assert_allclose(y, xo @ Wo.T, atol=2e-4)
+
+
+# ------------------------------------------------------------------ fused softmax -> Viterbi (logits + row statistics)
+def test_fused_logits_decode_equals_posterior_decode():
+    """The fused basecall path (final layer emits logits + per-slice (max, sum exp), the decoder applies
+    softmax division, min_prob floor and log itself) must give the same paths as decoding the
+    materialised posteriors, for dense and ragged batches."""
+    np.random.seed(21)
+    net = zoo.raw_rgrgr()
+    net.layers[-1].W.set_value(net.layers[-1].W.get_value() * 4)        # peaky posteriors like a trained model
+    calc = net.compile()
+    x = torch.randn((1500, 9, 1), device=DEV)
+    lengths = torch.tensor([1500, 1, 7, 640, 1499, 12, 300, 1000, 5], dtype=torch.int32, device=DEV)
+    for lens in (None, lengths):
+        std = calc.forward_device(x, lens)
+        fused = calc.forward_device(x, lens, fused_decode=True)
+        assert isinstance(fused, engine.LogitsAct)
+        s1, p1 = decode.viterbi_batch(std, None, min_prob=1e-5)
+        s2, p2 = decode.viterbi_batch(fused, None, min_prob=1e-5)
+        assert p1 == p2
+        np.testing.assert_allclose(s1, s2, rtol=1e-5, atol=1e-3)
+        # and both agree with the oracle decoding the same posteriors
+        post = std.data.cpu().numpy()
+        nev = std.lengths.cpu().numpy() if lens is not None else [post.shape[0]] * post.shape[1]
+        for b in (0, 3):
+            s_ref, p_ref = decode_ref.decode_post(post[:nev[b], b:b + 1], 5, 1e-5, skip=0.0)
+            assert p_ref == p1[b]
+    # min_prob = 0 disables the exact floor shortcut
+    s3, p3 = decode.viterbi_batch(calc.forward_device(x, None, fused_decode=True), None, min_prob=0.0)
+    s4, p4 = decode.viterbi_batch(calc.forward_device(x, None), None, min_prob=0.0)
+    assert p3 == p4
+
+
+def test_softmax_normalise_matches_oracle_with_stay_column():
+    np.random.seed(22)
+    layer = layers.Softmax(96, 1025, init=_init(), has_bias=True)
+    layer.W.set_value(layer.W.get_value() * 8)
+    x = np.tanh(np.random.standard_normal((70, 4, 96))).astype(np.float32)
+    got = _run(layer, x)[0]
+    ref = _oracle(layer, x)
+    assert got.shape == ref.shape and np.abs(got - ref).max() < 2e-5
+    a = engine.Act(torch.from_numpy(x).to(DEV))
+    la = engine.run_softmax_logits(layer, a)
+    torch.cuda.synchronize()
+    logits = la.data.cpu().numpy()
+    W, b = layer.W.get_value().astype(np.float64), layer.b.get_value().astype(np.float64)
+    exact = x.astype(np.float64) @ W.T + b
+    np.testing.assert_allclose(logits[:, :, :1024], exact[:, :, 1:], atol=2e-4)    # k-mer states first
+    np.testing.assert_allclose(logits[:, :, 1024], exact[:, :, 0], atol=2e-4)      # stay last
+    st = la.stats.cpu().numpy().reshape(70, 4, la.n_slices, 2)
+    m = st[..., 0].max(-1)
+    s = (st[..., 1] * np.exp(st[..., 0] - m[..., None])).sum(-1)
+    np.testing.assert_allclose(m, exact.max(-1), atol=2e-4)
+    np.testing.assert_allclose(s, np.exp(exact - exact.max(-1, keepdims=True)).sum(-1), rtol=1e-4)
