@@ -10,15 +10,16 @@
 // lo = x - hi (exact), and three MMAs  hi.hi + lo.hi + hi.lo  are accumulated in fp32 in TMEM; the
 // dropped lo.lo term is 2^-22 relative.
 //
-// Structure (one persistent CTA per SM, 320 threads, warp specialised):
+// Structure (one persistent CTA per SM, 448 threads, warp specialised):
 //   grid = n_slices x ctas_per_slice; a CTA owns output columns [n0, n0 + BN) and walks m-tiles.
 //   prologue   all warps: W slice -> smem as W_hi / W_lo in the UMMA K-major SWIZZLE_128B layout
 //   warp 4     TMA producer: x tile [128 rows x 32 k] per stage (cp.async.bulk.tensor, SWIZZLE_128B)
 //   warps 6-9  transform: raw fp32 tile -> hi (in place) + lo, fence.proxy.async, signal
 //   warp 5     MMA issuer: 4 K-steps x 3 tcgen05.mma (M=128, N=BN, K=8) per stage, accumulators in
 //              TMEM (2 stages x BN columns); tcgen05.commit frees the smem stage / publishes the tile
-//   warps 0-3  epilogue: tcgen05.ld (thread = row), + bias, activation, transpose through smem,
-//              coalesced 128-byte row stores
+//   warps 0-3, 10-13  epilogue (two groups on alternate 32-column chunks): tcgen05.ld (thread = row),
+//              + bias, activation, optional softmax row statistics, transpose through smem,
+//              coalesced 128-bit row stores
 #include <cstdlib>
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -31,7 +32,7 @@ constexpr int BM = 128;            // rows per tile (UMMA M)
 constexpr int KB = 32;             // k elements per K block (one 128-byte swizzle row)
 constexpr int MAX_STAGES = 8;      // smem stages of (hi, lo) x-tiles (as many as fit)
 constexpr int NACC = 2;            // TMEM accumulator stages
-constexpr int THREADS = 320;
+constexpr int THREADS = 448;        // 14 warps: 0-3 + 10-13 epilogue, 4 TMA, 5 MMA, 6-9 transform
 constexpr int A_TILE_BYTES = BM * KB * 4;        // 16 KB
 constexpr int TMEM_COLS = 512;
 constexpr int STG_LD = 36;           // staging row pitch (floats): 16-byte aligned rows, conflict-free float4 phases
@@ -44,10 +45,11 @@ struct Params {
     long M;
     int K, N, act;
     int BN, n_slices, ctas_per_slice, nkb;
-    float2 *stats;    // optional [M][n_slices] (row max, sum of exp(t - max)) of each row's slice, for the softmax
+    float2 *stats;    // optional [M][n_slices][2] (row max, sum of exp(t - max)) per slice and epilogue group
     int rot;          // output column n is computed from weight/bias row (n + rot) % N  (stay-last logits layout)
     int stages;       // smem pipeline depth
     int vec_out;      // rows of y are 16-byte aligned: 128-bit stores
+    int direct;       // vec_out && store rows straight from registers (no smem transpose)
     int dbg;          // timing experiments only (SLOIKA_B200_GEMM_DBG): 1 no split math, 2 no stores, 4 no MMA
 };
 
@@ -55,7 +57,7 @@ __host__ __device__ inline size_t smem_bytes(int BN, int nkb, int stages)
 {
     size_t w = (size_t)2 * nkb * BN * 128;                 // W_hi + W_lo
     size_t a = (size_t)stages * 2 * A_TILE_BYTES;          // (hi, lo) per stage
-    size_t stg = (size_t)4 * 32 * STG_LD * 4;              // epilogue transpose buffers
+    size_t stg = (size_t)8 * 32 * STG_LD * 4;              // epilogue transpose buffers (one per epilogue warp)
     size_t misc = (size_t)BN * 4 + 512;                    // bias slice + barriers
     return w + a + stg + misc + 1024;                      // + alignment slack
 }
@@ -72,7 +74,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params p)
     uint8_t *Wlo = Whi + (size_t)nkb * BN * 128;
     uint8_t *Abase = Wlo + (size_t)nkb * BN * 128;                        // stage s: hi at 2s, lo at 2s+1
     float *stg_all = reinterpret_cast<float *>(Abase + (size_t)STAGES * 2 * A_TILE_BYTES);
-    float *bias_s = stg_all + 4 * 32 * STG_LD;
+    float *bias_s = stg_all + 8 * 32 * STG_LD;
     uint64_t *bars = reinterpret_cast<uint64_t *>(bias_s + BN);
     uint64_t *full_raw = bars;                     // [STAGES] TMA -> transform
     uint64_t *full_split = bars + MAX_STAGES;      // [STAGES] transform -> MMA
@@ -90,7 +92,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params p)
     // ---------------- prologue ----------------
     if (tid == 0) {
         for (int s = 0; s < STAGES; s++) { tc::mbar_init(&full_raw[s], 1); tc::mbar_init(&full_split[s], 128); tc::mbar_init(&empty[s], 1); }
-        for (int a = 0; a < NACC; a++) { tc::mbar_init(&tmem_full[a], 1); tc::mbar_init(&tmem_empty[a], 128); }
+        for (int a = 0; a < NACC; a++) { tc::mbar_init(&tmem_full[a], 1); tc::mbar_init(&tmem_empty[a], 256); }
         tc::mbar_fence_init();
     }
     if (warp == 4 && lane == 0) tc::tma_prefetch_desc(&tmap_x);
@@ -164,7 +166,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params p)
                 tc::umma_commit(&tmem_full[a]);                 // accumulator tile complete
             }
         }
-    } else if (warp >= 6) {
+    } else if (warp >= 6 && warp < 10) {
         // ================= transform: fp32 -> (hi, lo) =================
         const int tt = tid - 6 * 32;                            // 0..127
         uint32_t it = 0;
@@ -191,62 +193,99 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params p)
                 tc::mbar_arrive(&full_split[s]);
             }
         }
-    } else {
-        // ================= epilogue (warps 0-3: TMEM lanes 32*warp .. +31) =================
-        float *stg = stg_all + warp * 32 * STG_LD;
+    } else if (warp < 4 || warp >= 10) {
+        // ================= epilogue: two groups of 4 warps (0-3 and 10-13) =================
+        // A warp may only read the TMEM lane quarter 32*(warp % 4); the two groups take alternate
+        // 32-column chunks of the tile so that every scheduler has two epilogue warps to interleave.
+        const int eg = warp < 4 ? 0 : 1;
+        const int lq = warp & 3;
+        float *stg = stg_all + (eg * 4 + lq) * 32 * STG_LD;
+        const int nchunks = (BN + 31) / 32;
         uint32_t tile = 0;
         for (long mt = cta_in_slice; mt < m_tiles; mt += p.ctas_per_slice, tile++) {
             const int a = tile % NACC;
             const uint32_t aph = (tile / NACC) & 1;
             tc::mbar_wait(&tmem_full[a], aph);
             tc::tc_fence_after();
-            const long row0 = mt * BM + warp * 32;
+            const long row0 = mt * BM + lq * 32;
             float m_run = -INFINITY, s_run = 0.0f;              // STATS: online (max, sum exp) of this thread's row
-            for (int c0 = 0; c0 < BN; c0 += 32) {
+            bool released = false;
+            for (int ci = eg; ci < nchunks; ci += 2) {
+                const int c0 = ci * 32;
                 const int width = (BN - c0) >= 32 ? 32 : 16;
                 uint32_t v[32];
-                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(a * BN + c0);
+                const uint32_t taddr = tmem_base + ((uint32_t)(lq * 32) << 16) + (uint32_t)(a * BN + c0);
                 if (width == 32) tc::tmem_ld_32x32b_x32(taddr, v);
                 else tc::tmem_ld_32x32b_x16(taddr, v);
                 tc::tmem_ld_wait();
-                if (c0 + 32 >= BN) {                             // last read of this accumulator: hand it back
+                if (ci + 2 >= nchunks) {                         // last read of this accumulator: hand it back
                     tc::tc_fence_before();
                     tc::mbar_arrive(&tmem_empty[a]);
+                    released = true;
                 }
-                // thread = row: bias + activation, then 8 x 128-bit writes into the staging tile
+                // thread = row: bias + activation
+                float o[32];
 #pragma unroll
                 for (int i = 0; i < 32; i += 4) {
                     if (i < width) {
-                        float4 o;
-                        o.x = apply_act_t<ACT>(__uint_as_float(v[i + 0]) + bias_s[c0 + i + 0]);
-                        o.y = apply_act_t<ACT>(__uint_as_float(v[i + 1]) + bias_s[c0 + i + 1]);
-                        o.z = apply_act_t<ACT>(__uint_as_float(v[i + 2]) + bias_s[c0 + i + 2]);
-                        o.w = apply_act_t<ACT>(__uint_as_float(v[i + 3]) + bias_s[c0 + i + 3]);
-                        *reinterpret_cast<float4 *>(&stg[lane * STG_LD + i]) = o;
-                        if constexpr (STATS) {                   // park the values for the reduction below
-                            v[i + 0] = __float_as_uint(o.x); v[i + 1] = __float_as_uint(o.y);
-                            v[i + 2] = __float_as_uint(o.z); v[i + 3] = __float_as_uint(o.w);
+                        const float4 b4 = *reinterpret_cast<const float4 *>(&bias_s[c0 + i]);
+                        o[i + 0] = apply_act_t<ACT>(__uint_as_float(v[i + 0]) + b4.x);
+                        o[i + 1] = apply_act_t<ACT>(__uint_as_float(v[i + 1]) + b4.y);
+                        o[i + 2] = apply_act_t<ACT>(__uint_as_float(v[i + 2]) + b4.z);
+                        o[i + 3] = apply_act_t<ACT>(__uint_as_float(v[i + 3]) + b4.w);
+                        if (!p.direct)
+                            *reinterpret_cast<float4 *>(&stg[lane * STG_LD + i]) = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
+                    }
+                }
+                if (p.direct && !(p.dbg & 2)) {
+                    // thread = row: 128-bit stores straight from registers (each row is written 16 bytes at a
+                    // time by consecutive instructions of the same thread; L2 merges the sectors)
+                    const long m = row0 + lane;
+                    if (m < p.M) {
+                        float *dst = p.y + m * p.ldy + n0 + c0;
+#pragma unroll
+                        for (int i = 0; i < 32; i += 4) {
+                            if (i < width) {
+                                const int n = n0 + c0 + i;
+                                if (n + 3 < p.N) {
+                                    __stcs(reinterpret_cast<float4 *>(dst + i), make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]));
+                                } else {
+                                    if (n < p.N) dst[i] = o[i];
+                                    if (n + 1 < p.N) dst[i + 1] = o[i + 1];
+                                    if (n + 2 < p.N) dst[i + 2] = o[i + 2];
+                                }
+                            }
                         }
                     }
                 }
                 if constexpr (STATS) {
                     const int nvalid = min(width, p.N - (n0 + c0));      // padded columns must not enter the max
-                    float cm = -INFINITY;
+                    if (nvalid == 32) {
+                        float cm = o[0];
 #pragma unroll
-                    for (int i = 0; i < 32; i++)
-                        if (i < nvalid) cm = fmaxf(cm, __uint_as_float(v[i]));
-                    if (nvalid > 0) {
+                        for (int i = 1; i < 32; i++) cm = fmaxf(cm, o[i]);
+                        const float nm = fmaxf(m_run, cm);
+                        float acc0 = 0.0f, acc1 = 0.0f;
+#pragma unroll
+                        for (int i = 0; i < 32; i += 2) { acc0 += __expf(o[i] - nm); acc1 += __expf(o[i + 1] - nm); }
+                        s_run = s_run * __expf(m_run - nm) + (acc0 + acc1);
+                        m_run = nm;
+                    } else if (nvalid > 0) {
+                        float cm = -INFINITY;
+#pragma unroll
+                        for (int i = 0; i < 32; i++)
+                            if (i < nvalid) cm = fmaxf(cm, o[i]);
                         const float nm = fmaxf(m_run, cm);
                         float acc = 0.0f;
 #pragma unroll
                         for (int i = 0; i < 32; i++)
-                            if (i < nvalid) acc += __expf(__uint_as_float(v[i]) - nm);
+                            if (i < nvalid) acc += __expf(o[i] - nm);
                         s_run = s_run * __expf(m_run - nm) + acc;
                         m_run = nm;
                     }
                 }
                 __syncwarp();
-                if (!(p.dbg & 2)) {
+                if (!p.direct && !(p.dbg & 2)) {
                     if (p.vec_out) {
                         // 8 lanes x float4 cover the 32 columns of one row: 4 rows (4 x 128 B) per instruction
                         const int cq = (lane & 7) * 4, rsub = lane >> 3;
@@ -257,14 +296,14 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params p)
                                 const int r = r4 * 4 + rsub;
                                 const long m = row0 + r;
                                 if (m < p.M) {
-                                    const float4 o = *reinterpret_cast<const float4 *>(&stg[r * STG_LD + cq]);
+                                    const float4 q = *reinterpret_cast<const float4 *>(&stg[r * STG_LD + cq]);
                                     float *dst = p.y + m * p.ldy + n;
                                     if (n + 3 < p.N) {
-                                        *reinterpret_cast<float4 *>(dst) = o;
+                                        __stcs(reinterpret_cast<float4 *>(dst), q);
                                     } else {
-                                        dst[0] = o.x;
-                                        if (n + 1 < p.N) dst[1] = o.y;
-                                        if (n + 2 < p.N) dst[2] = o.z;
+                                        dst[0] = q.x;
+                                        if (n + 1 < p.N) dst[1] = q.y;
+                                        if (n + 2 < p.N) dst[2] = q.z;
                                     }
                                 }
                             }
@@ -282,9 +321,13 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params p)
                 }
                 __syncwarp();
             }
+            if (!released) {                                     // a group without chunks still frees the stage
+                tc::tc_fence_before();
+                tc::mbar_arrive(&tmem_empty[a]);
+            }
             if constexpr (STATS) {
                 const long m = row0 + lane;
-                if (m < p.M) p.stats[m * p.n_slices + slice] = make_float2(m_run, s_run);
+                if (m < p.M) p.stats[(m * p.n_slices + slice) * 2 + eg] = make_float2(m_run, s_run);
             }
         }
     }
@@ -366,6 +409,8 @@ int launch(const float *x, long ldx, const float *W, const float *bias, float *y
     p.BN = BN; p.n_slices = n_slices; p.nkb = nkb;
     p.stats = stats; p.rot = rot;
     p.vec_out = ((ldy & 3) == 0) && (((uintptr_t)y & 15) == 0);
+    const char *direct = getenv("SLOIKA_B200_GEMM_DIRECT");
+    p.direct = (p.vec_out && direct && atoi(direct) != 0) ? 1 : 0;
     const char *dbg = getenv("SLOIKA_B200_GEMM_DBG");
     p.dbg = dbg ? atoi(dbg) : 0;
     const long m_tiles = (M + BM - 1) / BM;

@@ -310,6 +310,10 @@ static int launch_gru(const float *vI, const float *sW, const float *sW2, float 
     SLOIKA_RETURN_LAUNCH_STATUS();
 }
 
+namespace gru3 {
+int dispatch(const float *vI, const float *sW, const float *sW2, float *y, long ldy, const int32_t *lengths, int T, int B,
+             int H, int reverse, int act, int gate_act, cudaStream_t st);
+}
 namespace gru2 {
 int dispatch(const float *vI, const float *sW, const float *sW2, float *y, long ldy, const int32_t *lengths, int T, int B,
              int H, int reverse, int act, int gate_act, cudaStream_t st);
@@ -327,9 +331,15 @@ extern "C" int sloika_gru_recurrence_fwd(const float *vI, const float *sW, const
     if (!act_known(act) || !act_known(gate_act)) return SLOIKA_ERR_UNSUPPORTED;
     if (T == 0) return SLOIKA_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    {   // register-resident kernel (gru_v2.cu) where it covers the size; SLOIKA_B200_GRU=v1 forces the first kernel
+    {   // kernel generations, newest first: mma.sync tensor-core kernel (gru_mma.cu, H <= 96), register-resident
+        // FFMA2 kernel (gru_v2.cu), shared-memory FFMA2 kernel (this file).  SLOIKA_B200_GRU=v1|v2 caps the choice.
         const char *sel = getenv("SLOIKA_B200_GRU");
-        if (!(sel && sel[0] == 'v' && sel[1] == '1')) {
+        const int cap = (sel && sel[0] == 'v' && sel[1] >= '1' && sel[1] <= '3') ? sel[1] - '0' : 3;
+        if (cap >= 3) {
+            const int rc = gru3::dispatch(vI, sW, sW2, y, ldy, lengths, T, B, H, reverse, act, gate_act, st);
+            if (rc != SLOIKA_ERR_UNSUPPORTED) return rc;
+        }
+        if (cap >= 2) {
             const int rc = gru2::dispatch(vI, sW, sW2, y, ldy, lengths, T, B, H, reverse, act, gate_act, st);
             if (rc != SLOIKA_ERR_UNSUPPORTED) return rc;
         }

@@ -1,0 +1,361 @@
+// GRU recurrence on the tensor cores (warp-level mma.sync, 3xTF32 split = fp32-equivalent accuracy).
+//
+// Same semantics and CTA decomposition as gru.cu / gru_v2.cu (one persistent CTA per 8 sequences, all of
+// sW | sW2 on chip, two CTA barriers per step; reference sloika/layers.py:1010-1021, :85-88, :1449-1450).
+// Why a third kernel: measurements on B200 (tools/*_probe.cu, profiles/) showed
+//   * the FFMA2 kernels are bounded by register-delivery of h from shared memory (every lane must
+//     receive all 8 x H state values per phase: 128 B/clk/SM) plus ~1.4 us/step of shuffle / barrier /
+//     epilogue latency -> 2.7 us/step;
+//   * tcgen05.mma costs >= ~56 cycles per instruction however small N is, so 8 sequences per CTA cannot
+//     feed it (108 MMAs/step -> 6k cycles);
+//   * legacy mma.sync.m16n8k8.tf32 sustains one MMA per 2.16 cycles per SM with 23 cycles latency, and
+//     its operand fragments cut the shared-memory traffic of a step to two 4-byte loads per k-chunk.
+//
+// Layout: rows of a gate are cut in 16-row tiles (jt); warp (jt, role) holds the A fragments (weights)
+// of its tiles in REGISTERS for the whole scan:
+//     role 0 ("owner")  z tile of sW in phase 1, c tile of sW2 in phase 2, keeps z and h in registers,
+//                       does the blend and publishes h_t (fp32 + tf32 hi/lo split) to shared memory
+//     role 1            r tile of sW in phase 1 (writes r*h split hi/lo); in phase 2 it computes the second
+//                       half of the k range of the c tile (partial sums handed to the owner through shared
+//                       memory and a 64-thread named barrier) and then does the HBM traffic: cp.async
+//                       staging of vI[t+2] and the coalesced store of h_{t-1}
+// D[16 x 8] tiles: N = 8 sequences.  Every product is hi*hi + lo*hi + hi*lo with hi = top 19 bits.
+#include <cstdlib>
+#include "common.cuh"
+
+namespace sloika {
+namespace gru3 {
+
+
+constexpr int BT = 8;
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+// named barrier 1: non-blocking arrive (producers) / blocking sync (consumers)
+__device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+__device__ __forceinline__ void split_tf32(float w, uint32_t &hi, uint32_t &lo) {
+    hi = __float_as_uint(w) & 0xffffe000u;
+    lo = __float_as_uint(w - __uint_as_float(hi));
+}
+
+// D (16x8, fp32) += A (16x8, tf32, row) * B (8x8, tf32, col)
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// B fragments (the 8 sequences' state, tf32 hi / lo parts in [8][P] K-major arrays) of all k chunks, loaded up
+// front: with the loads batched ahead of the MMA chain the tensor pipe is never left waiting on a 30-cycle
+// shared-memory round trip per chunk (which is what bounded the first version of this kernel).
+template <int NKC, int P>
+__device__ __forceinline__ void load_bfrags(const uint32_t *__restrict__ Bhi, const uint32_t *__restrict__ Blo, int g, int t4,
+                                            uint32_t (&bh)[NKC][2], uint32_t (&bl)[NKC][2])
+{
+#pragma unroll
+    for (int kc = 0; kc < NKC; kc++) {
+        const int o = g * P + 8 * kc + t4;
+        bh[kc][0] = Bhi[o]; bh[kc][1] = Bhi[o + 4];
+        bl[kc][0] = Blo[o]; bl[kc][1] = Blo[o + 4];
+    }
+}
+
+// One 16-row tile (A fragments in registers, split on the fly) times the 8 sequences.
+template <int NKC, int P>
+__device__ __forceinline__ void tile_matvec(const float (&w)[NKC][4], const uint32_t *__restrict__ Bhi,
+                                            const uint32_t *__restrict__ Blo, int g, int t4, float (&out)[4])
+{
+    uint32_t bh[NKC][2], bl[NKC][2];
+    load_bfrags<NKC, P>(Bhi, Blo, g, t4, bh, bl);
+    float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f}, acc2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int kc = 0; kc < NKC; kc++) {
+        uint32_t ah[4], al[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) split_tf32(w[kc][i], ah[i], al[i]);
+        mma_tf32(acc0, ah, bh[kc][0], bh[kc][1]);
+        mma_tf32(acc1, al, bh[kc][0], bh[kc][1]);
+        mma_tf32(acc2, ah, bl[kc][0], bl[kc][1]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) out[i] = acc0[i] + (acc1[i] + acc2[i]);
+}
+
+// Same, with the A fragments pre-split into tf32 hi / lo and stored in shared memory in fragment order
+// (one 128-bit load per lane, chunk and part): used for the phase-2 tile so that a warp keeps only its
+// phase-1 weights in registers.  A fragments are fetched one chunk ahead of the MMAs that use them.
+template <int KC0, int KC1, int P>
+__device__ __forceinline__ void tile_matvec_smemA(const uint4 *__restrict__ Ahi, const uint4 *__restrict__ Alo, int lane,
+                                                  const uint32_t *__restrict__ Bhi, const uint32_t *__restrict__ Blo,
+                                                  int g, int t4, float (&out)[4])
+{
+    constexpr int N = KC1 - KC0;             // this warp's share of the k chunks
+    uint32_t bh[N][2], bl[N][2];
+#pragma unroll
+    for (int c = 0; c < N; c++) {
+        const int o = g * P + 8 * (KC0 + c) + t4;
+        bh[c][0] = Bhi[o]; bh[c][1] = Bhi[o + 4];
+        bl[c][0] = Blo[o]; bl[c][1] = Blo[o + 4];
+    }
+    float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f}, acc2[4] = {0.f, 0.f, 0.f, 0.f};
+    uint4 h4 = Ahi[KC0 * 32 + lane], l4 = Alo[KC0 * 32 + lane];
+#pragma unroll
+    for (int c = 0; c < N; c++) {
+        const uint32_t ah[4] = {h4.x, h4.y, h4.z, h4.w}, al[4] = {l4.x, l4.y, l4.z, l4.w};
+        if (c + 1 < N) { h4 = Ahi[(KC0 + c + 1) * 32 + lane]; l4 = Alo[(KC0 + c + 1) * 32 + lane]; }
+        mma_tf32(acc0, ah, bh[c][0], bh[c][1]);
+        mma_tf32(acc1, al, bh[c][0], bh[c][1]);
+        mma_tf32(acc2, ah, bl[c][0], bl[c][1]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) out[i] = acc0[i] + (acc1[i] + acc2[i]);
+}
+
+template <int HP>
+__global__ void __launch_bounds__(HP * 4, 1)
+gru_mma_kernel(const float *__restrict__ vI, const float *__restrict__ sW, const float *__restrict__ sW2,
+               float *__restrict__ y, long ldy, const int32_t *__restrict__ lengths, int T, int B, int H, int reverse)
+{
+    constexpr int NT = HP / 16;              // 16-row tiles per gate
+    constexpr int NKC = HP / 8;              // 8-wide k chunks
+    constexpr int P = HP + 4;                // pitch of the [8][P] state arrays: conflict-free fragment loads
+    constexpr int VLD = 3 * HP + 4;          // pitch of the staged vI rows
+    constexpr int NTHREADS = HP * 4;         // 2 * NT warps
+    extern __shared__ __align__(16) float smem[];
+    float *Hf = smem;                                            // [2][8][P]  h (fp32), double buffered by step parity
+    uint32_t *Hhi = reinterpret_cast<uint32_t *>(Hf + 2 * BT * P);   // [8][P]  tf32 hi of h_{t-1}
+    uint32_t *Hlo = Hhi + BT * P;                                // [8][P]  tf32 lo
+    uint32_t *RHhi = Hlo + BT * P;                               // [8][P]  r * h_{t-1}, hi
+    uint32_t *RHlo = RHhi + BT * P;                              // [8][P]  lo
+    float *vbuf = reinterpret_cast<float *>(RHlo + BT * P);      // [3][8][VLD] staged vI (ring: t, t+1, t+2)
+    uint4 *Wchi = reinterpret_cast<uint4 *>(vbuf + 3 * BT * VLD);     // [NT][NKC][32] sW2 A fragments, tf32 hi
+    uint4 *Wclo = Wchi + NT * NKC * 32;                          //                                      tf32 lo
+    float4 *Cx = reinterpret_cast<float4 *>(Wclo + NT * NKC * 32);   // [NT][32] phase-2 partial sums of the role-1 warps
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t4 = lane & 3;
+    const int jt = warp % NT, role = warp / NT;
+    const int b_base = blockIdx.x * BT;
+
+    // ---- A fragments (weights) -> registers, zero padded ----
+    auto wload = [&](const float *Wm, int row_in_gate, int gate_row0, int k) -> float {
+        return (row_in_gate < H && k < H) ? __ldg(Wm + (long)(gate_row0 + row_in_gate) * H + k) : 0.0f;
+    };
+    float wa[NKC][4];                        // phase 1: z tile (role 0) or r tile (role 1) of sW
+    for (int e = tid; e < 6 * BT * P + 3 * BT * VLD; e += NTHREADS) smem[e] = 0.0f;
+    {
+        const int r0 = 16 * jt + g, r1 = r0 + 8;
+        const int gate0 = role == 0 ? 0 : H;
+#pragma unroll
+        for (int kc = 0; kc < NKC; kc++) {
+            const int k0 = 8 * kc + t4, k1 = k0 + 4;
+            wa[kc][0] = wload(sW, r0, gate0, k0);
+            wa[kc][1] = wload(sW, r1, gate0, k0);
+            wa[kc][2] = wload(sW, r0, gate0, k1);
+            wa[kc][3] = wload(sW, r1, gate0, k1);
+            if (role == 0) {                 // phase-2 (sW2) fragments of this tile -> shared memory, pre-split
+                uint4 h4, l4;
+                split_tf32(wload(sW2, r0, 0, k0), h4.x, l4.x);
+                split_tf32(wload(sW2, r1, 0, k0), h4.y, l4.y);
+                split_tf32(wload(sW2, r0, 0, k1), h4.z, l4.z);
+                split_tf32(wload(sW2, r1, 0, k1), h4.w, l4.w);
+                Wchi[(jt * NKC + kc) * 32 + lane] = h4;
+                Wclo[(jt * NKC + kc) * 32 + lane] = l4;
+            }
+        }
+    }
+
+    // fragment element i of this lane: row j = 16*jt + g + 8*(i >> 1), sequence b = 2*t4 + (i & 1)
+    int jrow[4], bcol[4], len[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        jrow[i] = 16 * jt + g + 8 * (i >> 1);
+        bcol[i] = 2 * t4 + (i & 1);
+        const int bg = b_base + bcol[i];
+        len[i] = bg < B ? (lengths ? min(lengths[bg], T) : T) : 0;
+    }
+
+    // ---- I/O (role-1 warps): per-thread work lists are fixed for the whole scan, so the index math is done once ----
+    const int io_tid = tid - NT * 32, io_n = NT * 32;
+    const long H3 = 3L * H;
+    const bool vec_vi = ((H3 & 3) == 0) && (((uintptr_t)vI & 15) == 0);
+    const bool vec_y = ((ldy & 3) == 0) && ((H & 3) == 0) && (((uintptr_t)y & 15) == 0);
+    constexpr int MAXV = (BT * 3 * HP / 4 + 32 * (HP / 16) - 1) / (32 * (HP / 16));     // float4 copies of vI per I/O thread
+    constexpr int MAXY = (BT * HP / 4 + 32 * (HP / 16) - 1) / (32 * (HP / 16));         // float4 copies of h per I/O thread
+    int v_src[MAXV], v_dst[MAXV], y_src[MAXY];      // element offsets (-1 = none); src relative to row (t, b_base)
+    long y_dst[MAXY];
+    {
+        const int n4 = (int)(H3 >> 2), h4 = H >> 2;
+#pragma unroll
+        for (int i = 0; i < MAXV; i++) {
+            const int e = io_tid + i * io_n;
+            v_src[i] = -1; v_dst[i] = 0;
+            if (role == 1 && vec_vi && e < BT * n4) {
+                const int b = e / n4, c = e - b * n4;
+                if (b_base + b < B) { v_src[i] = b * (int)H3 + 4 * c; v_dst[i] = b * VLD + 4 * c; }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < MAXY; i++) {
+            const int e = io_tid + i * io_n;
+            y_src[i] = -1; y_dst[i] = 0;
+            if (role == 1 && vec_y && e < BT * h4) {
+                const int b = e / h4, c = e - b * h4;
+                if (b_base + b < B) { y_src[i] = b * P + 4 * c; y_dst[i] = (long)b * ldy + 4 * c; }
+            }
+        }
+    }
+    auto stage_vi = [&](int t, int slot, int who, int nwho) {          // generic (prologue / unaligned) path
+        if (t < 0 || t >= T) return;
+        float *dst = vbuf + slot * BT * VLD;
+        for (int e = who; e < BT * (int)H3; e += nwho) {
+            const int b = e / (int)H3, c = e - b * (int)H3;
+            if (b_base + b < B) dst[b * VLD + c] = __ldg(vI + ((long)t * B + b_base + b) * H3 + c);
+        }
+    };
+    auto stage_vi_fast = [&](int t, int slot) {                        // role-1 threads, cp.async
+        if (t < 0 || t >= T) return;
+        if (!vec_vi) { stage_vi(t, slot, io_tid, io_n); return; }
+        float *dst = vbuf + slot * BT * VLD;
+        const float *src = vI + ((long)t * B + b_base) * H3;
+#pragma unroll
+        for (int i = 0; i < MAXV; i++)
+            if (v_src[i] >= 0) cp_async16(dst + v_dst[i], src + v_src[i]);
+    };
+    auto store_h = [&](int t, int slot, int who, int nwho) {           // generic path: Hf[slot] -> y[t]
+        const float *src = Hf + slot * BT * P;
+        for (int e = who; e < BT * H; e += nwho) {
+            const int b = e / H, j = e - b * H;
+            if (b_base + b < B) y[((long)t * B + b_base + b) * ldy + j] = src[b * P + j];
+        }
+    };
+    auto store_h_fast = [&](int t, int slot) {                         // role-1 threads, 128-bit
+        if (!vec_y) { store_h(t, slot, io_tid, io_n); return; }
+        const float *src = Hf + slot * BT * P;
+        float *dst = y + ((long)t * B + b_base) * ldy;
+#pragma unroll
+        for (int i = 0; i < MAXY; i++)
+            if (y_src[i] >= 0) *reinterpret_cast<float4 *>(dst + y_dst[i]) = *reinterpret_cast<const float4 *>(src + y_src[i]);
+    };
+
+    const int tstep = reverse ? -1 : 1;
+    int t = reverse ? T - 1 : 0;
+    __syncthreads();
+    stage_vi(t, 0, tid, NTHREADS);
+    stage_vi(t + tstep, 1, tid, NTHREADS);
+    __syncthreads();
+
+    float hreg[4] = {0.f, 0.f, 0.f, 0.f};    // role 0: state of this lane's 4 (row, sequence) elements
+    float zreg[4];
+
+    // smem offsets of this lane's 4 fragment elements (row j, sequence b): fixed for the whole scan
+    int o_st[4], o_vi[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) { o_st[i] = bcol[i] * P + jrow[i]; o_vi[i] = bcol[i] * VLD + jrow[i]; }
+
+    for (int s = 0; s < T; s++, t += tstep) {
+        const int slot = s & 1;              // Hf[slot] receives h_t, Hf[slot^1] holds h_{t-1}
+        const float *vrow = vbuf + (s % 3) * BT * VLD;
+
+        // ---------------- phase 1: z (role 0) / r (role 1) pre-activations ----------------
+        // the epilogues below are written load-all / compute-all / store-all with unconditional stores
+        // (rows j >= H carry exact zeros) so that the four elements' MUFU chains overlap
+        float pre[4];
+        tile_matvec<NKC, P>(wa, Hhi, Hlo, g, t4, pre);
+        if (role == 0) {
+            float vz[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) vz[i] = vrow[o_vi[i]];
+#pragma unroll
+            for (int i = 0; i < 4; i++) zreg[i] = sigmoid_fast(pre[i] + vz[i]);
+            bar_sync(1, NTHREADS);           // wait for r*h of every row
+        } else {
+            const float *hprev = Hf + (slot ^ 1) * BT * P;
+            float vr[4], hp[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) { vr[i] = vrow[o_vi[i] + H]; hp[i] = hprev[o_st[i]]; }
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) split_tf32(sigmoid_fast(pre[i] + vr[i]) * hp[i], hi[i], lo[i]);
+#pragma unroll
+            for (int i = 0; i < 4; i++) { RHhi[o_st[i]] = hi[i]; RHlo[o_st[i]] = lo[i]; }
+        }
+
+        // ---------------- phase 2 ----------------
+        if (role == 0) {
+            float cpre[4];
+            tile_matvec_smemA<0, NKC / 2, P>(Wchi + jt * NKC * 32, Wclo + jt * NKC * 32, lane, RHhi, RHlo, g, t4, cpre);
+            bar_sync(2 + jt, 64);            // partner's half of the k range
+            {
+                const float4 px = Cx[jt * 32 + lane];
+                cpre[0] += px.x; cpre[1] += px.y; cpre[2] += px.z; cpre[3] += px.w;
+            }
+            float *hout = Hf + slot * BT * P;
+            float vc[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) vc[i] = vrow[o_vi[i] + 2 * H];
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const float hbar = tanh_fast(cpre[i] + vc[i]);
+                float hn = zreg[i] * hreg[i] + (1.0f - zreg[i]) * hbar;
+                hn = (t < len[i] && jrow[i] < H) ? hn : 0.0f;     // ragged batch: state stays 0 outside the read
+                hreg[i] = hn;
+                split_tf32(hn, hi[i], lo[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; i++) { hout[o_st[i]] = hreg[i]; Hhi[o_st[i]] = hi[i]; Hlo[o_st[i]] = lo[i]; }
+        } else {
+            bar_sync(1, NTHREADS);           // r*h of every row: now every warp consumes it
+            float cpart[4];
+            tile_matvec_smemA<NKC / 2, NKC, P>(Wchi + jt * NKC * 32, Wclo + jt * NKC * 32, lane, RHhi, RHlo, g, t4, cpart);
+            Cx[jt * 32 + lane] = make_float4(cpart[0], cpart[1], cpart[2], cpart[3]);
+            bar_arrive(2 + jt, 64);
+            // HBM traffic: vI two steps ahead (slot read last in step s-1), h_{t-1} (complete since the last barrier) out
+            stage_vi_fast(t + 2 * tstep, (s + 2) % 3);
+            cp_async_commit();
+            if (s > 0) store_h_fast(t - tstep, slot ^ 1);
+            cp_async_wait_1();               // vI of step s+1 (issued one step ago) has landed
+        }
+        __syncthreads();
+    }
+    if (T > 0) store_h(t - tstep, (T - 1) & 1, tid, NTHREADS);           // last step's state
+}
+
+template <int HP>
+static int launch(const float *vI, const float *sW, const float *sW2, float *y, long ldy, const int32_t *lengths, int T,
+                  int B, int H, int reverse, cudaStream_t st)
+{
+    constexpr int P = HP + 4, VLD = 3 * HP + 4;
+    const size_t smem = sizeof(float) * ((size_t)6 * BT * P + (size_t)3 * BT * VLD) + (size_t)2 * (HP / 16) * (HP / 8) * 32 * 16 +
+                        (size_t)(HP / 16) * 32 * 16;
+    auto kern = gru_mma_kernel<HP>;
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return (int)err;
+    const unsigned grid = (unsigned)ceil_div(B, BT);
+    kern<<<grid, HP * 4, smem, st>>>(vI, sW, sW2, y, ldy, lengths, T, B, H, reverse);
+    SLOIKA_RETURN_LAUNCH_STATUS();
+}
+
+// tanh / sigmoid GRUs with H <= 96; SLOIKA_ERR_UNSUPPORTED otherwise (caller falls back to gru_v2 / gru).
+int dispatch(const float *vI, const float *sW, const float *sW2, float *y, long ldy, const int32_t *lengths, int T, int B,
+             int H, int reverse, int act, int gate_act, cudaStream_t st)
+{
+    if (act != SLOIKA_ACT_TANH || gate_act != SLOIKA_ACT_SIGMOID) return SLOIKA_ERR_UNSUPPORTED;
+    if (H <= 32) return launch<32>(vI, sW, sW2, y, ldy, lengths, T, B, H, reverse, st);
+    if (H <= 48) return launch<48>(vI, sW, sW2, y, ldy, lengths, T, B, H, reverse, st);
+    if (H <= 64) return launch<64>(vI, sW, sW2, y, ldy, lengths, T, B, H, reverse, st);
+    if (H <= 80) return launch<80>(vI, sW, sW2, y, ldy, lengths, T, B, H, reverse, st);
+    if (H <= 96) return launch<96>(vI, sW, sW2, y, ldy, lengths, T, B, H, reverse, st);
+    return SLOIKA_ERR_UNSUPPORTED;
+}
+
+}  // namespace gru3
+}  // namespace sloika

@@ -19,6 +19,7 @@
 //   * vI of step t+1 is brought into shared memory with cp.async during step t (coalesced 16-byte
 //     copies, no register staging); h_t is written to HBM with coalesced 128-bit stores from the
 //     shared state buffer.
+#include <cstdlib>
 #include "common.cuh"
 
 namespace sloika {
@@ -26,7 +27,6 @@ namespace gru2 {
 
 constexpr int BT = 8;        // sequences per CTA
 constexpr int S = 8;         // k-slices (lanes that share a row group)
-constexpr int THREADS = 256;
 
 __device__ __forceinline__ float2 lo2(const float4 &v) { return make_float2(v.x, v.y); }
 __device__ __forceinline__ float2 hi2(const float4 &v) { return make_float2(v.z, v.w); }
@@ -71,22 +71,23 @@ __device__ __forceinline__ void reduce_to_own_sequence(float (&v)[R][BT], float 
     }
 }
 
-template <int HP>
+template <int HP, int THREADS>
 struct Cfg {
     static_assert(HP % 32 == 0, "HP must be a multiple of 32");
-    static constexpr int RPT = HP / 32;          // rows per gate per thread
+    static_assert(HP % (THREADS / S) == 0, "row groups must divide HP");
+    static constexpr int RPT = HP / (THREADS / S);   // rows per gate per thread
     static constexpr int NG = HP / 32;           // float4 granules per k-slice (KS = 4*NG = HP/8)
     static constexpr int VLD = 3 * HP + 4;       // smem row pitch of the staged vI (floats, 16-byte multiple)
 };
 
 // W1REG: sW (2H x H) register resident (else read from shared memory every step); sW2 always in registers.
-template <int HP, bool W1REG, int ACT, int GATE>
+template <int HP, int THREADS, bool W1REG, int ACT, int GATE>
 __global__ void __launch_bounds__(THREADS, 1)
 gru_recurrence_v2_kernel(const float *__restrict__ vI, const float *__restrict__ sW, const float *__restrict__ sW2,
                          float *__restrict__ y, long ldy, const int32_t *__restrict__ lengths, int T, int B, int H,
-                         int reverse)
+                         int reverse, int dbg)
 {
-    using C = Cfg<HP>;
+    using C = Cfg<HP, THREADS>;
     constexpr int RPT = C::RPT, NG = C::NG, HP4 = HP / 4, VLD = C::VLD;
     extern __shared__ __align__(16) float smem[];
     float *hs = smem;                            // [BT][HP]   h_{t-1}
@@ -173,7 +174,7 @@ gru_recurrence_v2_kernel(const float *__restrict__ vI, const float *__restrict__
 
     for (int s = 0; s < T; s++, t += tstep) {
         const int slot = s & 1;
-        stage_vi(t + tstep, slot ^ 1);           // lands during this step; consumed next step
+        if (!(dbg & 16)) stage_vi(t + tstep, slot ^ 1);           // lands during this step; consumed next step
         cp_async_commit();
 
         // ---------------- phase 1: vS = h sW'  (rows z_j, r_j : 2*RPT rows) ----------------
@@ -181,6 +182,7 @@ gru_recurrence_v2_kernel(const float *__restrict__ vI, const float *__restrict__
 #pragma unroll
         for (int half = 0; half < 2; half++) {
             float2 acc[2 * RPT][4];
+            if (dbg & 1) { for (int r = 0; r < 2 * RPT; r++) for (int b = 0; b < 4; b++) part[r][4 * half + b] = hs[r + b + ks]; continue; }
 #pragma unroll
             for (int r = 0; r < 2 * RPT; r++)
 #pragma unroll
@@ -213,15 +215,16 @@ gru_recurrence_v2_kernel(const float *__restrict__ vI, const float *__restrict__
                 for (int b = 0; b < 4; b++) part[r][4 * half + b] = acc[r][b].x + acc[r][b].y;
         }
         float pre1[2 * RPT];
-        reduce_to_own_sequence<2 * RPT>(part, pre1, ks);
+        if (dbg & 4) { for (int r = 0; r < 2 * RPT; r++) pre1[r] = part[r][0] + part[r][7]; }
+        else reduce_to_own_sequence<2 * RPT>(part, pre1, ks);
 
         const float *vrow = vbuf + slot * BT * VLD + b_own * VLD;
         float zg[RPT];
 #pragma unroll
         for (int i = 0; i < RPT; i++) {
             const int j = j0 + i;
-            const float z = apply_act_fast<GATE>(pre1[i] + vrow[j]);
-            const float r = apply_act_fast<GATE>(pre1[RPT + i] + vrow[H + j]);
+            const float z = (dbg & 8) ? 0.5f + 0.001f * (pre1[i] + vrow[j]) : apply_act_fast<GATE>(pre1[i] + vrow[j]);
+            const float r = (dbg & 8) ? 0.5f + 0.001f * (pre1[RPT + i] + vrow[H + j]) : apply_act_fast<GATE>(pre1[RPT + i] + vrow[H + j]);
             zg[i] = z;
             if (j < H) rh[b_own * HP + j] = r * h_own[i];
         }
@@ -232,6 +235,7 @@ gru_recurrence_v2_kernel(const float *__restrict__ vI, const float *__restrict__
 #pragma unroll
         for (int half = 0; half < 2; half++) {
             float2 acc[RPT][4];
+            if (dbg & 2) { for (int r = 0; r < RPT; r++) for (int b = 0; b < 4; b++) part2[r][4 * half + b] = rh[r + b + ks]; continue; }
 #pragma unroll
             for (int r = 0; r < RPT; r++)
 #pragma unroll
@@ -256,13 +260,14 @@ gru_recurrence_v2_kernel(const float *__restrict__ vI, const float *__restrict__
                 for (int b = 0; b < 4; b++) part2[r][4 * half + b] = acc[r][b].x + acc[r][b].y;
         }
         float pre2[RPT];
-        reduce_to_own_sequence<RPT>(part2, pre2, ks);
+        if (dbg & 4) { for (int r = 0; r < RPT; r++) pre2[r] = part2[r][0] + part2[r][7]; }
+        else reduce_to_own_sequence<RPT>(part2, pre2, ks);
 
         const bool live = t < len_own;           // ragged batch: state stays 0 outside the read
 #pragma unroll
         for (int i = 0; i < RPT; i++) {
             const int j = j0 + i;
-            const float hbar = apply_act_fast<ACT>(pre2[i] + vrow[2 * H + j]);
+            const float hbar = (dbg & 8) ? 0.001f * (pre2[i] + vrow[2 * H + j]) : apply_act_fast<ACT>(pre2[i] + vrow[2 * H + j]);
             float hn = zg[i] * h_own[i] + (1.0f - zg[i]) * hbar;
             hn = (live && j < H) ? hn : 0.0f;
             h_own[i] = hn;
@@ -272,6 +277,7 @@ gru_recurrence_v2_kernel(const float *__restrict__ vI, const float *__restrict__
         __syncthreads();
 
         // ---------------- h_t -> HBM, coalesced from the shared state ----------------
+        if (dbg & 32) continue;
         if (vec_y) {
             for (int e = tid; e < BT * HP4; e += THREADS) {
                 const int b = e / HP4, c = e - b * HP4;
@@ -287,19 +293,20 @@ gru_recurrence_v2_kernel(const float *__restrict__ vI, const float *__restrict__
     }
 }
 
-template <int HP, bool W1REG>
+template <int HP, int THREADS, bool W1REG>
 static int launch(const float *vI, const float *sW, const float *sW2, float *y, long ldy, const int32_t *lengths, int T,
                   int B, int H, int reverse, int act, int gate_act, cudaStream_t st)
 {
-    using C = Cfg<HP>;
+    using C = Cfg<HP, THREADS>;
     const size_t smem = sizeof(float) * ((size_t)2 * BT * HP + (size_t)2 * BT * C::VLD + (W1REG ? 0 : (size_t)2 * HP * HP));
     // the models on the path use tanh / sigmoid (every models/*.py); other pairs go to the generic kernel
     if (act != SLOIKA_ACT_TANH || gate_act != SLOIKA_ACT_SIGMOID) return SLOIKA_ERR_UNSUPPORTED;
-    auto kern = gru_recurrence_v2_kernel<HP, W1REG, SLOIKA_ACT_TANH, SLOIKA_ACT_SIGMOID>;
+    auto kern = gru_recurrence_v2_kernel<HP, THREADS, W1REG, SLOIKA_ACT_TANH, SLOIKA_ACT_SIGMOID>;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return (int)err;
     const unsigned grid = (unsigned)ceil_div(B, BT);
-    kern<<<grid, THREADS, smem, st>>>(vI, sW, sW2, y, ldy, lengths, T, B, H, reverse);
+    const char *dbg = getenv("SLOIKA_B200_GRU_DBG");
+    kern<<<grid, THREADS, smem, st>>>(vI, sW, sW2, y, ldy, lengths, T, B, H, reverse, dbg ? atoi(dbg) : 0);
     SLOIKA_RETURN_LAUNCH_STATUS();
 }
 
@@ -307,10 +314,15 @@ static int launch(const float *vI, const float *sW, const float *sW2, float *y, 
 int dispatch(const float *vI, const float *sW, const float *sW2, float *y, long ldy, const int32_t *lengths, int T, int B,
              int H, int reverse, int act, int gate_act, cudaStream_t st)
 {
-    if (H <= 32) return launch<32, true>(vI, sW, sW2, y, ldy, lengths, T, B, H, reverse, act, gate_act, st);
-    if (H <= 64) return launch<64, true>(vI, sW, sW2, y, ldy, lengths, T, B, H, reverse, act, gate_act, st);
-    if (H > 80 && H <= 96) return launch<96, true>(vI, sW, sW2, y, ldy, lengths, T, B, H, reverse, act, gate_act, st);
-    if (H > 112 && H <= 128) return launch<128, false>(vI, sW, sW2, y, ldy, lengths, T, B, H, reverse, act, gate_act, st);
+    const char *geo = getenv("SLOIKA_B200_GRU_THREADS");           // tuning experiments
+    const int want = geo ? atoi(geo) : 0;
+    if (H <= 32) return launch<32, 256, true>(vI, sW, sW2, y, ldy, lengths, T, B, H, reverse, act, gate_act, st);
+    if (H <= 64) return launch<64, 256, true>(vI, sW, sW2, y, ldy, lengths, T, B, H, reverse, act, gate_act, st);
+    if (H > 80 && H <= 96) {
+        if (want == 256) return launch<96, 256, true>(vI, sW, sW2, y, ldy, lengths, T, B, H, reverse, act, gate_act, st);
+        return launch<96, 384, true>(vI, sW, sW2, y, ldy, lengths, T, B, H, reverse, act, gate_act, st);
+    }
+    if (H > 112 && H <= 128) return launch<128, 256, false>(vI, sW, sW2, y, ldy, lengths, T, B, H, reverse, act, gate_act, st);
     return SLOIKA_ERR_UNSUPPORTED;
 }
 

@@ -224,7 +224,8 @@ extern "C" int sloika_linear_fwd(const float *x, long ldx, const float *W, const
 extern "C" int sloika_softmax_slices(int K, int N)
 {
     if (N > 32 * 256) return 0;
-    const int n = gemm_tc::plan_slices(K, N, nullptr);
+    // the kernel writes one (max, sum exp) pair per column slice AND per epilogue warp group
+    const int n = 2 * gemm_tc::plan_slices(K, N, nullptr);
     return n > 32 ? 0 : n;
 }
 
