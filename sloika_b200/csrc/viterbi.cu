@@ -179,8 +179,15 @@ viterbi_kernel(const float *__restrict__ post, long ld_t, long ld_b, const int32
 //                      posterior matrix is never written to HBM on the fused basecall path.
 constexpr int IN_POST = 0, IN_LOG = 1, IN_LOGITS = 2;
 
+__device__ __forceinline__ void cp_async16_v(void *smem_dst, const void *gsrc) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_v() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait1_v() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+
 template <int MODE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 7)      // 7 CTAs/SM: all 1024 reads of a batch resident in one wave on 148 SMs
 viterbi_k1024_kernel(const float *__restrict__ post, long ld_t, long ld_b, const float2 *__restrict__ stats, int n_slices,
                      const int32_t *__restrict__ lengths, int T, int B, float skip_pen, float c0, float c1,
                      float skip_below, uint8_t *__restrict__ tb, int32_t *__restrict__ path_out,
@@ -188,10 +195,12 @@ viterbi_k1024_kernel(const float *__restrict__ post, long ld_t, long ld_b, const
 {
     constexpr int K = 1024, RS = 256, RK = 64;
     __shared__ __align__(16) float vbuf[2][K];
-    __shared__ float2 ms_s[2];                       // (row max, row sum) of the softmax, double buffered
+    __shared__ float2 ms_s[2];                       // (row max, 1 / row sum) of the softmax, double buffered
+    __shared__ float2 m4_s[256];                     // per row r: (max_a p[a*256 + r], 4 * argmax) of the current event
     __shared__ float red_v[8];
     __shared__ int red_i[8];
-    __shared__ int s_best;
+    __shared__ int s_best, s_state;
+    __shared__ __align__(16) uint8_t tb_s2[8 * 1024];   // second traceback chunk buffer of the backtrace
 
     const int b = blockIdx.x;
     const int r = threadIdx.x;
@@ -202,14 +211,16 @@ viterbi_k1024_kernel(const float *__restrict__ post, long ld_t, long ld_b, const
     }
     const float *pb = post + (long)b * ld_b;
     uint8_t *tbb = tb + (size_t)b * (size_t)T * (size_t)K;
-    const float lp_floor = logf(__fadd_rn(c0, VIT_ETA));
 
     // softmax row statistics of event i -> ms_s[i & 1] (warp 0; visible after the next barrier)
+    const float2 *stp = stats + (long)b * n_slices + r;               // advanced by B*n_slices per event
+    const long st_step = (long)B * n_slices;
     auto row_stats = [&](int i) {
         if (MODE != IN_LOGITS || r >= 32) return;
         float m = -INFINITY, s = 0.0f;
         if (r < n_slices) {
-            const float2 st = __ldg(stats + ((long)i * B + b) * n_slices + r);
+            const float2 st = __ldg(stp);
+            stp += st_step;
             m = st.x;
             s = st.y;
         }
@@ -219,11 +230,13 @@ viterbi_k1024_kernel(const float *__restrict__ post, long ld_t, long ld_b, const
         float tot = r < n_slices ? s * expf(m - mx) : 0.0f;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-        if (r == 0) ms_s[i & 1] = make_float2(mx, tot);
+        if (r == 0) ms_s[i & 1] = make_float2(mx, __frcp_rn(tot));      // (row max, 1 / row sum)
     };
     // raw row values of event i for this thread: 4 k-mer columns + the stay column
+    const float *rowp = pb;                                           // advanced by ld_t per event
     auto fetch = [&](int i, float (&x)[4], float &x0) {
-        const float *row = pb + (long)i * ld_t;
+        const float *row = rowp;
+        rowp += ld_t;
         if (MODE == IN_LOGITS) {
             const float4 q = __ldg(reinterpret_cast<const float4 *>(row) + r);
             x[0] = q.x; x[1] = q.y; x[2] = q.z; x[3] = q.w;
@@ -237,9 +250,11 @@ viterbi_k1024_kernel(const float *__restrict__ post, long ld_t, long ld_b, const
     auto lpost_of = [&](float v, float2 ms) -> float {
         if (MODE == IN_LOG) return v;
         if (MODE == IN_LOGITS) {
-            const float d = v - ms.x;
-            if (d < skip_below) return lp_floor;                 // p below half an ulp of min_prob: exact shortcut
-            v = __fdiv_rn(expf(d), ms.y);                        // Softmax.run: exp(t - m) / rowsum
+            // fused path: softmax (exp(t - m) * 1/rowsum), min_prob floor and log with the MUFU ex2 / lg2
+            // approximations (|error| ~1e-6 on a log-posterior, inside what libm-vs-device logf already allows);
+            // branch free, ~10 instructions per value instead of ~60
+            const float pr = __expf(v - ms.x) * ms.y;
+            return __logf(__fadd_rn(__fadd_rn(c0, __fmul_rn(c1, pr)), VIT_ETA));
         }
         return logf(__fadd_rn(__fadd_rn(c0, __fmul_rn(c1, v)), VIT_ETA));
     };
@@ -258,14 +273,14 @@ viterbi_k1024_kernel(const float *__restrict__ post, long ld_t, long ld_b, const
     __syncthreads();
 
     int cur = 0;
+    unsigned *tbp = reinterpret_cast<unsigned *>(tbb) + r;             // traceback word of this thread, advanced per event
     for (int i = 1; i < nev; i++) {
         float x[4] = {xn[0], xn[1], xn[2], xn[3]};
         const float x0 = xn0;
         const float2 ms = ms_s[i & 1];
         if (i + 1 < nev) { row_stats(i + 1); fetch(i + 1, xn, xn0); }   // next event, off the critical path
         const float *p = vbuf[cur];
-        const float lp0 = lpost_of(x0, ms);
-        // step: first maximum over a of p[a*256 + r]
+        // step: first maximum over a of p[a*256 + r]; published as (value, 4*a) for the skip search
         float ss = p[r];
         int as = 0;
 #pragma unroll
@@ -273,33 +288,47 @@ viterbi_k1024_kernel(const float *__restrict__ post, long ld_t, long ld_b, const
             const float c = p[a * RS + r];
             if (c > ss) { ss = c; as = a; }
         }
-        // skip: first maximum over a of p[a*64 + r/4]
-        const int q = r >> 2;
-        float sk = p[q];
-        int ak = 0;
+        m4_s[r] = make_float2(ss, __int_as_float(4 * as));
+        const float4 pv = reinterpret_cast<const float4 *>(p)[r];
+        const float lp0 = lpost_of(x0, ms);
+        float lp[4];
 #pragma unroll
-        for (int a = 1; a < 16; a++) {
-            const float c = p[a * RK + q];
-            if (c > sk) { sk = c; ak = a; }
+        for (int c = 0; c < 4; c++) lp[c] = lpost_of(x[c], ms);
+        __syncthreads();
+        // skip: predecessor a*64 + q with a = 4*a_hi + a_lo is p[a_hi*256 + (a_lo*64 + q)], so its maximum is
+        // the maximum over a_lo of the published step maxima of rows a_lo*64 + q; "first maximum" = smallest a
+        const int q = r >> 2;
+        float sk;
+        int ak;
+        {
+            const float2 e0 = m4_s[q];
+            sk = e0.x;
+            ak = __float_as_int(e0.y);
+#pragma unroll
+            for (int al = 1; al < 4; al++) {
+                const float2 e = m4_s[al * RK + q];
+                const int key = __float_as_int(e.y) + al;
+                if (e.x > sk || (e.x == sk && key < ak)) { sk = e.x; ak = key; }
+            }
         }
         sk = __fsub_rn(sk, skip_pen);
         const bool use_step = ss > sk;                               // tie -> skip (decode.py:76)
         const float best = use_step ? ss : sk;
         const unsigned code = use_step ? (1u + as) : (5u + ak);
-        const float4 pv = reinterpret_cast<const float4 *>(p)[r];
         const float pj[4] = {pv.x, pv.y, pv.z, pv.w};
         float vo[4];
         unsigned packed = 0;
 #pragma unroll
         for (int c = 0; c < 4; c++) {
-            const float move = __fadd_rn(lpost_of(x[c], ms), best);
+            const float move = __fadd_rn(lp[c], best);
             const float stay = __fadd_rn(pj[c], lp0);
             const bool mv = move > stay;                             // tie -> stay (decode.py:81)
             vo[c] = mv ? move : stay;
             packed |= (mv ? code : 0u) << (8 * c);
         }
         reinterpret_cast<float4 *>(vbuf[cur ^ 1])[r] = make_float4(vo[0], vo[1], vo[2], vo[3]);
-        reinterpret_cast<unsigned *>(tbb + (size_t)i * K)[r] = packed;
+        tbp += K / 4;
+        *tbp = packed;
         cur ^= 1;
         __syncthreads();
     }
@@ -325,19 +354,52 @@ viterbi_k1024_kernel(const float *__restrict__ post, long ld_t, long ld_b, const
         for (int w = 1; w < 8; w++)
             if (red_v[w] > bv || (red_v[w] == bv && red_i[w] < bi)) { bv = red_v[w]; bi = red_i[w]; }
         score_out[b] = bv;
-        int32_t *out = path_out + (size_t)b * T;
-        int pos = nev - 1;
-        int state = bi;
-        out[pos] = state;
-        for (int i = nev - 1; i > 0; i--) {
-            const unsigned cd = tbb[(size_t)i * K + state];
-            if (cd != 0) {
-                state = cd <= 4u ? (int)(cd - 1) * RS + (state >> 2) : (int)(cd - 5) * RK + (state >> 4);
-                out[--pos] = state;
+        s_state = bi;
+        s_best = nev - 1;
+        path_out[(size_t)b * T + nev - 1] = bi;
+    }
+    // ---- backtrace (decode.py:84-91).  The walk itself is sequential (one thread), but each step would
+    // be a dependent ~1 us HBM access; instead the whole CTA streams the traceback rows backwards in chunks
+    // of 8 events through shared memory (cp.async, next chunk in flight while this one is walked). ----
+    {
+        constexpr int CH = 8;
+        // two 8 KB chunk buffers: vbuf (free now that v_T has been reduced) and tb_s2
+        uint8_t *bufs[2] = {reinterpret_cast<uint8_t *>(&vbuf[0][0]), tb_s2};
+        auto issue = [&](int hi, int which) {                              // rows (hi-CH, hi], clipped at 1
+            uint8_t *dst = bufs[which];
+            for (int e = r; e < CH * (K / 16); e += 256) {
+                const int row = hi - e / (K / 16);
+                if (row >= 1) cp_async16_v(dst + (size_t)e * 16, tbb + (size_t)row * K + (size_t)(e % (K / 16)) * 16);
             }
+            cp_async_commit_v();
+        };
+        __syncthreads();
+        int hi = nev - 1, which = 0;
+        if (hi >= 1) issue(hi, 0);
+        while (hi >= 1) {
+            const int nxt = hi - CH;
+            if (nxt >= 1) issue(nxt, which ^ 1); else cp_async_commit_v();
+            cp_async_wait1_v();
+            __syncthreads();
+            if (r == 0) {
+                const uint8_t *src = bufs[which];
+                int state = s_state, pos = s_best;
+                int32_t *out = path_out + (size_t)b * T;
+                for (int k = 0; k < CH && hi - k >= 1; k++) {
+                    const unsigned cd = src[k * K + state];
+                    if (cd != 0) {
+                        state = cd <= 4u ? (int)(cd - 1) * RS + (state >> 2) : (int)(cd - 5) * RK + (state >> 4);
+                        out[--pos] = state;
+                    }
+                }
+                s_state = state;
+                s_best = pos;
+            }
+            __syncthreads();
+            hi = nxt;
+            which ^= 1;
         }
-        path_len[b] = nev - pos;
-        s_best = pos;
+        if (r == 0) path_len[b] = nev - s_best;
     }
     __syncthreads();
     const int off = s_best;
