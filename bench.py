@@ -34,13 +34,14 @@ INPUT_SEED = 20261017
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--steps', type=int, default=30)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default='raw_rgrgr')
     ap.add_argument('--batch', type=int, default=BATCH_PER_GPU, help='chunks per GPU')
     ap.add_argument('--chunk', type=int, default=CHUNK_LEN, help='raw samples per chunk')
-    ap.add_argument('--cpu-sample-chunks', type=int, default=32, help='chunks in the bounded CPU-baseline sample')
+    ap.add_argument('--cpu-sample-chunks', type=int, default=None,
+                    help='chunks in the bounded CPU sample (default: 384 once for cpu_baseline, 32 per step for --impl reference)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     return ap.parse_args()
 
@@ -117,7 +118,7 @@ class ClockSampler(object):
     def start(self):
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu_index), '--query-gpu=' + self.FIELDS,
-                                          '--format=csv,noheader,nounits', '-lms', '200'],
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -199,7 +200,7 @@ def run_reference_arm(args):
     if rank != 0:
         return
     net = build_network(args.workload)
-    nchunks = args.cpu_sample_chunks
+    nchunks = args.cpu_sample_chunks or 32
     value, sec_per_step, cores = time_cpu_reference(net, args.chunk, nchunks, args.steps, args.warmup)
     sample = "{} chunks x {} samples per step (of {} per GPU), oracle NumPy forward + NumPy Viterbi over {} processes".format(
         nchunks, args.chunk, args.batch, min(cores, nchunks))
@@ -334,8 +335,15 @@ def run_b200_arm(args):
     dom_ms, dom_calls = kernel_ms[dominant]
     dom_bytes_per_launch = alg_by_kernel.get(dominant, 0.0) * samples_per_step * args.steps / dom_calls
     achieved = dom_bytes_per_launch / (dom_ms / dom_calls * 1e-3) / 1e9
+    traffic = None
+    try:
+        if args.workload == 'raw_rgrgr' and B == BATCH_PER_GPU and T == CHUNK_LEN:
+            with open(os.path.join(ROOT, 'profiles', 'r1g_traffic.json')) as fh:
+                traffic = json.load(fh).get(dominant)
+    except Exception:
+        traffic = None
     roofline = {"kernel": dominant, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                "frac": achieved / hbm_peak, "traffic": None, "peak_source": peaks_src,
+                "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peaks_src,
                 "algorithmic_bytes_per_launch": dom_bytes_per_launch,
                 "avg_launch_ms": dom_ms / dom_calls, "share_of_step": dom_ms / (ms_dev if world == 1 else sum(v[0] for v in kernel_ms.values()))}
     total_alg = sum(alg.values())
@@ -343,7 +351,7 @@ def run_b200_arm(args):
 
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
-        nchunks = args.cpu_sample_chunks
+        nchunks = args.cpu_sample_chunks or 384
         cpu_value, sec_per_step, cores = time_cpu_reference(net, T, nchunks, steps=1, warmup=0)
         cpu_baseline = {"value": cpu_value, "unit": UNIT, "cores": cores, "kind": "port",
                         "sample": "{} chunks x {} samples once: oracle NumPy forward (BLAS threads) + NumPy Viterbi over {} processes, {:.1f} s".format(
