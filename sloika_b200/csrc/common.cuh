@@ -45,6 +45,21 @@ __device__ __forceinline__ float apply_act_t(float x) {
     else return x;
 }
 
+// Raw MUFU approximations (flush-to-zero forms: no denormal fix-up code around them).  Callers guarantee the
+// argument range: ex2 inputs <= 0 (results in [0, 1], tiny ones may flush to 0), lg2 inputs >= 1e-10.
+__device__ __forceinline__ float ex2_ftz(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float lg2_ftz(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+constexpr float SLOIKA_LOG2E = 1.4426950408889634f;
+constexpr float SLOIKA_LN2 = 0.6931471805599453f;
+
 // Fast variants for the latency-bound recurrence epilogue: MUFU ex2 / rcp based, absolute error ~1e-7
 // (relative 2^-21 on the exponential), three orders of magnitude inside the 1e-4 posterior budget.
 __device__ __forceinline__ float sigmoid_fast(float x) {

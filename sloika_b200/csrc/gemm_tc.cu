@@ -265,10 +265,14 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params p)
 #pragma unroll
                         for (int i = 1; i < 32; i++) cm = fmaxf(cm, o[i]);
                         const float nm = fmaxf(m_run, cm);
+                        const float nms = nm * SLOIKA_LOG2E;                 // exp(o - nm) = ex2(o*log2e - nm*log2e)
                         float acc0 = 0.0f, acc1 = 0.0f;
 #pragma unroll
-                        for (int i = 0; i < 32; i += 2) { acc0 += __expf(o[i] - nm); acc1 += __expf(o[i + 1] - nm); }
-                        s_run = s_run * __expf(m_run - nm) + (acc0 + acc1);
+                        for (int i = 0; i < 32; i += 2) {
+                            acc0 += ex2_ftz(fmaf(o[i], SLOIKA_LOG2E, -nms));
+                            acc1 += ex2_ftz(fmaf(o[i + 1], SLOIKA_LOG2E, -nms));
+                        }
+                        s_run = s_run * ex2_ftz(fmaf(m_run, SLOIKA_LOG2E, -nms)) + (acc0 + acc1);
                         m_run = nm;
                     } else if (nvalid > 0) {
                         float cm = -INFINITY;

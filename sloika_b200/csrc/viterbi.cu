@@ -253,8 +253,8 @@ viterbi_k1024_kernel(const float *__restrict__ post, long ld_t, long ld_b, const
             // fused path: softmax (exp(t - m) * 1/rowsum), min_prob floor and log with the MUFU ex2 / lg2
             // approximations (|error| ~1e-6 on a log-posterior, inside what libm-vs-device logf already allows);
             // branch free, ~10 instructions per value instead of ~60
-            const float pr = __expf(v - ms.x) * ms.y;
-            return __logf(__fadd_rn(__fadd_rn(c0, __fmul_rn(c1, pr)), VIT_ETA));
+            const float pr = ex2_ftz((v - ms.x) * SLOIKA_LOG2E) * ms.y;           // v <= row max: argument <= 0
+            return lg2_ftz(__fadd_rn(__fadd_rn(c0, __fmul_rn(c1, pr)), VIT_ETA)) * SLOIKA_LN2;
         }
         return logf(__fadd_rn(__fadd_rn(c0, __fmul_rn(c1, v)), VIT_ETA));
     };
