@@ -56,33 +56,34 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
 // front: with the loads batched ahead of the MMA chain the tensor pipe is never left waiting on a 30-cycle
 // shared-memory round trip per chunk (which is what bounded the first version of this kernel).
 template <int NKC, int P>
-__device__ __forceinline__ void load_bfrags(const uint32_t *__restrict__ Bhi, const uint32_t *__restrict__ Blo, int g, int t4,
-                                            uint32_t (&bh)[NKC][2], uint32_t (&bl)[NKC][2])
+__device__ __forceinline__ void load_bfrags(const float *__restrict__ Bf, int g, int t4, float (&bf)[NKC][2])
 {
 #pragma unroll
     for (int kc = 0; kc < NKC; kc++) {
         const int o = g * P + 8 * kc + t4;
-        bh[kc][0] = Bhi[o]; bh[kc][1] = Bhi[o + 4];
-        bl[kc][0] = Blo[o]; bl[kc][1] = Blo[o + 4];
+        bf[kc][0] = Bf[o];
+        bf[kc][1] = Bf[o + 4];
     }
 }
 
 // One 16-row tile (A fragments in registers, split on the fly) times the 8 sequences.
 template <int NKC, int P>
-__device__ __forceinline__ void tile_matvec(const float (&w)[NKC][4], const uint32_t *__restrict__ Bhi,
-                                            const uint32_t *__restrict__ Blo, int g, int t4, float (&out)[4])
+__device__ __forceinline__ void tile_matvec(const float (&w)[NKC][4], const float *__restrict__ Bf, int g, int t4,
+                                            float (&out)[4])
 {
-    uint32_t bh[NKC][2], bl[NKC][2];
-    load_bfrags<NKC, P>(Bhi, Blo, g, t4, bh, bl);
+    float bf[NKC][2];
+    load_bfrags<NKC, P>(Bf, g, t4, bf);
     float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f}, acc2[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int kc = 0; kc < NKC; kc++) {
-        uint32_t ah[4], al[4];
+        uint32_t ah[4], al[4], bh0, bl0, bh1, bl1;
 #pragma unroll
         for (int i = 0; i < 4; i++) split_tf32(w[kc][i], ah[i], al[i]);
-        mma_tf32(acc0, ah, bh[kc][0], bh[kc][1]);
-        mma_tf32(acc1, al, bh[kc][0], bh[kc][1]);
-        mma_tf32(acc2, ah, bl[kc][0], bl[kc][1]);
+        split_tf32(bf[kc][0], bh0, bl0);
+        split_tf32(bf[kc][1], bh1, bl1);
+        mma_tf32(acc0, ah, bh0, bh1);
+        mma_tf32(acc1, al, bh0, bh1);
+        mma_tf32(acc2, ah, bl0, bl1);
     }
 #pragma unroll
     for (int i = 0; i < 4; i++) out[i] = acc0[i] + (acc1[i] + acc2[i]);
@@ -93,16 +94,15 @@ __device__ __forceinline__ void tile_matvec(const float (&w)[NKC][4], const uint
 // phase-1 weights in registers.  A fragments are fetched one chunk ahead of the MMAs that use them.
 template <int KC0, int KC1, int P>
 __device__ __forceinline__ void tile_matvec_smemA(const uint4 *__restrict__ Ahi, const uint4 *__restrict__ Alo, int lane,
-                                                  const uint32_t *__restrict__ Bhi, const uint32_t *__restrict__ Blo,
-                                                  int g, int t4, float (&out)[4])
+                                                  const float *__restrict__ Bf, int g, int t4, float (&out)[4])
 {
     constexpr int N = KC1 - KC0;             // this warp's share of the k chunks
-    uint32_t bh[N][2], bl[N][2];
+    float bf[N][2];
 #pragma unroll
     for (int c = 0; c < N; c++) {
         const int o = g * P + 8 * (KC0 + c) + t4;
-        bh[c][0] = Bhi[o]; bh[c][1] = Bhi[o + 4];
-        bl[c][0] = Blo[o]; bl[c][1] = Blo[o + 4];
+        bf[c][0] = Bf[o];
+        bf[c][1] = Bf[o + 4];
     }
     float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f}, acc2[4] = {0.f, 0.f, 0.f, 0.f};
     uint4 h4 = Ahi[KC0 * 32 + lane], l4 = Alo[KC0 * 32 + lane];
@@ -110,9 +110,12 @@ __device__ __forceinline__ void tile_matvec_smemA(const uint4 *__restrict__ Ahi,
     for (int c = 0; c < N; c++) {
         const uint32_t ah[4] = {h4.x, h4.y, h4.z, h4.w}, al[4] = {l4.x, l4.y, l4.z, l4.w};
         if (c + 1 < N) { h4 = Ahi[(KC0 + c + 1) * 32 + lane]; l4 = Alo[(KC0 + c + 1) * 32 + lane]; }
-        mma_tf32(acc0, ah, bh[c][0], bh[c][1]);
-        mma_tf32(acc1, al, bh[c][0], bh[c][1]);
-        mma_tf32(acc2, ah, bl[c][0], bl[c][1]);
+        uint32_t bh0, bl0, bh1, bl1;
+        split_tf32(bf[c][0], bh0, bl0);
+        split_tf32(bf[c][1], bh1, bl1);
+        mma_tf32(acc0, ah, bh0, bh1);
+        mma_tf32(acc1, al, bh0, bh1);
+        mma_tf32(acc2, ah, bl0, bl1);
     }
 #pragma unroll
     for (int i = 0; i < 4; i++) out[i] = acc0[i] + (acc1[i] + acc2[i]);
@@ -130,11 +133,8 @@ gru_mma_kernel(const float *__restrict__ vI, const float *__restrict__ sW, const
     constexpr int NTHREADS = HP * 4;         // 2 * NT warps
     extern __shared__ __align__(16) float smem[];
     float *Hf = smem;                                            // [2][8][P]  h (fp32), double buffered by step parity
-    uint32_t *Hhi = reinterpret_cast<uint32_t *>(Hf + 2 * BT * P);   // [8][P]  tf32 hi of h_{t-1}
-    uint32_t *Hlo = Hhi + BT * P;                                // [8][P]  tf32 lo
-    uint32_t *RHhi = Hlo + BT * P;                               // [8][P]  r * h_{t-1}, hi
-    uint32_t *RHlo = RHhi + BT * P;                              // [8][P]  lo
-    float *vbuf = reinterpret_cast<float *>(RHlo + BT * P);      // [3][8][VLD] staged vI (ring: t, t+1, t+2)
+    float *RH = Hf + 2 * BT * P;                                 // [8][P]  r * h_{t-1} (consumers split to tf32 hi/lo on the fly)
+    float *vbuf = RH + BT * P;                                   // [3][8][VLD] staged vI (ring: t, t+1, t+2)
     uint4 *Wchi = reinterpret_cast<uint4 *>(vbuf + 3 * BT * VLD);     // [NT][NKC][32] sW2 A fragments, tf32 hi
     uint4 *Wclo = Wchi + NT * NKC * 32;                          //                                      tf32 lo
     float4 *Cx = reinterpret_cast<float4 *>(Wclo + NT * NKC * 32);   // [NT][32] phase-2 partial sums of the role-1 warps
@@ -149,7 +149,7 @@ gru_mma_kernel(const float *__restrict__ vI, const float *__restrict__ sW, const
         return (row_in_gate < H && k < H) ? __ldg(Wm + (long)(gate_row0 + row_in_gate) * H + k) : 0.0f;
     };
     float wa[NKC][4];                        // phase 1: z tile (role 0) or r tile (role 1) of sW
-    for (int e = tid; e < 6 * BT * P + 3 * BT * VLD; e += NTHREADS) smem[e] = 0.0f;
+    for (int e = tid; e < 3 * BT * P + 3 * BT * VLD; e += NTHREADS) smem[e] = 0.0f;
     {
         const int r0 = 16 * jt + g, r1 = r0 + 8;
         const int gate0 = role == 0 ? 0 : H;
@@ -268,7 +268,7 @@ gru_mma_kernel(const float *__restrict__ vI, const float *__restrict__ sW, const
         // the epilogues below are written load-all / compute-all / store-all with unconditional stores
         // (rows j >= H carry exact zeros) so that the four elements' MUFU chains overlap
         float pre[4];
-        tile_matvec<NKC, P>(wa, Hhi, Hlo, g, t4, pre);
+        tile_matvec<NKC, P>(wa, Hf + (slot ^ 1) * BT * P, g, t4, pre);
         if (role == 0) {
             float vz[4];
 #pragma unroll
@@ -281,17 +281,17 @@ gru_mma_kernel(const float *__restrict__ vI, const float *__restrict__ sW, const
             float vr[4], hp[4];
 #pragma unroll
             for (int i = 0; i < 4; i++) { vr[i] = vrow[o_vi[i] + H]; hp[i] = hprev[o_st[i]]; }
-            uint32_t hi[4], lo[4];
+            float rh[4];
 #pragma unroll
-            for (int i = 0; i < 4; i++) split_tf32(sigmoid_fast(pre[i] + vr[i]) * hp[i], hi[i], lo[i]);
+            for (int i = 0; i < 4; i++) rh[i] = sigmoid_fast(pre[i] + vr[i]) * hp[i];
 #pragma unroll
-            for (int i = 0; i < 4; i++) { RHhi[o_st[i]] = hi[i]; RHlo[o_st[i]] = lo[i]; }
+            for (int i = 0; i < 4; i++) RH[o_st[i]] = rh[i];
         }
 
         // ---------------- phase 2 ----------------
         if (role == 0) {
             float cpre[4];
-            tile_matvec_smemA<0, NKC / 2, P>(Wchi + jt * NKC * 32, Wclo + jt * NKC * 32, lane, RHhi, RHlo, g, t4, cpre);
+            tile_matvec_smemA<0, NKC / 2, P>(Wchi + jt * NKC * 32, Wclo + jt * NKC * 32, lane, RH, g, t4, cpre);
             bar_sync(2 + jt, 64);            // partner's half of the k range
             {
                 const float4 px = Cx[jt * 32 + lane];
@@ -301,21 +301,19 @@ gru_mma_kernel(const float *__restrict__ vI, const float *__restrict__ sW, const
             float vc[4];
 #pragma unroll
             for (int i = 0; i < 4; i++) vc[i] = vrow[o_vi[i] + 2 * H];
-            uint32_t hi[4], lo[4];
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 const float hbar = tanh_fast(cpre[i] + vc[i]);
                 float hn = zreg[i] * hreg[i] + (1.0f - zreg[i]) * hbar;
                 hn = (t < len[i] && jrow[i] < H) ? hn : 0.0f;     // ragged batch: state stays 0 outside the read
                 hreg[i] = hn;
-                split_tf32(hn, hi[i], lo[i]);
             }
 #pragma unroll
-            for (int i = 0; i < 4; i++) { hout[o_st[i]] = hreg[i]; Hhi[o_st[i]] = hi[i]; Hlo[o_st[i]] = lo[i]; }
+            for (int i = 0; i < 4; i++) hout[o_st[i]] = hreg[i];
         } else {
             bar_sync(1, NTHREADS);           // r*h of every row: now every warp consumes it
             float cpart[4];
-            tile_matvec_smemA<NKC / 2, NKC, P>(Wchi + jt * NKC * 32, Wclo + jt * NKC * 32, lane, RHhi, RHlo, g, t4, cpart);
+            tile_matvec_smemA<NKC / 2, NKC, P>(Wchi + jt * NKC * 32, Wclo + jt * NKC * 32, lane, RH, g, t4, cpart);
             Cx[jt * 32 + lane] = make_float4(cpart[0], cpart[1], cpart[2], cpart[3]);
             bar_arrive(2 + jt, 64);
             // HBM traffic: vI two steps ahead (slot read last in step s-1), h_{t-1} (complete since the last barrier) out
@@ -334,7 +332,7 @@ static int launch(const float *vI, const float *sW, const float *sW2, float *y, 
                   int B, int H, int reverse, cudaStream_t st)
 {
     constexpr int P = HP + 4, VLD = 3 * HP + 4;
-    const size_t smem = sizeof(float) * ((size_t)6 * BT * P + (size_t)3 * BT * VLD) + (size_t)2 * (HP / 16) * (HP / 8) * 32 * 16 +
+    const size_t smem = sizeof(float) * ((size_t)3 * BT * P + (size_t)3 * BT * VLD) + (size_t)2 * (HP / 16) * (HP / 8) * 32 * 16 +
                         (size_t)(HP / 16) * 32 * 16;
     auto kern = gru_mma_kernel<HP>;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
