@@ -89,6 +89,65 @@ __device__ __forceinline__ void tile_matvec(const float (&w)[NKC][4], const floa
     for (int i = 0; i < 4; i++) out[i] = acc0[i] + (acc1[i] + acc2[i]);
 }
 
+// Phase-1 variant for layers too wide for register-resident weights (H > 96): the A fragments stay in shared
+// memory as fp32 in fragment order (one 128-bit load per lane and chunk, fetched one chunk ahead) and are split
+// into tf32 hi / lo on the fly like the B words.
+template <int NKC, int P>
+__device__ __forceinline__ void tile_matvec_smemA32(const float4 *__restrict__ Af, int lane, const float *__restrict__ Bf,
+                                                    int g, int t4, float (&out)[4])
+{
+    float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f}, acc2[4] = {0.f, 0.f, 0.f, 0.f};
+    float4 a4 = Af[lane];
+    float b0 = Bf[g * P + t4], b1 = Bf[g * P + t4 + 4];
+#pragma unroll
+    for (int kc = 0; kc < NKC; kc++) {
+        const float w[4] = {a4.x, a4.y, a4.z, a4.w};
+        const float c0 = b0, c1 = b1;
+        if (kc + 1 < NKC) {
+            a4 = Af[(kc + 1) * 32 + lane];
+            b0 = Bf[g * P + 8 * (kc + 1) + t4];
+            b1 = Bf[g * P + 8 * (kc + 1) + t4 + 4];
+        }
+        uint32_t ah[4], al[4], bh0, bl0, bh1, bl1;
+#pragma unroll
+        for (int i = 0; i < 4; i++) split_tf32(w[i], ah[i], al[i]);
+        split_tf32(c0, bh0, bl0);
+        split_tf32(c1, bh1, bl1);
+        mma_tf32(acc0, ah, bh0, bh1);
+        mma_tf32(acc1, al, bh0, bh1);
+        mma_tf32(acc2, ah, bl0, bl1);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) out[i] = acc0[i] + (acc1[i] + acc2[i]);
+}
+
+// Register-A variant over a sub-range of the k chunks (phase 2 of the wide kernel: half the range per warp).
+template <int KC0, int N, int P>
+__device__ __forceinline__ void tile_matvec_range(const float (&w)[N][4], const float *__restrict__ Bf, int g, int t4,
+                                                  float (&out)[4])
+{
+    float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f}, acc2[4] = {0.f, 0.f, 0.f, 0.f};
+    float b0 = Bf[g * P + 8 * KC0 + t4], b1 = Bf[g * P + 8 * KC0 + t4 + 4];
+#pragma unroll
+    for (int c = 0; c < N; c++) {
+        const float c0 = b0, c1 = b1;
+        if (c + 1 < N) {
+            b0 = Bf[g * P + 8 * (KC0 + c + 1) + t4];
+            b1 = Bf[g * P + 8 * (KC0 + c + 1) + t4 + 4];
+        }
+        uint32_t ah[4], al[4], bh0, bl0, bh1, bl1;
+#pragma unroll
+        for (int i = 0; i < 4; i++) split_tf32(w[c][i], ah[i], al[i]);
+        split_tf32(c0, bh0, bl0);
+        split_tf32(c1, bh1, bl1);
+        mma_tf32(acc0, ah, bh0, bh1);
+        mma_tf32(acc1, al, bh0, bh1);
+        mma_tf32(acc2, ah, bl0, bl1);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) out[i] = acc0[i] + (acc1[i] + acc2[i]);
+}
+
 // Same, with the A fragments pre-split into tf32 hi / lo and stored in shared memory in fragment order
 // (one 128-bit load per lane, chunk and part): used for the phase-2 tile so that a warp keeps only its
 // phase-1 weights in registers.  A fragments are fetched one chunk ahead of the MMAs that use them.

@@ -119,11 +119,12 @@ def _empty(shape, device):
 
 
 def _out_buffer(act, T, F, out):
-    """Output activation: a fresh dense buffer, or the caller's column slice (Parallel)."""
+    """Output activation: a fresh buffer whose rows are padded to 16 bytes (so the next layer's TMA-fed GEMM
+    and 128-bit accesses apply to odd widths such as 110 or 142), or the caller's column slice (Parallel)."""
     if out is not None:
         assert out.shape == (T, act.B, F)
         return out
-    return _empty((T, act.B, F), act.device)
+    return _padded_rows(T, act.B, F, act.device)
 
 
 def run_convolution(layer, act, out=None):

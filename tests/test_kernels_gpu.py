@@ -369,3 +369,33 @@ def test_softmax_normalise_matches_oracle_with_stay_column():
     s = (st[..., 1] * np.exp(st[..., 0] - m[..., None])).sum(-1)
     np.testing.assert_allclose(m, exact.max(-1), atol=2e-4)
     np.testing.assert_allclose(s, np.exp(exact - exact.max(-1, keepdims=True)).sum(-1), rtol=1e-4)
+
+
+# ------------------------------------------------------------------ config 5: long reads, decode only
+def test_viterbi_long_reads_bit_exact():
+    """Decode-only sweep shape (synthetic posteriors, tens of thousands of events per read): scores and paths
+    bit-identical to the C oracle given the same log-posteriors; the traceback lives in HBM (30 MB/read)."""
+    rng = np.random.default_rng(33)
+    T, B, S = 30000, 3, 1025
+    lp = torch.empty((T, B, S), device=DEV)
+    gen = torch.Generator(device=DEV).manual_seed(5)
+    for b in range(B):                                   # built on the device to keep the test quick
+        logits = 3 * torch.randn((T, S), generator=gen, device=DEV)
+        logits[:, 0] += 6
+        lp[:, b] = torch.log_softmax(logits, dim=1)
+    lengths = np.array([T, 12345, 29999], dtype=np.int32)
+    score, paths = decode.viterbi_batch(lp, lengths, log=True)
+    ref_score, ref_paths = cbind.viterbi_batch(lp.cpu().numpy(), lengths)
+    assert paths == ref_paths
+    assert np.array_equal(score, ref_score)
+    assert all(len(p) > 1000 for p in paths)
+
+
+def test_batch_not_multiple_of_cta_tile():
+    """1023 sequences (the GRU kernels tile 8 per CTA, Viterbi 1 per CTA): last CTA partially filled."""
+    np.random.seed(44)
+    net = zoo.raw_rgrgr()
+    x = torch.randn((300, 13, 1), device=DEV)
+    post13 = net.compile().forward_device(x).data.cpu().numpy()
+    ref = _oracle(net, x.cpu().numpy())
+    assert np.abs(post13 - ref).max() < 1e-4
