@@ -33,6 +33,10 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
     const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void cp_async4(void *smem_dst, const void *gsrc) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
@@ -92,7 +96,7 @@ __device__ __forceinline__ void tile_matvec(const float (&w)[NKC][4], const floa
 // Phase-1 variant for layers too wide for register-resident weights (H > 96): the A fragments stay in shared
 // memory as fp32 in fragment order (one 128-bit load per lane and chunk, fetched one chunk ahead) and are split
 // into tf32 hi / lo on the fly like the B words.
-template <int NKC, int P>
+template <int NKC, int P, bool ACC3>
 __device__ __forceinline__ void tile_matvec_smemA32(const float4 *__restrict__ Af, int lane, const float *__restrict__ Bf,
                                                     int g, int t4, float (&out)[4])
 {
@@ -115,14 +119,14 @@ __device__ __forceinline__ void tile_matvec_smemA32(const float4 *__restrict__ A
         split_tf32(c1, bh1, bl1);
         mma_tf32(acc0, ah, bh0, bh1);
         mma_tf32(acc1, al, bh0, bh1);
-        mma_tf32(acc2, ah, bl0, bl1);
+        if constexpr (ACC3) mma_tf32(acc2, ah, bl0, bl1); else mma_tf32(acc1, ah, bl0, bl1);
     }
 #pragma unroll
     for (int i = 0; i < 4; i++) out[i] = acc0[i] + (acc1[i] + acc2[i]);
 }
 
 // Register-A variant over a sub-range of the k chunks (phase 2 of the wide kernel: half the range per warp).
-template <int KC0, int N, int P>
+template <int KC0, int N, int P, bool ACC3>
 __device__ __forceinline__ void tile_matvec_range(const float (&w)[N][4], const float *__restrict__ Bf, int g, int t4,
                                                   float (&out)[4])
 {
@@ -142,7 +146,7 @@ __device__ __forceinline__ void tile_matvec_range(const float (&w)[N][4], const 
         split_tf32(c1, bh1, bl1);
         mma_tf32(acc0, ah, bh0, bh1);
         mma_tf32(acc1, al, bh0, bh1);
-        mma_tf32(acc2, ah, bl0, bl1);
+        if constexpr (ACC3) mma_tf32(acc2, ah, bl0, bl1); else mma_tf32(acc1, ah, bl0, bl1);
     }
 #pragma unroll
     for (int i = 0; i < 4; i++) out[i] = acc0[i] + (acc1[i] + acc2[i]);
@@ -180,7 +184,10 @@ __device__ __forceinline__ void tile_matvec_smemA(const uint4 *__restrict__ Ahi,
     for (int i = 0; i < 4; i++) out[i] = acc0[i] + (acc1[i] + acc2[i]);
 }
 
-template <int HP>
+// WIDE (H > 96): 2*NT warps can no longer keep a whole 16 x HP phase-1 tile in registers (the register file is
+// 64K words per SM), so the phase-1 fragments of sW live in shared memory as fp32 (2*HP*HP words) and each warp
+// keeps its HALF of the phase-2 (sW2) tile in registers instead.
+template <int HP, bool WIDE>
 __global__ void __launch_bounds__(HP * 4, 1)
 gru_mma_kernel(const float *__restrict__ vI, const float *__restrict__ sW, const float *__restrict__ sW2,
                float *__restrict__ y, long ldy, const int32_t *__restrict__ lengths, int T, int B, int H, int reverse)
@@ -196,7 +203,9 @@ gru_mma_kernel(const float *__restrict__ vI, const float *__restrict__ sW, const
     float *vbuf = RH + BT * P;                                   // [3][8][VLD] staged vI (ring: t, t+1, t+2)
     uint4 *Wchi = reinterpret_cast<uint4 *>(vbuf + 3 * BT * VLD);     // [NT][NKC][32] sW2 A fragments, tf32 hi
     uint4 *Wclo = Wchi + NT * NKC * 32;                          //                                      tf32 lo
+    float4 *W1f = reinterpret_cast<float4 *>(Wchi);              // WIDE: [2*NT][NKC][32] sW A fragments, fp32 (same bytes)
     float4 *Cx = reinterpret_cast<float4 *>(Wclo + NT * NKC * 32);   // [NT][32] phase-2 partial sums of the role-1 warps
+    float4 *Zx = Cx + NT * 32;                                   // WIDE: [NT][32] the owners' z, parked during phase 2
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t4 = lane & 3;
@@ -207,9 +216,27 @@ gru_mma_kernel(const float *__restrict__ vI, const float *__restrict__ sW, const
     auto wload = [&](const float *Wm, int row_in_gate, int gate_row0, int k) -> float {
         return (row_in_gate < H && k < H) ? __ldg(Wm + (long)(gate_row0 + row_in_gate) * H + k) : 0.0f;
     };
-    float wa[NKC][4];                        // phase 1: z tile (role 0) or r tile (role 1) of sW
+    constexpr int NWA = WIDE ? NKC / 2 : NKC;
+    constexpr bool PIN_W = HP >= 144;        // 18 warps: 96 registers per thread
+    float wa[NWA][4];                        // phase 1: z tile (role 0) or r tile (role 1) of sW; WIDE: half c tile of sW2
     for (int e = tid; e < 3 * BT * P + 3 * BT * VLD; e += NTHREADS) smem[e] = 0.0f;
-    {
+    if constexpr (WIDE) {
+        const int r0 = 16 * jt + g, r1 = r0 + 8;
+        const int gate0 = role == 0 ? 0 : H;
+        for (int kc = 0; kc < NKC; kc++) {
+            const int k0 = 8 * kc + t4, k1 = k0 + 4;
+            W1f[((role * NT + jt) * NKC + kc) * 32 + lane] =
+                make_float4(wload(sW, r0, gate0, k0), wload(sW, r1, gate0, k0), wload(sW, r0, gate0, k1), wload(sW, r1, gate0, k1));
+        }
+#pragma unroll
+        for (int c = 0; c < NWA; c++) {
+            const int k0 = 8 * (role * NWA + c) + t4, k1 = k0 + 4;
+            wa[c][0] = wload(sW2, r0, 0, k0);
+            wa[c][1] = wload(sW2, r1, 0, k0);
+            wa[c][2] = wload(sW2, r0, 0, k1);
+            wa[c][3] = wload(sW2, r1, 0, k1);
+        }
+    } else {
         const int r0 = 16 * jt + g, r1 = r0 + 8;
         const int gate0 = role == 0 ? 0 : H;
 #pragma unroll
@@ -232,13 +259,13 @@ gru_mma_kernel(const float *__restrict__ vI, const float *__restrict__ sW, const
     }
 
     // fragment element i of this lane: row j = 16*jt + g + 8*(i >> 1), sequence b = 2*t4 + (i & 1)
-    int jrow[4], bcol[4], len[4];
+    // len[i] = number of steps for which element i is live (0 for padding rows j >= H and sequences past B)
+    int len[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) {
-        jrow[i] = 16 * jt + g + 8 * (i >> 1);
-        bcol[i] = 2 * t4 + (i & 1);
-        const int bg = b_base + bcol[i];
-        len[i] = bg < B ? (lengths ? min(lengths[bg], T) : T) : 0;
+        const int j = 16 * jt + g + 8 * (i >> 1);
+        const int bg = b_base + 2 * t4 + (i & 1);
+        len[i] = (bg < B && j < H) ? (lengths ? min(lengths[bg], T) : T) : 0;
     }
 
     // ---- I/O (role-1 warps): per-thread work lists are fixed for the whole scan, so the index math is done once ----
@@ -246,31 +273,10 @@ gru_mma_kernel(const float *__restrict__ vI, const float *__restrict__ sW, const
     const long H3 = 3L * H;
     const bool vec_vi = ((H3 & 3) == 0) && (((uintptr_t)vI & 15) == 0);
     const bool vec_y = ((ldy & 3) == 0) && ((H & 3) == 0) && (((uintptr_t)y & 15) == 0);
-    constexpr int MAXV = (BT * 3 * HP / 4 + 32 * (HP / 16) - 1) / (32 * (HP / 16));     // float4 copies of vI per I/O thread
-    constexpr int MAXY = (BT * HP / 4 + 32 * (HP / 16) - 1) / (32 * (HP / 16));         // float4 copies of h per I/O thread
-    int v_src[MAXV], v_dst[MAXV], y_src[MAXY];      // element offsets (-1 = none); src relative to row (t, b_base)
-    long y_dst[MAXY];
-    {
-        const int n4 = (int)(H3 >> 2), h4 = H >> 2;
-#pragma unroll
-        for (int i = 0; i < MAXV; i++) {
-            const int e = io_tid + i * io_n;
-            v_src[i] = -1; v_dst[i] = 0;
-            if (role == 1 && vec_vi && e < BT * n4) {
-                const int b = e / n4, c = e - b * n4;
-                if (b_base + b < B) { v_src[i] = b * (int)H3 + 4 * c; v_dst[i] = b * VLD + 4 * c; }
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < MAXY; i++) {
-            const int e = io_tid + i * io_n;
-            y_src[i] = -1; y_dst[i] = 0;
-            if (role == 1 && vec_y && e < BT * h4) {
-                const int b = e / h4, c = e - b * h4;
-                if (b_base + b < B) { y_src[i] = b * P + 4 * c; y_dst[i] = (long)b * ldy + 4 * c; }
-            }
-        }
-    }
+    // aligned (128-bit) work split, fixed for the whole scan: vI row b = vq + 2k (k = 0..3), float4 column vc;
+    // h row yb, float4 column yc.  io_n = 2*HP threads; 3H/4 < HP and 8 * (HP/4) = io_n.
+    // (derived from the thread index inside the lambdas: the wide kernel recomputes them every step from a
+    // laundered copy rather than holding them in registers across the matrix products)
     auto stage_vi = [&](int t, int slot, int who, int nwho) {          // generic (prologue / unaligned) path
         if (t < 0 || t >= T) return;
         float *dst = vbuf + slot * BT * VLD;
@@ -279,14 +285,29 @@ gru_mma_kernel(const float *__restrict__ vI, const float *__restrict__ sW, const
             if (b_base + b < B) dst[b * VLD + c] = __ldg(vI + ((long)t * B + b_base + b) * H3 + c);
         }
     };
-    auto stage_vi_fast = [&](int t, int slot) {                        // role-1 threads, cp.async
+    auto stage_vi_fast = [&](int t, int slot, int io_tid) {                        // role-1 threads, cp.async
         if (t < 0 || t >= T) return;
-        if (!vec_vi) { stage_vi(t, slot, io_tid, io_n); return; }
         float *dst = vbuf + slot * BT * VLD;
         const float *src = vI + ((long)t * B + b_base) * H3;
+        if (!vec_vi) {                       // rows not 16-byte aligned: 4-byte async copies, <= 2 columns per thread and row
+            const int c0 = io_tid, c1 = io_tid + io_n;                 // io_n = 2*HP >= 2*H, so 3H < 2*io_n
 #pragma unroll
-        for (int i = 0; i < MAXV; i++)
-            if (v_src[i] >= 0) cp_async16(dst + v_dst[i], src + v_src[i]);
+            for (int b = 0; b < BT; b++) {
+                if (b_base + b < B) {
+                    if (c0 < (int)H3) cp_async4(dst + b * VLD + c0, src + b * H3 + c0);
+                    if (c1 < (int)H3) cp_async4(dst + b * VLD + c1, src + b * H3 + c1);
+                }
+            }
+            return;
+        }
+        const int vq = io_tid / HP, vc = io_tid - vq * HP;
+        if (4 * vc < (int)H3) {
+#pragma unroll
+            for (int k = 0; k < BT / 2; k++) {
+                const int b = vq + 2 * k;
+                if (b_base + b < B) cp_async16(dst + b * VLD + 4 * vc, src + b * H3 + 4 * vc);
+            }
+        }
     };
     auto store_h = [&](int t, int slot, int who, int nwho) {           // generic path: Hf[slot] -> y[t]
         const float *src = Hf + slot * BT * P;
@@ -295,13 +316,19 @@ gru_mma_kernel(const float *__restrict__ vI, const float *__restrict__ sW, const
             if (b_base + b < B) y[((long)t * B + b_base + b) * ldy + j] = src[b * P + j];
         }
     };
-    auto store_h_fast = [&](int t, int slot) {                         // role-1 threads, 128-bit
-        if (!vec_y) { store_h(t, slot, io_tid, io_n); return; }
+    auto store_h_fast = [&](int t, int slot, int io_tid) {                         // role-1 threads, 128-bit
         const float *src = Hf + slot * BT * P;
         float *dst = y + ((long)t * B + b_base) * ldy;
+        if (!vec_y) {                        // unaligned rows: one column per thread and row, coalesced 4-byte stores
+            if (io_tid < H) {
 #pragma unroll
-        for (int i = 0; i < MAXY; i++)
-            if (y_src[i] >= 0) *reinterpret_cast<float4 *>(dst + y_dst[i]) = *reinterpret_cast<const float4 *>(src + y_src[i]);
+                for (int b = 0; b < BT; b++)
+                    if (b_base + b < B) dst[(long)b * ldy + io_tid] = src[b * P + io_tid];
+            }
+            return;
+        }
+        const int yb = io_tid / (HP / 4), yc = io_tid - yb * (HP / 4);
+        if (4 * yc < H && b_base + yb < B) *reinterpret_cast<float4 *>(dst + (long)yb * ldy + 4 * yc) = *reinterpret_cast<const float4 *>(src + yb * P + 4 * yc);
     };
 
     const int tstep = reverse ? -1 : 1;
@@ -315,42 +342,41 @@ gru_mma_kernel(const float *__restrict__ vI, const float *__restrict__ sW, const
     float zreg[4];
 
     // smem offsets of this lane's 4 fragment elements (row j, sequence b): fixed for the whole scan
+    // (element i sits at compile-time offsets from element 0, so one base register serves all four)
+    const int o_st0 = 2 * t4 * P + 16 * jt + g, o_vi0 = 2 * t4 * VLD + 16 * jt + g;
     int o_st[4], o_vi[4];
 #pragma unroll
-    for (int i = 0; i < 4; i++) { o_st[i] = bcol[i] * P + jrow[i]; o_vi[i] = bcol[i] * VLD + jrow[i]; }
+    for (int i = 0; i < 4; i++) { o_st[i] = o_st0 + (i & 1) * P + 8 * (i >> 1); o_vi[i] = o_vi0 + (i & 1) * VLD + 8 * (i >> 1); }
 
-    for (int s = 0; s < T; s++, t += tstep) {
-        const int slot = s & 1;              // Hf[slot] receives h_t, Hf[slot^1] holds h_{t-1}
-        const float *vrow = vbuf + (s % 3) * BT * VLD;
-
-        // ---------------- phase 1: z (role 0) / r (role 1) pre-activations ----------------
-        // the epilogues below are written load-all / compute-all / store-all with unconditional stores
-        // (rows j >= H carry exact zeros) so that the four elements' MUFU chains overlap
-        float pre[4];
-        tile_matvec<NKC, P>(wa, Hf + (slot ^ 1) * BT * P, g, t4, pre);
-        if (role == 0) {
+    // The two roles run separate copies of the scan loop (same barrier sequence) so that neither carries the
+    // other's loop state in registers: the owners keep z / h / lengths, the role-1 warps the I/O bookkeeping.
+    // The epilogues are written load-all / compute-all / store-all with unconditional stores so that the four
+    // elements' MUFU chains overlap.
+    if (role == 0) {
+        for (int s = 0; s < T; s++, t += tstep) {
+            const int slot = s & 1;          // Hf[slot] receives h_t, Hf[slot^1] holds h_{t-1}
+            const float *vrow = vbuf + (s % 3) * BT * VLD;
+            if constexpr (PIN_W) {           // keep the compiler from hoisting the tf32 split of the weights (2x the registers)
+#pragma unroll
+                for (int c = 0; c < NWA; c++)
+#pragma unroll
+                    for (int i = 0; i < 4; i++) asm volatile("" : "+f"(wa[c][i]));
+            }
+            // ---- phase 1: z pre-activations ----
+            float pre[4];
+            if constexpr (WIDE) tile_matvec_smemA32<NKC, P, (HP < 160)>(W1f + jt * NKC * 32, lane, Hf + (slot ^ 1) * BT * P, g, t4, pre);
+            else tile_matvec<NKC, P>(wa, Hf + (slot ^ 1) * BT * P, g, t4, pre);
             float vz[4];
 #pragma unroll
             for (int i = 0; i < 4; i++) vz[i] = vrow[o_vi[i]];
 #pragma unroll
             for (int i = 0; i < 4; i++) zreg[i] = sigmoid_fast(pre[i] + vz[i]);
+            if constexpr (WIDE) Zx[jt * 32 + lane] = make_float4(zreg[0], zreg[1], zreg[2], zreg[3]);   // (registers are short)
             bar_sync(1, NTHREADS);           // wait for r*h of every row
-        } else {
-            const float *hprev = Hf + (slot ^ 1) * BT * P;
-            float vr[4], hp[4];
-#pragma unroll
-            for (int i = 0; i < 4; i++) { vr[i] = vrow[o_vi[i] + H]; hp[i] = hprev[o_st[i]]; }
-            float rh[4];
-#pragma unroll
-            for (int i = 0; i < 4; i++) rh[i] = sigmoid_fast(pre[i] + vr[i]) * hp[i];
-#pragma unroll
-            for (int i = 0; i < 4; i++) RH[o_st[i]] = rh[i];
-        }
-
-        // ---------------- phase 2 ----------------
-        if (role == 0) {
+            // ---- phase 2: first half of the k range of the c tile, blend ----
             float cpre[4];
-            tile_matvec_smemA<0, NKC / 2, P>(Wchi + jt * NKC * 32, Wclo + jt * NKC * 32, lane, RH, g, t4, cpre);
+            if constexpr (WIDE) tile_matvec_range<0, NWA, P, (HP < 160)>(wa, RH, g, t4, cpre);
+            else tile_matvec_smemA<0, NKC / 2, P>(Wchi + jt * NKC * 32, Wclo + jt * NKC * 32, lane, RH, g, t4, cpre);
             bar_sync(2 + jt, 64);            // partner's half of the k range
             {
                 const float4 px = Cx[jt * 32 + lane];
@@ -360,29 +386,65 @@ gru_mma_kernel(const float *__restrict__ vI, const float *__restrict__ sW, const
             float vc[4];
 #pragma unroll
             for (int i = 0; i < 4; i++) vc[i] = vrow[o_vi[i] + 2 * H];
+            if constexpr (WIDE) {            // z and h_{t-1} come back from shared memory (same lane wrote both)
+                const float4 z4 = Zx[jt * 32 + lane];
+                zreg[0] = z4.x; zreg[1] = z4.y; zreg[2] = z4.z; zreg[3] = z4.w;
+                const float *hprev = Hf + (slot ^ 1) * BT * P;
+#pragma unroll
+                for (int i = 0; i < 4; i++) hreg[i] = hprev[o_st[i]];
+            }
 #pragma unroll
             for (int i = 0; i < 4; i++) {
                 const float hbar = tanh_fast(cpre[i] + vc[i]);
                 float hn = zreg[i] * hreg[i] + (1.0f - zreg[i]) * hbar;
-                hn = (t < len[i] && jrow[i] < H) ? hn : 0.0f;     // ragged batch: state stays 0 outside the read
+                hn = t < len[i] ? hn : 0.0f;     // ragged batch: state stays 0 outside the read
                 hreg[i] = hn;
             }
 #pragma unroll
             for (int i = 0; i < 4; i++) hout[o_st[i]] = hreg[i];
-        } else {
+            bar_sync(0, NTHREADS);
+        }
+    } else {
+        for (int s = 0; s < T; s++, t += tstep) {
+            const int slot = s & 1;
+            const float *vrow = vbuf + (s % 3) * BT * VLD;
+            if constexpr (PIN_W) {
+#pragma unroll
+                for (int c = 0; c < NWA; c++)
+#pragma unroll
+                    for (int i = 0; i < 4; i++) asm volatile("" : "+f"(wa[c][i]));
+            }
+            // ---- phase 1: r pre-activations, r * h_{t-1} ----
+            float pre[4];
+            if constexpr (WIDE) tile_matvec_smemA32<NKC, P, (HP < 160)>(W1f + (NT + jt) * NKC * 32, lane, Hf + (slot ^ 1) * BT * P, g, t4, pre);
+            else tile_matvec<NKC, P>(wa, Hf + (slot ^ 1) * BT * P, g, t4, pre);
+            const float *hprev = Hf + (slot ^ 1) * BT * P;
+            float vr[4], hp[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) { vr[i] = vrow[o_vi[i] + H]; hp[i] = hprev[o_st[i]]; }
+            float rh[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) rh[i] = sigmoid_fast(pre[i] + vr[i]) * hp[i];
+#pragma unroll
+            for (int i = 0; i < 4; i++) RH[o_st[i]] = rh[i];
             bar_sync(1, NTHREADS);           // r*h of every row: now every warp consumes it
+            // ---- phase 2: second half of the k range of the c tile ----
             float cpart[4];
-            tile_matvec_smemA<NKC / 2, NKC, P>(Wchi + jt * NKC * 32, Wclo + jt * NKC * 32, lane, RH, g, t4, cpart);
+            if constexpr (WIDE) tile_matvec_range<NKC / 2, NWA, P, (HP < 160)>(wa, RH, g, t4, cpart);
+            else tile_matvec_smemA<NKC / 2, NKC, P>(Wchi + jt * NKC * 32, Wclo + jt * NKC * 32, lane, RH, g, t4, cpart);
             Cx[jt * 32 + lane] = make_float4(cpart[0], cpart[1], cpart[2], cpart[3]);
             bar_arrive(2 + jt, 64);
             // HBM traffic: vI two steps ahead (slot read last in step s-1), h_{t-1} (complete since the last barrier) out
-            stage_vi_fast(t + 2 * tstep, (s + 2) % 3);
+            int it = io_tid;
+            if constexpr (WIDE) { it = (int)threadIdx.x - NT * 32; asm volatile("" : "+r"(it)); }
+            stage_vi_fast(t + 2 * tstep, (s + 2) % 3, it);
             cp_async_commit();
-            if (s > 0) store_h_fast(t - tstep, slot ^ 1);
+            if (s > 0) store_h_fast(t - tstep, slot ^ 1, it);
             cp_async_wait_1();               // vI of step s+1 (issued one step ago) has landed
+            bar_sync(0, NTHREADS);
         }
-        __syncthreads();
     }
+    t = (reverse ? T - 1 : 0) + T * tstep;
     if (T > 0) store_h(t - tstep, (T - 1) & 1, tid, NTHREADS);           // last step's state
 }
 
@@ -392,8 +454,8 @@ static int launch(const float *vI, const float *sW, const float *sW2, float *y, 
 {
     constexpr int P = HP + 4, VLD = 3 * HP + 4;
     const size_t smem = sizeof(float) * ((size_t)3 * BT * P + (size_t)3 * BT * VLD) + (size_t)2 * (HP / 16) * (HP / 8) * 32 * 16 +
-                        (size_t)(HP / 16) * 32 * 16;
-    auto kern = gru_mma_kernel<HP>;
+                        (size_t)(HP / 16) * 32 * 16 * (HP > 96 ? 2 : 1);
+    auto kern = gru_mma_kernel<HP, (HP > 96)>;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return (int)err;
     const unsigned grid = (unsigned)ceil_div(B, BT);
@@ -401,7 +463,7 @@ static int launch(const float *vI, const float *sW, const float *sW2, float *y, 
     SLOIKA_RETURN_LAUNCH_STATUS();
 }
 
-// tanh / sigmoid GRUs with H <= 96; SLOIKA_ERR_UNSUPPORTED otherwise (caller falls back to gru_v2 / gru).
+// tanh / sigmoid GRUs with H <= 144; SLOIKA_ERR_UNSUPPORTED otherwise (caller falls back to gru_v2 / gru).
 int dispatch(const float *vI, const float *sW, const float *sW2, float *y, long ldy, const int32_t *lengths, int T, int B,
              int H, int reverse, int act, int gate_act, cudaStream_t st)
 {
@@ -411,6 +473,9 @@ int dispatch(const float *vI, const float *sW, const float *sW2, float *y, long 
     if (H <= 64) return launch<64>(vI, sW, sW2, y, ldy, lengths, T, B, H, reverse, st);
     if (H <= 80) return launch<80>(vI, sW, sW2, y, ldy, lengths, T, B, H, reverse, st);
     if (H <= 96) return launch<96>(vI, sW, sW2, y, ldy, lengths, T, B, H, reverse, st);
+    if (H <= 112) return launch<112>(vI, sW, sW2, y, ldy, lengths, T, B, H, reverse, st);
+    if (H <= 128) return launch<128>(vI, sW, sW2, y, ldy, lengths, T, B, H, reverse, st);
+    if (H <= 144) return launch<144>(vI, sW, sW2, y, ldy, lengths, T, B, H, reverse, st);
     return SLOIKA_ERR_UNSUPPORTED;
 }
 
