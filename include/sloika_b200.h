@@ -118,8 +118,9 @@ int sloika_gru_fwd(const float *x, long ldx, const float *iW, const float *sW, c
                    const float *b, float *y, long ldy, void *ws, size_t ws_bytes, const int32_t *lengths,
                    int T, int B, int I, int H, int reverse, int act, int gate_act, void *stream);
 
-/* The recurrence alone, given vI [T,B,3H] dense (what sloika_gru_fwd runs after the projection). */
-int sloika_gru_recurrence_fwd(const float *vI, const float *sW, const float *sW2, float *y, long ldy,
+/* The recurrence alone, given vI: T*B rows of 3H floats with row pitch ld_vi >= 3H (what sloika_gru_fwd runs
+ * after the projection; a pitch that is a multiple of 4 floats keeps every row 16-byte aligned for odd H). */
+int sloika_gru_recurrence_fwd(const float *vI, long ld_vi, const float *sW, const float *sW2, float *y, long ldy,
                               const int32_t *lengths, int T, int B, int H, int reverse, int act,
                               int gate_act, void *stream);
 

@@ -89,7 +89,7 @@ __device__ __forceinline__ void reduce_scatter(float (&v)[R][GRU_BT], float (&ou
 
 template <int HP, int S, int W2MODE>
 __global__ void __launch_bounds__(GruCfg<HP, S>::THREADS, 1)
-gru_recurrence_kernel(const float *__restrict__ vI, const float *__restrict__ sW, const float *__restrict__ sW2,
+gru_recurrence_kernel(const float *__restrict__ vI, long ldv, const float *__restrict__ sW, const float *__restrict__ sW2,
                       float *__restrict__ y, long ldy, const int32_t *__restrict__ lengths, int T, int B, int H,
                       int reverse, int act, int gate_act)
 {
@@ -156,9 +156,8 @@ gru_recurrence_kernel(const float *__restrict__ vI, const float *__restrict__ sW
         len[e] = bok[e] ? (lengths ? min(lengths[bgl], T) : T) : 0;
     }
 
-    const long H3 = 3L * H;
     auto vi_ptr = [&](int t, int e, int jj, int gate) -> const float * {
-        return vI + ((long)t * B + (b_base + bl0 + e)) * H3 + (long)gate * H + jown[jj];
+        return vI + ((long)t * B + (b_base + bl0 + e)) * ldv + (long)gate * H + jown[jj];
     };
     // vI registers for the current step: [jj][e][gate]
     float vcur[NJ][2][3];
@@ -296,7 +295,7 @@ gru_recurrence_kernel(const float *__restrict__ vI, const float *__restrict__ sW
 }
 
 template <int HP, int S, int W2MODE>
-static int launch_gru(const float *vI, const float *sW, const float *sW2, float *y, long ldy, const int32_t *lengths,
+static int launch_gru(const float *vI, long ldv, const float *sW, const float *sW2, float *y, long ldy, const int32_t *lengths,
                       int T, int B, int H, int reverse, int act, int gate_act, cudaStream_t st)
 {
     using Cfg = GruCfg<HP, S>;
@@ -306,16 +305,12 @@ static int launch_gru(const float *vI, const float *sW, const float *sW2, float 
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return (int)err;
     const unsigned grid = (unsigned)ceil_div(B, GRU_BT);
-    kern<<<grid, Cfg::THREADS, smem, st>>>(vI, sW, sW2, y, ldy, lengths, T, B, H, reverse, act, gate_act);
+    kern<<<grid, Cfg::THREADS, smem, st>>>(vI, ldv, sW, sW2, y, ldy, lengths, T, B, H, reverse, act, gate_act);
     SLOIKA_RETURN_LAUNCH_STATUS();
 }
 
 namespace gru3 {
-int dispatch(const float *vI, const float *sW, const float *sW2, float *y, long ldy, const int32_t *lengths, int T, int B,
-             int H, int reverse, int act, int gate_act, cudaStream_t st);
-}
-namespace gru2 {
-int dispatch(const float *vI, const float *sW, const float *sW2, float *y, long ldy, const int32_t *lengths, int T, int B,
+int dispatch(const float *vI, long ldv, const float *sW, const float *sW2, float *y, long ldy, const int32_t *lengths, int T, int B,
              int H, int reverse, int act, int gate_act, cudaStream_t st);
 }
 
@@ -323,29 +318,24 @@ int dispatch(const float *vI, const float *sW, const float *sW2, float *y, long 
 
 using namespace sloika;
 
-extern "C" int sloika_gru_recurrence_fwd(const float *vI, const float *sW, const float *sW2, float *y, long ldy,
+extern "C" int sloika_gru_recurrence_fwd(const float *vI, long ldv, const float *sW, const float *sW2, float *y, long ldy,
                                          const int32_t *lengths, int T, int B, int H, int reverse, int act,
                                          int gate_act, void *stream)
 {
-    if (!vI || !sW || !sW2 || !y || T < 0 || B <= 0 || H <= 0 || ldy < H) return SLOIKA_ERR_ARG;
+    if (!vI || !sW || !sW2 || !y || T < 0 || B <= 0 || H <= 0 || ldy < H || ldv < 3L * H) return SLOIKA_ERR_ARG;
     if (!act_known(act) || !act_known(gate_act)) return SLOIKA_ERR_UNSUPPORTED;
     if (T == 0) return SLOIKA_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    {   // kernel generations, newest first: mma.sync tensor-core kernel (gru_mma.cu, H <= 96), register-resident
-        // FFMA2 kernel (gru_v2.cu), shared-memory FFMA2 kernel (this file).  SLOIKA_B200_GRU=v1|v2 caps the choice.
+    {   // mma.sync tensor-core kernel (gru_mma.cu: tanh / sigmoid, H <= 144) first, then the FFMA2 kernel of this
+        // file (any activation pair).  SLOIKA_B200_GRU=v1 forces the latter (A/B measurements, tests).
         const char *sel = getenv("SLOIKA_B200_GRU");
-        const int cap = (sel && sel[0] == 'v' && sel[1] >= '1' && sel[1] <= '3') ? sel[1] - '0' : 3;
-        if (cap >= 3) {
-            const int rc = gru3::dispatch(vI, sW, sW2, y, ldy, lengths, T, B, H, reverse, act, gate_act, st);
-            if (rc != SLOIKA_ERR_UNSUPPORTED) return rc;
-        }
-        if (cap >= 2) {
-            const int rc = gru2::dispatch(vI, sW, sW2, y, ldy, lengths, T, B, H, reverse, act, gate_act, st);
+        if (!(sel && sel[0] == 'v' && sel[1] == '1')) {
+            const int rc = gru3::dispatch(vI, ldv, sW, sW2, y, ldy, lengths, T, B, H, reverse, act, gate_act, st);
             if (rc != SLOIKA_ERR_UNSUPPORTED) return rc;
         }
     }
 #define GRU_CASE(HP_, S_, W2R_) \
-    return launch_gru<HP_, S_, W2R_>(vI, sW, sW2, y, ldy, lengths, T, B, H, reverse, act, gate_act, st)
+    return launch_gru<HP_, S_, W2R_>(vI, ldv, sW, sW2, y, ldy, lengths, T, B, H, reverse, act, gate_act, st)
     if (H <= 16) GRU_CASE(16, 4, 0);
     if (H <= 32) GRU_CASE(32, 8, 0);
     if (H <= 48) GRU_CASE(48, 4, 0);
@@ -375,5 +365,5 @@ extern "C" int sloika_gru_fwd(const float *x, long ldx, const float *iW, const f
     float *vI = static_cast<float *>(ws);
     int rc = sloika_linear_fwd(x, ldx, iW, b, vI, 3L * H, (long)T * B, I, 3 * H, SLOIKA_ACT_LINEAR, stream);
     if (rc != SLOIKA_OK) return rc;
-    return sloika_gru_recurrence_fwd(vI, sW, sW2, y, ldy, lengths, T, B, H, reverse, act, gate_act, stream);
+    return sloika_gru_recurrence_fwd(vI, 3L * H, sW, sW2, y, ldy, lengths, T, B, H, reverse, act, gate_act, stream);
 }

@@ -1,6 +1,6 @@
 // GRU recurrence on the tensor cores (warp-level mma.sync, 3xTF32 split = fp32-equivalent accuracy).
 //
-// Same semantics and CTA decomposition as gru.cu / gru_v2.cu (one persistent CTA per 8 sequences, all of
+// Same semantics and CTA decomposition as gru.cu (one persistent CTA per 8 sequences, all of
 // sW | sW2 on chip, two CTA barriers per step; reference sloika/layers.py:1010-1021, :85-88, :1449-1450).
 // Why a third kernel: measurements on B200 (tools/*_probe.cu, profiles/) showed
 //   * the FFMA2 kernels are bounded by register-delivery of h from shared memory (every lane must
@@ -189,7 +189,7 @@ __device__ __forceinline__ void tile_matvec_smemA(const uint4 *__restrict__ Ahi,
 // keeps its HALF of the phase-2 (sW2) tile in registers instead.
 template <int HP, bool WIDE>
 __global__ void __launch_bounds__(HP * 4, 1)
-gru_mma_kernel(const float *__restrict__ vI, const float *__restrict__ sW, const float *__restrict__ sW2,
+gru_mma_kernel(const float *__restrict__ vI, long ldv, const float *__restrict__ sW, const float *__restrict__ sW2,
                float *__restrict__ y, long ldy, const int32_t *__restrict__ lengths, int T, int B, int H, int reverse)
 {
     constexpr int NT = HP / 16;              // 16-row tiles per gate
@@ -271,8 +271,8 @@ gru_mma_kernel(const float *__restrict__ vI, const float *__restrict__ sW, const
     // ---- I/O (role-1 warps): per-thread work lists are fixed for the whole scan, so the index math is done once ----
     const int io_tid = tid - NT * 32, io_n = NT * 32;
     const long H3 = 3L * H;
-    const bool vec_vi = ((H3 & 3) == 0) && (((uintptr_t)vI & 15) == 0);
-    const bool vec_y = ((ldy & 3) == 0) && ((H & 3) == 0) && (((uintptr_t)y & 15) == 0);
+    const bool vec_vi = ((ldv & 3) == 0) && (((uintptr_t)vI & 15) == 0);    // then ldv >= roundup4(3H): whole float4s
+    const bool vec_y = ((ldy & 3) == 0) && (((uintptr_t)y & 15) == 0);
     // aligned (128-bit) work split, fixed for the whole scan: vI row b = vq + 2k (k = 0..3), float4 column vc;
     // h row yb, float4 column yc.  io_n = 2*HP threads; 3H/4 < HP and 8 * (HP/4) = io_n.
     // (derived from the thread index inside the lambdas: the wide kernel recomputes them every step from a
@@ -282,20 +282,20 @@ gru_mma_kernel(const float *__restrict__ vI, const float *__restrict__ sW, const
         float *dst = vbuf + slot * BT * VLD;
         for (int e = who; e < BT * (int)H3; e += nwho) {
             const int b = e / (int)H3, c = e - b * (int)H3;
-            if (b_base + b < B) dst[b * VLD + c] = __ldg(vI + ((long)t * B + b_base + b) * H3 + c);
+            if (b_base + b < B) dst[b * VLD + c] = __ldg(vI + ((long)t * B + b_base + b) * ldv + c);
         }
     };
     auto stage_vi_fast = [&](int t, int slot, int io_tid) {                        // role-1 threads, cp.async
         if (t < 0 || t >= T) return;
         float *dst = vbuf + slot * BT * VLD;
-        const float *src = vI + ((long)t * B + b_base) * H3;
+        const float *src = vI + ((long)t * B + b_base) * ldv;
         if (!vec_vi) {                       // rows not 16-byte aligned: 4-byte async copies, <= 2 columns per thread and row
             const int c0 = io_tid, c1 = io_tid + io_n;                 // io_n = 2*HP >= 2*H, so 3H < 2*io_n
 #pragma unroll
             for (int b = 0; b < BT; b++) {
                 if (b_base + b < B) {
-                    if (c0 < (int)H3) cp_async4(dst + b * VLD + c0, src + b * H3 + c0);
-                    if (c1 < (int)H3) cp_async4(dst + b * VLD + c1, src + b * H3 + c1);
+                    if (c0 < (int)H3) cp_async4(dst + b * VLD + c0, src + b * ldv + c0);
+                    if (c1 < (int)H3) cp_async4(dst + b * VLD + c1, src + b * ldv + c1);
                 }
             }
             return;
@@ -305,7 +305,7 @@ gru_mma_kernel(const float *__restrict__ vI, const float *__restrict__ sW, const
 #pragma unroll
             for (int k = 0; k < BT / 2; k++) {
                 const int b = vq + 2 * k;
-                if (b_base + b < B) cp_async16(dst + b * VLD + 4 * vc, src + b * H3 + 4 * vc);
+                if (b_base + b < B) cp_async16(dst + b * VLD + 4 * vc, src + b * ldv + 4 * vc);
             }
         }
     };
@@ -328,7 +328,17 @@ gru_mma_kernel(const float *__restrict__ vI, const float *__restrict__ sW, const
             return;
         }
         const int yb = io_tid / (HP / 4), yc = io_tid - yb * (HP / 4);
-        if (4 * yc < H && b_base + yb < B) *reinterpret_cast<float4 *>(dst + (long)yb * ldy + 4 * yc) = *reinterpret_cast<const float4 *>(src + yb * P + 4 * yc);
+        if (4 * yc < H && b_base + yb < B) {
+            float *d = dst + (long)yb * ldy + 4 * yc;
+            const float *sp = src + yb * P + 4 * yc;
+            if (4 * yc + 3 < H) {
+                *reinterpret_cast<float4 *>(d) = *reinterpret_cast<const float4 *>(sp);
+            } else {                         // last, partial quad of a row whose width is not a multiple of 4
+                d[0] = sp[0];
+                if (4 * yc + 1 < H) d[1] = sp[1];
+                if (4 * yc + 2 < H) d[2] = sp[2];
+            }
+        }
     };
 
     const int tstep = reverse ? -1 : 1;
@@ -449,7 +459,7 @@ gru_mma_kernel(const float *__restrict__ vI, const float *__restrict__ sW, const
 }
 
 template <int HP>
-static int launch(const float *vI, const float *sW, const float *sW2, float *y, long ldy, const int32_t *lengths, int T,
+static int launch(const float *vI, long ldv, const float *sW, const float *sW2, float *y, long ldy, const int32_t *lengths, int T,
                   int B, int H, int reverse, cudaStream_t st)
 {
     constexpr int P = HP + 4, VLD = 3 * HP + 4;
@@ -459,23 +469,23 @@ static int launch(const float *vI, const float *sW, const float *sW2, float *y, 
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return (int)err;
     const unsigned grid = (unsigned)ceil_div(B, BT);
-    kern<<<grid, HP * 4, smem, st>>>(vI, sW, sW2, y, ldy, lengths, T, B, H, reverse);
+    kern<<<grid, HP * 4, smem, st>>>(vI, ldv, sW, sW2, y, ldy, lengths, T, B, H, reverse);
     SLOIKA_RETURN_LAUNCH_STATUS();
 }
 
-// tanh / sigmoid GRUs with H <= 144; SLOIKA_ERR_UNSUPPORTED otherwise (caller falls back to gru_v2 / gru).
-int dispatch(const float *vI, const float *sW, const float *sW2, float *y, long ldy, const int32_t *lengths, int T, int B,
+// tanh / sigmoid GRUs with H <= 144; SLOIKA_ERR_UNSUPPORTED otherwise (caller falls back to gru.cu).
+int dispatch(const float *vI, long ldv, const float *sW, const float *sW2, float *y, long ldy, const int32_t *lengths, int T, int B,
              int H, int reverse, int act, int gate_act, cudaStream_t st)
 {
     if (act != SLOIKA_ACT_TANH || gate_act != SLOIKA_ACT_SIGMOID) return SLOIKA_ERR_UNSUPPORTED;
-    if (H <= 32) return launch<32>(vI, sW, sW2, y, ldy, lengths, T, B, H, reverse, st);
-    if (H <= 48) return launch<48>(vI, sW, sW2, y, ldy, lengths, T, B, H, reverse, st);
-    if (H <= 64) return launch<64>(vI, sW, sW2, y, ldy, lengths, T, B, H, reverse, st);
-    if (H <= 80) return launch<80>(vI, sW, sW2, y, ldy, lengths, T, B, H, reverse, st);
-    if (H <= 96) return launch<96>(vI, sW, sW2, y, ldy, lengths, T, B, H, reverse, st);
-    if (H <= 112) return launch<112>(vI, sW, sW2, y, ldy, lengths, T, B, H, reverse, st);
-    if (H <= 128) return launch<128>(vI, sW, sW2, y, ldy, lengths, T, B, H, reverse, st);
-    if (H <= 144) return launch<144>(vI, sW, sW2, y, ldy, lengths, T, B, H, reverse, st);
+    if (H <= 32) return launch<32>(vI, ldv, sW, sW2, y, ldy, lengths, T, B, H, reverse, st);
+    if (H <= 48) return launch<48>(vI, ldv, sW, sW2, y, ldy, lengths, T, B, H, reverse, st);
+    if (H <= 64) return launch<64>(vI, ldv, sW, sW2, y, ldy, lengths, T, B, H, reverse, st);
+    if (H <= 80) return launch<80>(vI, ldv, sW, sW2, y, ldy, lengths, T, B, H, reverse, st);
+    if (H <= 96) return launch<96>(vI, ldv, sW, sW2, y, ldy, lengths, T, B, H, reverse, st);
+    if (H <= 112) return launch<112>(vI, ldv, sW, sW2, y, ldy, lengths, T, B, H, reverse, st);
+    if (H <= 128) return launch<128>(vI, ldv, sW, sW2, y, ldy, lengths, T, B, H, reverse, st);
+    if (H <= 144) return launch<144>(vI, ldv, sW, sW2, y, ldy, lengths, T, B, H, reverse, st);
     return SLOIKA_ERR_UNSUPPORTED;
 }
 

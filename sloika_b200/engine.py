@@ -231,13 +231,13 @@ def run_gru(layer, act, out=None):
     # sloika_gru_fwd == input projection for all steps + recurrence; issued as its two halves so
     # that each kernel can be timed on its own
     H = layer.size
-    vI = _empty((act.T, act.B, 3 * H), dev)
+    vI = _padded_rows(act.T, act.B, 3 * H, dev)          # 16-byte row pitch also for odd H
     st = cabi.stream_ptr(dev)
     launch('gru_projection', 1, lib.sloika_linear_fwd,
            cabi.ptr(act.data), act.ld, cabi.ptr(layer.iW.device(dev)), cabi.ptr(layer.b.device(dev)),
-           cabi.ptr(vI), 3 * H, act.T * act.B, layer.insize, 3 * H, 0, st)
+           cabi.ptr(vI), _row_stride(vI), act.T * act.B, layer.insize, 3 * H, 0, st)
     launch('gru_recurrence', 1, lib.sloika_gru_recurrence_fwd,
-           cabi.ptr(vI), cabi.ptr(layer.sW.device(dev)), cabi.ptr(layer.sW2.device(dev)), cabi.ptr(y),
+           cabi.ptr(vI), _row_stride(vI), cabi.ptr(layer.sW.device(dev)), cabi.ptr(layer.sW2.device(dev)), cabi.ptr(y),
            _row_stride(y), cabi.ptr(act.lengths), act.T, act.B, H, 1 if act.reverse else 0,
            code_of(layer.fun), code_of(layer.gatefun), st)
     return act.like(y)

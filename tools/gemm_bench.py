@@ -6,21 +6,27 @@ from sloika_b200 import cabi
 lib = cabi.load()
 dev = torch.device('cuda:0')
 def run(M, K, N, algo, reps=5):
-    x = torch.randn(M, K, device=dev); W = torch.randn(N, K, device=dev); b = torch.randn(N, device=dev)
-    y = torch.empty(M, N, device=dev)
+    pad = lambda n: (n + 3) // 4 * 4
+    x = torch.randn(M, pad(K), device=dev)[:, :K]; W = torch.randn(N, K, device=dev); b = torch.randn(N, device=dev)
+    y = torch.empty(M, pad(N), device=dev)[:, :N]
     st = cabi.stream_ptr(dev)
     for _ in range(2):
-        rc = lib.sloika_linear_fwd_ex(cabi.ptr(x), K, cabi.ptr(W), cabi.ptr(b), cabi.ptr(y), N, M, K, N, 0, algo, st)
+        rc = lib.sloika_linear_fwd_ex(cabi.ptr(x), x.stride(0), cabi.ptr(W), cabi.ptr(b), cabi.ptr(y), y.stride(0), M, K, N, 0, algo, st)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(reps):
-        rc = lib.sloika_linear_fwd_ex(cabi.ptr(x), K, cabi.ptr(W), cabi.ptr(b), cabi.ptr(y), N, M, K, N, 0, algo, st)
+        rc = lib.sloika_linear_fwd_ex(cabi.ptr(x), x.stride(0), cabi.ptr(W), cabi.ptr(b), cabi.ptr(y), y.stride(0), M, K, N, 0, algo, st)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
     gb = (M * K + M * N) * 4 / 1e9
     return rc, ms, gb / ms * 1e3, 2.0 * M * K * N / ms / 1e9
-for (M, K, N) in [(819200, 96, 288), (819200, 96, 1025), (819200, 128, 336), (819200, 144, 336)]:
+shapes = [(819200, 96, 288), (819200, 96, 1025), (819200, 128, 336), (819200, 144, 336)]
+if os.environ.get("SHAPES") == "one":
+    shapes = [(2048000, 128, 336)]
+elif os.environ.get("SHAPES") == "rGr":
+    shapes = [(2048000, 128, 330), (2048000, 110, 426), (2048000, 142, 330), (2048000, 128, 336), (2048000, 112, 432), (2048000, 110, 1025)]
+for (M, K, N) in shapes:
     for algo in (2, 1):
         rc, ms, gbs, tf = run(M, K, N, algo)
         print("M=%d K=%d N=%d algo=%s rc=%d: %.3f ms  %.0f GB/s  %.1f TFLOP/s  dbg=%s" % (M, K, N, {1: 'simt', 2: 'tc'}[algo], rc, ms, gbs, tf, os.environ.get('SLOIKA_B200_GEMM_DBG', '0')))

@@ -12,7 +12,7 @@ sW2 = torch.randn(H, H, device=dev) * 0.1
 y = torch.empty(T, B, H, device=dev)
 st = cabi.stream_ptr(dev)
 def run():
-    return lib.sloika_gru_recurrence_fwd(cabi.ptr(vI), cabi.ptr(sW), cabi.ptr(sW2), cabi.ptr(y), H, None, T, B, H, 0, 1, 2, st)
+    return lib.sloika_gru_recurrence_fwd(cabi.ptr(vI), 3 * H, cabi.ptr(sW), cabi.ptr(sW2), cabi.ptr(y), H, None, T, B, H, 0, 1, 2, st)
 for _ in range(2): rc = run()
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
