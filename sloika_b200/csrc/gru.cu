@@ -309,6 +309,10 @@ static int launch_gru(const float *vI, long ldv, const float *sW, const float *s
     SLOIKA_RETURN_LAUNCH_STATUS();
 }
 
+namespace gru4 {
+int dispatch(const float *vI, long ldv, const float *sW, const float *sW2, float *y, long ldy, const int32_t *lengths, int T,
+             int B, int H, int reverse, int act, int gate_act, cudaStream_t st);
+}
 namespace gru3 {
 int dispatch(const float *vI, long ldv, const float *sW, const float *sW2, float *y, long ldy, const int32_t *lengths, int T, int B,
              int H, int reverse, int act, int gate_act, cudaStream_t st);
@@ -326,10 +330,16 @@ extern "C" int sloika_gru_recurrence_fwd(const float *vI, long ldv, const float 
     if (!act_known(act) || !act_known(gate_act)) return SLOIKA_ERR_UNSUPPORTED;
     if (T == 0) return SLOIKA_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    {   // mma.sync tensor-core kernel (gru_mma.cu: tanh / sigmoid, H <= 144) first, then the FFMA2 kernel of this
-        // file (any activation pair).  SLOIKA_B200_GRU=v1 forces the latter (A/B measurements, tests).
+    {   // kernel generations, newest first (tanh / sigmoid, H <= 144): fp16x3 mma.sync kernel (gru_h16.cu), 3xTF32
+        // mma.sync kernel (gru_mma.cu); then the FFMA2 kernel of this file (any activation pair).
+        // SLOIKA_B200_GRU=v1|v3 caps the choice (A/B measurements, tests).
         const char *sel = getenv("SLOIKA_B200_GRU");
-        if (!(sel && sel[0] == 'v' && sel[1] == '1')) {
+        const int cap = (sel && sel[0] == 'v' && sel[1] >= '1' && sel[1] <= '4') ? sel[1] - '0' : 4;
+        if (cap >= 4) {
+            const int rc = gru4::dispatch(vI, ldv, sW, sW2, y, ldy, lengths, T, B, H, reverse, act, gate_act, st);
+            if (rc != SLOIKA_ERR_UNSUPPORTED) return rc;
+        }
+        if (cap >= 3) {
             const int rc = gru3::dispatch(vI, ldv, sW, sW2, y, ldy, lengths, T, B, H, reverse, act, gate_act, st);
             if (rc != SLOIKA_ERR_UNSUPPORTED) return rc;
         }
