@@ -76,6 +76,11 @@ int sloika_linear_fwd(const float *x, long ldx, const float *W, const float *bia
 #define SLOIKA_GEMM_AUTO 0
 #define SLOIKA_GEMM_SIMT 1
 #define SLOIKA_GEMM_TC   2
+/* Tensor-core kernel on an fp16 hi/lo split (kind::f16) instead of the tf32 one: same fp32-equivalent accuracy
+ * (each operand is represented to 2^-22 relative, absolute floor 2^-25) at twice the MMA rate and half the
+ * on-chip weight footprint -- but ONLY valid when |x| and |W| stay far below the fp16 range (65504): the caller
+ * asserts that, e.g. x produced by a tanh / sigmoid / GRU layer.  Never chosen by SLOIKA_GEMM_AUTO. */
+#define SLOIKA_GEMM_TC_F16 3
 int sloika_linear_fwd_ex(const float *x, long ldx, const float *W, const float *bias, float *y, long ldy,
                          long M, int K, int N, int act, int algo, void *stream);
 
@@ -97,9 +102,9 @@ int sloika_softmax_fwd(const float *x, long ldx, const float *W, const float *bi
  *   sloika_softmax_normalise_fwd logits -> posteriors in place: exp(t - M) / S_row with the row maximum M and
  *                                row sum S_row combined from the slice pairs (layers.py:311-314)
  */
-int sloika_softmax_slices(int K, int N);
+int sloika_softmax_slices(int K, int N, int algo);
 int sloika_softmax_logits_fwd(const float *x, long ldx, const float *W, const float *bias, float *logits, long ldl,
-                              float *stats, long M, int K, int N, int stay_last, void *stream);
+                              float *stats, long M, int K, int N, int stay_last, int algo, void *stream);
 int sloika_softmax_normalise_fwd(float *logits, long ldl, const float *stats, int n_slices, long M, int N,
                                  void *stream);
 

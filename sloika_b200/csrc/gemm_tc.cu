@@ -21,6 +21,7 @@
 //              + bias, activation, optional softmax row statistics, transpose through smem,
 //              coalesced 128-bit row stores
 #include <cstdlib>
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -53,16 +54,19 @@ struct Params {
     int dbg;          // timing experiments only (SLOIKA_B200_GEMM_DBG): 1 no split math, 2 no stores, 4 no MMA
 };
 
-__host__ __device__ inline size_t smem_bytes(int BN, int nkb, int stages)
+__host__ __device__ inline size_t smem_bytes(int BN, int nkb, int stages, bool f16)
 {
-    size_t w = (size_t)2 * nkb * BN * 128;                 // W_hi + W_lo
+    size_t w = (size_t)2 * nkb * BN * (f16 ? 64 : 128);    // W_hi + W_lo
     size_t a = (size_t)stages * 2 * A_TILE_BYTES;          // (hi, lo) per stage
     size_t stg = (size_t)8 * 32 * STG_LD * 4;              // epilogue transpose buffers (one per epilogue warp)
     size_t misc = (size_t)BN * 4 + 512;                    // bias slice + barriers
     return w + a + stg + misc + 1024;                      // + alignment slack
 }
 
-template <int ACT, bool STATS>
+// F16: operands split into fp16 hi / lo pairs (kind::f16, K = 16 per MMA, SWIZZLE_64B tiles) instead of tf32
+// hi / lo: half the shared-memory footprint of the weights (wider column slices) and twice the MMA rate.  Only for
+// callers that know |x| and |W| stay far below the fp16 range (bounded activations): see sloika_linear_fwd_ex.
+template <int ACT, bool STATS, bool F16>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params p)
 {
@@ -70,9 +74,11 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params p)
     // 1024-byte alignment for the 128-byte swizzle; plain pointer arithmetic keeps the shared address space
     uint8_t *smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
     const int BN = p.BN, nkb = p.nkb, STAGES = p.stages;
+    constexpr int WROW = F16 ? 64 : 128;                                  // bytes of one weight row per K block
     uint8_t *Whi = smem;
-    uint8_t *Wlo = Whi + (size_t)nkb * BN * 128;
-    uint8_t *Abase = Wlo + (size_t)nkb * BN * 128;                        // stage s: hi at 2s, lo at 2s+1
+    uint8_t *Wlo = Whi + (size_t)nkb * BN * WROW;
+    uint8_t *Abase = Wlo + (size_t)nkb * BN * WROW;                       // stage s: hi at 2s, lo at 2s+1
+                                                                          // (F16: raw at 2s, hi16 | lo16 halves of 2s+1)
     float *stg_all = reinterpret_cast<float *>(Abase + (size_t)STAGES * 2 * A_TILE_BYTES);
     float *bias_s = stg_all + 8 * 32 * STG_LD;
     uint64_t *bars = reinterpret_cast<uint64_t *>(bias_s + BN);
@@ -102,10 +108,17 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params p)
         const int k = e % (nkb * KB), n = e / (nkb * KB);
         float w = 0.0f;
         if (n0 + n < p.N && k < p.K) w = __ldg(p.W + (long)((n0 + n + p.rot) % p.N) * p.K + k);
-        const float hi = __uint_as_float(__float_as_uint(w) & 0xffffe000u);
-        const uint32_t off = (uint32_t)(k / KB) * (uint32_t)(BN * 128) + tc::sw128_offset(n, k % KB);
-        *reinterpret_cast<float *>(Whi + off) = hi;
-        *reinterpret_cast<float *>(Wlo + off) = w - hi;
+        if constexpr (F16) {
+            const __half hi = __float2half_rn(w);
+            const uint32_t off = (uint32_t)(k / KB) * (uint32_t)(BN * 64) + tc::sw64_offset(n, k % KB);
+            *reinterpret_cast<__half *>(Whi + off) = hi;
+            *reinterpret_cast<__half *>(Wlo + off) = __float2half_rn(w - __half2float(hi));
+        } else {
+            const float hi = __uint_as_float(__float_as_uint(w) & 0xffffe000u);
+            const uint32_t off = (uint32_t)(k / KB) * (uint32_t)(BN * 128) + tc::sw128_offset(n, k % KB);
+            *reinterpret_cast<float *>(Whi + off) = hi;
+            *reinterpret_cast<float *>(Wlo + off) = w - hi;
+        }
     }
     for (int n = tid; n < BN; n += THREADS) bias_s[n] = (p.bias && n0 + n < p.N) ? __ldg(p.bias + (n0 + n + p.rot) % p.N) : 0.0f;
     tc::fence_proxy_async();
@@ -131,7 +144,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params p)
     } else if (warp == 5) {
         // ================= MMA issuer =================
         if (lane == 0) {
-            const uint32_t idesc = tc::umma_idesc_tf32_m128(BN);
+            const uint32_t idesc = F16 ? tc::umma_idesc_f16_m128(BN) : tc::umma_idesc_tf32_m128(BN);
             uint32_t it = 0, tile = 0;
             for (long mt = cta_in_slice; mt < m_tiles; mt += p.ctas_per_slice, tile++) {
                 const int a = tile % NACC;
@@ -144,11 +157,30 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params p)
                     const uint32_t ph = (it / STAGES) & 1;
                     tc::mbar_wait(&full_split[s], ph);
                     tc::tc_fence_after();
+                    const int krem = p.K - kb * KB;
+                    if constexpr (F16) {
+                        const uint32_t a_hi = tc::smem_u32(Abase + (size_t)(2 * s + 1) * A_TILE_BYTES);
+                        const uint32_t a_lo = a_hi + A_TILE_BYTES / 2;
+                        const uint32_t b_hi = tc::smem_u32(Whi) + (uint32_t)kb * (uint32_t)(BN * 64);
+                        const uint32_t b_lo = tc::smem_u32(Wlo) + (uint32_t)kb * (uint32_t)(BN * 64);
+                        const int ksteps = krem >= KB ? 2 : (krem + 15) / 16;
+#pragma unroll 1
+                        for (int ks = 0; ks < ksteps; ks++) {
+                            const uint64_t dah = tc::umma_desc_sw64_kmajor(a_hi + ks * 32);
+                            const uint64_t dal = tc::umma_desc_sw64_kmajor(a_lo + ks * 32);
+                            const uint64_t dbh = tc::umma_desc_sw64_kmajor(b_hi + ks * 32);
+                            const uint64_t dbl = tc::umma_desc_sw64_kmajor(b_lo + ks * 32);
+                            tc::umma_f16_ss(d_tmem, dah, dbh, idesc, (kb | ks) != 0);
+                            tc::umma_f16_ss(d_tmem, dal, dbh, idesc, true);
+                            tc::umma_f16_ss(d_tmem, dah, dbl, idesc, true);
+                        }
+                        tc::umma_commit(&empty[s]);
+                        continue;
+                    }
                     const uint32_t a_hi = tc::smem_u32(Abase + (size_t)(2 * s) * A_TILE_BYTES);
                     const uint32_t a_lo = a_hi + A_TILE_BYTES;
                     const uint32_t b_hi = tc::smem_u32(Whi) + (uint32_t)kb * (uint32_t)(BN * 128);
                     const uint32_t b_lo = tc::smem_u32(Wlo) + (uint32_t)kb * (uint32_t)(BN * 128);
-                    const int krem = p.K - kb * KB;
                     const int ksteps = krem >= KB ? 4 : (krem + 7) / 8;
 #pragma unroll 1
                     for (int ks = 0; ks < ksteps; ks++) {
@@ -175,6 +207,39 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params p)
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
                 tc::mbar_wait(&full_raw[s], ph);
+                if constexpr (F16) {
+                    // thread -> (row r, 32-byte pair p of the raw 128-byte row): 8 fp32 in, 8 fp16 hi + 8 fp16 lo out
+                    const uint8_t *raw = Abase + (size_t)(2 * s) * A_TILE_BYTES;
+                    uint8_t *h16 = Abase + (size_t)(2 * s + 1) * A_TILE_BYTES;
+                    float4 va[4], vb[4];
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const int q = tt + 128 * i, r = q >> 2, pp = q & 3;
+                        const uint32_t rb = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128);
+                        va[i] = *reinterpret_cast<const float4 *>(raw + rb + (((2 * pp) ^ (r & 7)) << 4));
+                        vb[i] = *reinterpret_cast<const float4 *>(raw + rb + (((2 * pp + 1) ^ (r & 7)) << 4));
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const int q = tt + 128 * i, r = q >> 2, pp = q & 3;
+                        const float v[8] = {va[i].x, va[i].y, va[i].z, va[i].w, vb[i].x, vb[i].y, vb[i].z, vb[i].w};
+                        uint32_t hw[4], lw[4];
+#pragma unroll
+                        for (int e = 0; e < 4; e++) {
+                            const __half2 h = __floats2half2_rn(v[2 * e], v[2 * e + 1]);
+                            const float2 hb = __half22float2(h);
+                            const __half2 l = __floats2half2_rn(v[2 * e] - hb.x, v[2 * e + 1] - hb.y);
+                            hw[e] = *reinterpret_cast<const uint32_t *>(&h);
+                            lw[e] = *reinterpret_cast<const uint32_t *>(&l);
+                        }
+                        const uint32_t off = (uint32_t)((r >> 3) * 512 + (r & 7) * 64 + (((pp ^ (r >> 1)) & 3) << 4));
+                        *reinterpret_cast<uint4 *>(h16 + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                        *reinterpret_cast<uint4 *>(h16 + A_TILE_BYTES / 2 + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                    }
+                    tc::fence_proxy_async();
+                    tc::mbar_arrive(&full_split[s]);
+                    continue;
+                }
                 float4 *hi = reinterpret_cast<float4 *>(Abase + (size_t)(2 * s) * A_TILE_BYTES);
                 float4 *lo = reinterpret_cast<float4 *>(Abase + (size_t)(2 * s + 1) * A_TILE_BYTES);
 #pragma unroll
@@ -366,14 +431,14 @@ static EncodeTiledFn encode_fn()
 
 // Returns SLOIKA_ERR_UNSUPPORTED when the shape/alignment cannot use the tensor path (caller falls back).
 // Column slices the kernel would use for (K, N) (0 = shape not supported): lets callers size `stats`.
-int plan_slices(int K, int N, int *bn_out)
+int plan_slices(int K, int N, int *bn_out, bool f16)
 {
     if (K <= 0 || K > 256 || N <= 0) return 0;
     const int nkb = (K + KB - 1) / KB;
     int bn_max = 256;
     const char *bn_env = getenv("SLOIKA_B200_GEMM_BN");
     if (bn_env && atoi(bn_env) >= 16) bn_max = atoi(bn_env) / 16 * 16;
-    while (bn_max >= 16 && smem_bytes(bn_max, nkb, 3) > 227 * 1024) bn_max -= 16;
+    while (bn_max >= 16 && smem_bytes(bn_max, nkb, 3, f16) > 227 * 1024) bn_max -= 16;
     if (bn_max < 16) return 0;
     const int n_slices = (N + bn_max - 1) / bn_max;
     if (bn_out) *bn_out = ((N + n_slices - 1) / n_slices + 15) / 16 * 16;
@@ -381,7 +446,7 @@ int plan_slices(int K, int N, int *bn_out)
 }
 
 int launch(const float *x, long ldx, const float *W, const float *bias, float *y, long ldy, long M, int K, int N,
-           int act, float2 *stats, int rot, cudaStream_t st)
+           int act, float2 *stats, int rot, bool f16, cudaStream_t st)
 {
     if ((ldx & 3) != 0 || ((uintptr_t)x & 15) != 0 || K > 256 || M < BM || M > 0x7fffffffL) return SLOIKA_ERR_UNSUPPORTED;
     EncodeTiledFn enc = encode_fn();
@@ -394,7 +459,7 @@ int launch(const float *x, long ldx, const float *W, const float *bias, float *y
     const int nkb = (K + KB - 1) / KB;
     // widest slice whose (hi, lo) weights fit beside (at least) 3 x stages in 227 KB of shared memory
     int BN = 0;
-    const int n_slices = plan_slices(K, N, &BN);
+    const int n_slices = plan_slices(K, N, &BN, f16);
     if (n_slices <= 0 || n_slices > sms) return SLOIKA_ERR_UNSUPPORTED;
     if (stats && act != SLOIKA_ACT_LINEAR) return SLOIKA_ERR_UNSUPPORTED;
 
@@ -422,23 +487,24 @@ int launch(const float *x, long ldx, const float *W, const float *bias, float *y
     if (per > m_tiles) per = m_tiles;
     p.ctas_per_slice = (int)per;
     int stages = 3;
-    while (stages < MAX_STAGES && smem_bytes(BN, nkb, stages + 1) <= 227 * 1024) stages++;
+    while (stages < MAX_STAGES && smem_bytes(BN, nkb, stages + 1, f16) <= 227 * 1024) stages++;
     p.stages = stages;
-    const size_t smem = smem_bytes(BN, nkb, stages);
+    const size_t smem = smem_bytes(BN, nkb, stages, f16);
     const unsigned grid = (unsigned)(n_slices * p.ctas_per_slice);
-#define LAUNCH_ACT(A)                                                                                         \
-    case A: {                                                                                                 \
-        cudaError_t err = cudaFuncSetAttribute(gemm_tf32x3_kernel<A, false>,                                  \
-                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
+#define LAUNCH_KERNEL(KERN)                                                                                    \
+    {                                                                                                         \
+        cudaError_t err = cudaFuncSetAttribute(KERN, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
         if (err != cudaSuccess) return (int)err;                                                              \
-        gemm_tf32x3_kernel<A, false><<<grid, THREADS, smem, st>>>(tmap, p);                                   \
-        break;                                                                                                \
+        KERN<<<grid, THREADS, smem, st>>>(tmap, p);                                                           \
     }
+#define LAUNCH_ACT(A)                                                                                         \
+    case A:                                                                                                   \
+        if (f16) LAUNCH_KERNEL((gemm_tf32x3_kernel<A, false, true>))                                          \
+        else LAUNCH_KERNEL((gemm_tf32x3_kernel<A, false, false>))                                             \
+        break;
     if (stats) {
-        cudaError_t err = cudaFuncSetAttribute(gemm_tf32x3_kernel<SLOIKA_ACT_LINEAR, true>,
-                                               cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (err != cudaSuccess) return (int)err;
-        gemm_tf32x3_kernel<SLOIKA_ACT_LINEAR, true><<<grid, THREADS, smem, st>>>(tmap, p);
+        if (f16) LAUNCH_KERNEL((gemm_tf32x3_kernel<SLOIKA_ACT_LINEAR, true, true>))
+        else LAUNCH_KERNEL((gemm_tf32x3_kernel<SLOIKA_ACT_LINEAR, true, false>))
         SLOIKA_RETURN_LAUNCH_STATUS();
     }
     switch (act) {
@@ -448,6 +514,7 @@ int launch(const float *x, long ldx, const float *W, const float *bias, float *y
         LAUNCH_ACT(SLOIKA_ACT_ELU)
         default: return SLOIKA_ERR_UNSUPPORTED;
     }
+#undef LAUNCH_KERNEL
 #undef LAUNCH_ACT
     SLOIKA_RETURN_LAUNCH_STATUS();
 }

@@ -181,9 +181,9 @@ static int launch_linear(const float *x, long ldx, const float *W, const float *
 }
 
 namespace gemm_tc {
-int plan_slices(int K, int N, int *bn_out);
+int plan_slices(int K, int N, int *bn_out, bool f16);
 int launch(const float *x, long ldx, const float *W, const float *bias, float *y, long ldy, long M, int K, int N,
-           int act, float2 *stats, int rot, cudaStream_t st);
+           int act, float2 *stats, int rot, bool f16, cudaStream_t st);
 }
 
 // algo: SLOIKA_GEMM_AUTO tries the tcgen05 3xTF32 kernel and falls back to the fp32 SIMT kernel when the
@@ -192,8 +192,8 @@ static int dispatch_linear(const float *x, long ldx, const float *W, const float
                            int K, int N, int act, int algo, cudaStream_t st)
 {
     if (algo != SLOIKA_GEMM_SIMT) {
-        const int rc = gemm_tc::launch(x, ldx, W, bias, y, ldy, M, K, N, act, nullptr, 0, st);
-        if (rc != SLOIKA_ERR_UNSUPPORTED || algo == SLOIKA_GEMM_TC) return rc;
+        const int rc = gemm_tc::launch(x, ldx, W, bias, y, ldy, M, K, N, act, nullptr, 0, algo == SLOIKA_GEMM_TC_F16, st);
+        if (rc != SLOIKA_ERR_UNSUPPORTED || algo == SLOIKA_GEMM_TC || algo == SLOIKA_GEMM_TC_F16) return rc;
     }
     return launch_linear(x, ldx, W, bias, y, ldy, M, K, N, act, st);
 }
@@ -206,7 +206,7 @@ extern "C" int sloika_linear_fwd_ex(const float *x, long ldx, const float *W, co
                                     long M, int K, int N, int act, int algo, void *stream)
 {
     if (!x || !W || !y || M < 0 || K <= 0 || N <= 0 || ldx < K || ldy < N) return SLOIKA_ERR_ARG;
-    if (algo < SLOIKA_GEMM_AUTO || algo > SLOIKA_GEMM_TC) return SLOIKA_ERR_ARG;
+    if (algo < SLOIKA_GEMM_AUTO || algo > SLOIKA_GEMM_TC_F16) return SLOIKA_ERR_ARG;
     if (!act_known(act)) return SLOIKA_ERR_UNSUPPORTED;
     if (M == 0) return SLOIKA_OK;
     return dispatch_linear(x, ldx, W, bias, y, ldy, M, K, N, act, algo, (cudaStream_t)stream);
@@ -221,22 +221,22 @@ extern "C" int sloika_linear_fwd(const float *x, long ldx, const float *W, const
     return dispatch_linear(x, ldx, W, bias, y, ldy, M, K, N, act, SLOIKA_GEMM_AUTO, (cudaStream_t)stream);
 }
 
-extern "C" int sloika_softmax_slices(int K, int N)
+extern "C" int sloika_softmax_slices(int K, int N, int algo)
 {
     if (N > 32 * 256) return 0;
     // the kernel writes one (max, sum exp) pair per column slice AND per epilogue warp group
-    const int n = 2 * gemm_tc::plan_slices(K, N, nullptr);
+    const int n = 2 * gemm_tc::plan_slices(K, N, nullptr, algo == SLOIKA_GEMM_TC_F16);
     return n > 32 ? 0 : n;
 }
 
 extern "C" int sloika_softmax_logits_fwd(const float *x, long ldx, const float *W, const float *bias, float *logits,
-                                         long ldl, float *stats, long M, int K, int N, int stay_last, void *stream)
+                                         long ldl, float *stats, long M, int K, int N, int stay_last, int algo, void *stream)
 {
     if (!x || !W || !logits || !stats || M < 0 || K <= 0 || N <= 0 || ldx < K || ldl < N) return SLOIKA_ERR_ARG;
     if (M == 0) return SLOIKA_OK;
-    if (sloika_softmax_slices(K, N) <= 0) return SLOIKA_ERR_UNSUPPORTED;
+    if (sloika_softmax_slices(K, N, algo) <= 0) return SLOIKA_ERR_UNSUPPORTED;
     return gemm_tc::launch(x, ldx, W, bias, logits, ldl, M, K, N, SLOIKA_ACT_LINEAR, reinterpret_cast<float2 *>(stats),
-                           stay_last ? 1 : 0, (cudaStream_t)stream);
+                           stay_last ? 1 : 0, algo == SLOIKA_GEMM_TC_F16, (cudaStream_t)stream);
 }
 
 extern "C" int sloika_softmax_normalise_fwd(float *logits, long ldl, const float *stats, int n_slices, long M, int N,

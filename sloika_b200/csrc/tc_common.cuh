@@ -103,9 +103,32 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_kmajor(uint32_t addr) {
     d |= (uint64_t)2 << 61;                         // layout type SWIZZLE_128B
     return d;
 }
+// Same for the SWIZZLE_64B layout: rows of 64 bytes (32 fp16), 8-row groups 512 bytes apart, 16-byte chunks
+// XOR-swizzled with (row >> 1) & 3; the tile base must be 512-byte aligned.
+__device__ __forceinline__ uint64_t umma_desc_sw64_kmajor(uint32_t addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr >> 4) & 0x3fff);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(512 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)4 << 61;                         // layout type SWIZZLE_64B
+    return d;
+}
 // Instruction descriptor for kind::tf32, fp32 accumulate, both operands K-major, M = 128.
 __host__ __device__ __forceinline__ uint32_t umma_idesc_tf32_m128(int n) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+}
+// kind::f16 with fp16 operands (format code 0), fp32 accumulate, both operands K-major, M = 128.
+__host__ __device__ __forceinline__ uint32_t umma_idesc_f16_m128(int n) {
+    return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"((uint32_t)accumulate)
+        : "memory");
 }
 // D[tmem] (+)= A[smem] . B[smem]^T   (single elected thread)
 __device__ __forceinline__ void umma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {
@@ -125,6 +148,11 @@ __device__ __forceinline__ void umma_commit(uint64_t *bar) {
 // Byte offset of element (row, k) inside one K block (32 fp32 = 128-byte rows) of a SWIZZLE_128B tile.
 __host__ __device__ __forceinline__ uint32_t sw128_offset(int row, int k) {
     return (uint32_t)((row >> 3) * 1024 + (row & 7) * 128 + ((((k >> 2) ^ row) & 7) << 4) + ((k & 3) << 2));
+}
+
+// Byte offset of element (row, k) (k in fp16 units, 0..31) inside one K block of a SWIZZLE_64B fp16 tile.
+__host__ __device__ __forceinline__ uint32_t sw64_offset(int row, int k) {
+    return (uint32_t)((row >> 3) * 512 + (row & 7) * 64 + ((((k >> 3) ^ (row >> 1)) & 3) << 4) + ((k & 7) << 1));
 }
 
 }  // namespace tc

@@ -22,9 +22,11 @@ class Act(object):
     data     torch CUDA tensor of shape [T, B, F]; rows (t, b) are `ld` floats apart
     lengths  optional int32 CUDA tensor [B]: valid steps per sequence (ragged whole-read batch)
     reverse  time direction flag toggled by `Reverse` (nothing is ever flipped in memory)
+    bounded  True when the producing layer guarantees |x| <= 1 (tanh / sigmoid / GRU / softmax outputs): the
+             next GEMM may then use the fp16-split tensor-core kernel (SLOIKA_GEMM_TC_F16)
     """
 
-    def __init__(self, data, lengths=None, reverse=False):
+    def __init__(self, data, lengths=None, reverse=False, bounded=False):
         assert data.dim() == 3
         T, B, F = data.shape
         # strides of size-1 dimensions are meaningless in torch; derive the row distance from a
@@ -41,6 +43,7 @@ class Act(object):
         self._ld = ld
         self.lengths = lengths
         self.reverse = reverse
+        self.bounded = bounded
 
     @property
     def T(self):
@@ -63,10 +66,10 @@ class Act(object):
         return self.data.device
 
     def flipped(self):
-        return Act(self.data, self.lengths, not self.reverse)
+        return Act(self.data, self.lengths, not self.reverse, self.bounded)
 
-    def like(self, data, lengths='same'):
-        return Act(data, self.lengths if lengths == 'same' else lengths, self.reverse)
+    def like(self, data, lengths='same', bounded=False):
+        return Act(data, self.lengths if lengths == 'same' else lengths, self.reverse, bounded)
 
 
 class KernelTimer(object):
@@ -127,6 +130,37 @@ def _out_buffer(act, T, F, out):
     return _padded_rows(T, act.B, F, act.device)
 
 
+GEMM_AUTO, GEMM_SIMT, GEMM_TC, GEMM_TC_F16 = 0, 1, 2, 3      # include/sloika_b200.h
+_F16_WEIGHT_LIMIT = 1.0e3
+
+
+def _bounded_fun(fun):
+    return code_of(fun) in (1, 2)               # tanh, sigmoid
+
+
+def _gemm_algo(act, *params):
+    """fp16-split tensor-core GEMM when the input is provably in [-1, 1] and the weights are far inside the
+    fp16 range; otherwise let the library choose (tf32 split / SIMT).  SLOIKA_B200_NO_F16=1 disables it."""
+    import os
+    if act.bounded and not os.environ.get('SLOIKA_B200_NO_F16') and \
+            all(p.absmax() < _F16_WEIGHT_LIMIT for p in params):
+        return GEMM_TC_F16
+    return GEMM_AUTO
+
+
+def _linear(name, lib, act, W, b, y, ldy, N, fun_code, dev):
+    """y = fun(x W' + b) through sloika_linear_fwd_ex; the fp16-split request degrades to AUTO when the
+    tensor-core kernel cannot take the shape."""
+    algo = _gemm_algo(act, W)
+    args = lambda a: (cabi.ptr(act.data), act.ld, cabi.ptr(W.device(dev)), cabi.ptr(b.device(dev)), cabi.ptr(y), ldy,
+                      act.T * act.B, act.F, N, fun_code, a, cabi.stream_ptr(dev))
+    if algo == GEMM_TC_F16 and act.ld % 4 == 0 and act.data.data_ptr() % 16 == 0 and act.T * act.B >= 128 \
+            and act.F <= 256:
+        launch(name, 1, lib.sloika_linear_fwd_ex, *args(GEMM_TC_F16))
+    else:
+        launch(name, 1, lib.sloika_linear_fwd_ex, *args(GEMM_AUTO))
+
+
 def run_convolution(layer, act, out=None):
     lib = cabi.load()
     assert act.F == layer.insize, "Convolution input has {} features, expected {}".format(act.F, layer.insize)
@@ -144,19 +178,15 @@ def run_convolution(layer, act, out=None):
         # per-read output length: each read is padded/convolved on its own (conv.py:66-111)
         span = act.lengths + (layer.padding[0] + layer.padding[1] - layer.winlen)
         lengths = (span.clamp(min=-layer.stride) // layer.stride + 1).clamp(min=0).to(act.lengths.dtype)
-    return act.like(y, lengths)
+    return act.like(y, lengths, bounded=_bounded_fun(layer.fun))
 
 
 def run_feedforward(layer, act, out=None):
     lib = cabi.load()
     assert act.F == layer.insize
     y = _out_buffer(act, act.T, layer.size, out)
-    dev = act.device
-    launch('feedforward', 1, lib.sloika_linear_fwd,
-           cabi.ptr(act.data), act.ld, cabi.ptr(layer.W.device(dev)), cabi.ptr(layer.b.device(dev)),
-           cabi.ptr(y), _row_stride(y), act.T * act.B, layer.insize, layer.size, code_of(layer.fun),
-           cabi.stream_ptr(dev))
-    return act.like(y)
+    _linear('feedforward', lib, act, layer.W, layer.b, y, _row_stride(y), layer.size, code_of(layer.fun), act.device)
+    return act.like(y, bounded=_bounded_fun(layer.fun))
 
 
 def _padded_rows(T, B, F, device):
@@ -176,9 +206,9 @@ class LogitsAct(object):
         self.data, self.stats, self.n_slices, self.lengths = data, stats, n_slices, lengths
 
 
-def _softmax_tc_ok(lib, layer, act):
+def _softmax_tc_ok(lib, layer, act, algo):
     return act.ld % 4 == 0 and act.data.data_ptr() % 16 == 0 and act.T * act.B >= 128 and \
-        lib.sloika_softmax_slices(layer.insize, layer.size) > 0
+        lib.sloika_softmax_slices(layer.insize, layer.size, algo) > 0
 
 
 def run_softmax_logits(layer, act):
@@ -187,15 +217,16 @@ def run_softmax_logits(layer, act):
     import torch
     lib = cabi.load()
     assert act.F == layer.insize
-    if not _softmax_tc_ok(lib, layer, act):
+    algo = _gemm_algo(act, layer.W)
+    if not _softmax_tc_ok(lib, layer, act, algo):
         return None
     dev = act.device
-    nsl = lib.sloika_softmax_slices(layer.insize, layer.size)
+    nsl = lib.sloika_softmax_slices(layer.insize, layer.size, algo)
     y = _padded_rows(act.T, act.B, layer.size, dev)
     stats = torch.empty((act.T * act.B, nsl, 2), dtype=torch.float32, device=dev)
     launch('softmax', 1, lib.sloika_softmax_logits_fwd,
            cabi.ptr(act.data), act.ld, cabi.ptr(layer.W.device(dev)), cabi.ptr(layer.b.device(dev)),
-           cabi.ptr(y), _row_stride(y), cabi.ptr(stats), act.T * act.B, layer.insize, layer.size, 1,
+           cabi.ptr(y), _row_stride(y), cabi.ptr(stats), act.T * act.B, layer.insize, layer.size, 1, algo,
            cabi.stream_ptr(dev))
     return LogitsAct(y, stats, nsl, act.lengths)
 
@@ -207,20 +238,22 @@ def run_softmax(layer, act, out=None):
     dev = act.device
     y = out if out is not None else _padded_rows(act.T, act.B, layer.size, dev)
     ldy = _row_stride(y)
-    if _softmax_tc_ok(lib, layer, act) and ldy % 4 == 0 and y.data_ptr() % 16 == 0:
+    algo = _gemm_algo(act, layer.W)
+    if _softmax_tc_ok(lib, layer, act, algo) and ldy % 4 == 0 and y.data_ptr() % 16 == 0:
         # tensor-core logits + per-slice row statistics, then one normalising pass (read + write)
-        nsl = lib.sloika_softmax_slices(layer.insize, layer.size)
+        nsl = lib.sloika_softmax_slices(layer.insize, layer.size, algo)
         stats = torch.empty((act.T * act.B, nsl, 2), dtype=torch.float32, device=dev)
         launch('softmax', 1, lib.sloika_softmax_logits_fwd,
                cabi.ptr(act.data), act.ld, cabi.ptr(layer.W.device(dev)), cabi.ptr(layer.b.device(dev)),
-               cabi.ptr(y), ldy, cabi.ptr(stats), act.T * act.B, layer.insize, layer.size, 0, cabi.stream_ptr(dev))
+               cabi.ptr(y), ldy, cabi.ptr(stats), act.T * act.B, layer.insize, layer.size, 0, algo,
+               cabi.stream_ptr(dev))
         launch('softmax_normalise', 1, lib.sloika_softmax_normalise_fwd,
                cabi.ptr(y), ldy, cabi.ptr(stats), nsl, act.T * act.B, layer.size, cabi.stream_ptr(dev))
     else:
         launch('softmax', 2, lib.sloika_softmax_fwd,
                cabi.ptr(act.data), act.ld, cabi.ptr(layer.W.device(dev)), cabi.ptr(layer.b.device(dev)),
                cabi.ptr(y), ldy, act.T * act.B, layer.insize, layer.size, cabi.stream_ptr(dev))
-    return act.like(y)
+    return act.like(y, bounded=True)
 
 
 def run_gru(layer, act, out=None):
@@ -233,14 +266,13 @@ def run_gru(layer, act, out=None):
     H = layer.size
     vI = _padded_rows(act.T, act.B, 3 * H, dev)          # 16-byte row pitch also for odd H
     st = cabi.stream_ptr(dev)
-    launch('gru_projection', 1, lib.sloika_linear_fwd,
-           cabi.ptr(act.data), act.ld, cabi.ptr(layer.iW.device(dev)), cabi.ptr(layer.b.device(dev)),
-           cabi.ptr(vI), _row_stride(vI), act.T * act.B, layer.insize, 3 * H, 0, st)
+    _linear('gru_projection', lib, act, layer.iW, layer.b, vI, _row_stride(vI), 3 * H, 0, dev)
     launch('gru_recurrence', 1, lib.sloika_gru_recurrence_fwd,
            cabi.ptr(vI), _row_stride(vI), cabi.ptr(layer.sW.device(dev)), cabi.ptr(layer.sW2.device(dev)), cabi.ptr(y),
            _row_stride(y), cabi.ptr(act.lengths), act.T, act.B, H, 1 if act.reverse else 0,
            code_of(layer.fun), code_of(layer.gatefun), st)
-    return act.like(y)
+    # h is a convex combination of act(.) values when the gates are sigmoids
+    return act.like(y, bounded=_bounded_fun(layer.fun) and code_of(layer.gatefun) == 2)
 
 
 _SLICE_WRITERS = {}
@@ -252,6 +284,7 @@ def run_parallel(layer, act, out=None):
     y = _out_buffer(act, act.T, layer.size, out)
     col = 0
     result = None
+    bounded = True
     for sub in layer.layers:
         view = y[:, :, col:col + sub.size]
         inner, flips = sub, 0
@@ -267,12 +300,13 @@ def run_parallel(layer, act, out=None):
         else:
             res = sub.run(act)                  # nested containers: run, then place
             view.copy_(res.data)
-            res = act.like(view, res.lengths)
+            res = act.like(view, res.lengths, bounded=res.bounded)
             flips = 0
         if result is None:
             result = res.flipped() if flips % 2 else res
+        bounded = bounded and res.bounded
         col += sub.size
-    return Act(y, result.lengths, act.reverse)
+    return Act(y, result.lengths, act.reverse, bounded)
 
 
 class CompiledNetwork(object):

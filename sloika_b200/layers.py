@@ -49,6 +49,13 @@ class Param(object):
     def set_value(self, value):
         self._host = np.ascontiguousarray(value, dtype=sloika_dtype)
         self._dev = {}
+        self._absmax = None
+
+    def absmax(self):
+        """max |value| (cached): lets the engine decide whether the fp16-split tensor-core kernels apply."""
+        if getattr(self, '_absmax', None) is None:
+            self._absmax = float(np.abs(self._host).max()) if self._host.size else 0.0
+        return self._absmax
 
     def device(self, dev):
         """float32 buffer on torch device `dev`, uploaded once per device."""

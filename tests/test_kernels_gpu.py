@@ -300,6 +300,63 @@ def test_tensor_core_gemm_matches_fp32(M, K, N, act_code):
     assert err_tc <= max(4 * err_simt, 4e-6 * scale), (err_tc, err_simt, scale)
 
 
+@pytest.mark.parametrize('M,K,N,act_code', [(4096, 96, 288, 0), (1000, 96, 288, 1), (128, 96, 96, 0), (777, 128, 336, 0),
+                                            (3000, 110, 426, 0), (2500, 144, 336, 2), (2048, 96, 1025, 0),
+                                            (640, 32, 96, 3), (513, 40, 50, 0), (300, 8, 16, 0), (20000, 192, 128, 1),
+                                            (1500, 256, 300, 0)])
+def test_tensor_core_gemm_fp16_split_matches_fp32(M, K, N, act_code):
+    """SLOIKA_GEMM_TC_F16 (fp16 hi/lo operands, for inputs bounded by 1) is as accurate as fp32 accumulation,
+    including inputs so small that the lo parts fall into the fp16 subnormal range."""
+    rng = np.random.default_rng(M + K + N)
+    x = np.tanh(rng.standard_normal((M, K))).astype(np.float32)
+    x[::7] *= 1e-4                                                      # rows of tiny activations
+    W = (rng.standard_normal((N, K)) * 1.5).astype(np.float32)
+    b = rng.standard_normal(N).astype(np.float32)
+    Kp = (K + 3) // 4 * 4                                               # TMA needs 16-byte rows
+    xp = np.zeros((M, Kp), dtype=np.float32)
+    xp[:, :K] = x
+    lib = cabi.load()
+    xd, Wd, bd = torch.from_numpy(xp).to(DEV), torch.from_numpy(W).to(DEV), torch.from_numpy(b).to(DEV)
+    out = {}
+    for algo in (3, 1):
+        y = torch.full((M, N), -7.0, dtype=torch.float32, device=DEV)
+        rc = lib.sloika_linear_fwd_ex(cabi.ptr(xd), Kp, cabi.ptr(Wd), cabi.ptr(bd), cabi.ptr(y), N, M, K, N, act_code, algo,
+                                      cabi.stream_ptr(torch.device(DEV)))
+        assert rc == 0
+        torch.cuda.synchronize()
+        out[algo] = y.cpu().numpy()
+    exact = x.astype(np.float64) @ W.astype(np.float64).T + b
+    fun = {0: lambda v: v, 1: np.tanh, 2: lambda v: 1 / (1 + np.exp(-v)), 3: lambda v: np.where(v > 0, v, np.expm1(np.minimum(v, 0)))}[act_code]
+    exact = fun(exact)
+    err_tc, err_simt = np.abs(out[3] - exact).max(), np.abs(out[1] - exact).max()
+    scale = np.abs(exact).max()
+    assert err_tc <= max(4 * err_simt, 4e-6 * scale), (err_tc, err_simt, scale)
+
+
+def test_engine_picks_fp16_split_only_for_bounded_inputs(monkeypatch):
+    """tanh / GRU outputs feed the fp16-split GEMM, elu outputs and huge weights do not; results agree either way."""
+    np.random.seed(4)
+    net = zoo.raw_rgrgr()
+    x = torch.randn((600, 16, 1), device=DEV)
+    calc = net.compile()
+    with_f16 = calc.forward_device(x, None).data.cpu().numpy()
+    monkeypatch.setenv('SLOIKA_B200_NO_F16', '1')
+    without = calc.forward_device(x, None).data.cpu().numpy()
+    monkeypatch.delenv('SLOIKA_B200_NO_F16')
+    np.testing.assert_allclose(with_f16, without, atol=2e-5)
+    a = engine.Act(torch.zeros((4, 2, 8), device=DEV), bounded=True)
+    big = layers.Param(np.full((3, 8), 5e4, dtype=np.float32))
+    assert engine._gemm_algo(a, net.layers[-1].W) == engine.GEMM_TC_F16
+    assert engine._gemm_algo(a, big) == engine.GEMM_AUTO
+    assert engine._gemm_algo(engine.Act(torch.zeros((4, 2, 8), device=DEV)), net.layers[-1].W) == engine.GEMM_AUTO
+    elu_out = engine.run_convolution(layers.Convolution(1, 8, 11, 2, has_bias=True, fun=act.elu),
+                                     engine.Act(torch.randn((100, 2, 1), device=DEV)))
+    assert not elu_out.bounded
+    tanh_out = engine.run_convolution(layers.Convolution(1, 8, 11, 2, has_bias=True, fun=act.tanh),
+                                      engine.Act(torch.randn((100, 2, 1), device=DEV)))
+    assert tanh_out.bounded
+
+
 def test_tensor_core_gemm_column_slice_and_fallback():
     rng = np.random.default_rng(1)
     x = rng.standard_normal((512, 64)).astype(np.float32)

@@ -7,7 +7,7 @@ lib = cabi.load()
 dev = torch.device('cuda:0')
 def run(M, K, N, algo, reps=5):
     pad = lambda n: (n + 3) // 4 * 4
-    x = torch.randn(M, pad(K), device=dev)[:, :K]; W = torch.randn(N, K, device=dev); b = torch.randn(N, device=dev)
+    x = torch.tanh(torch.randn(M, pad(K), device=dev))[:, :K]; W = torch.randn(N, K, device=dev); b = torch.randn(N, device=dev)
     y = torch.empty(M, pad(N), device=dev)[:, :N]
     st = cabi.stream_ptr(dev)
     for _ in range(2):
@@ -27,6 +27,6 @@ if os.environ.get("SHAPES") == "one":
 elif os.environ.get("SHAPES") == "rGr":
     shapes = [(2048000, 128, 330), (2048000, 110, 426), (2048000, 142, 330), (2048000, 128, 336), (2048000, 112, 432), (2048000, 110, 1025)]
 for (M, K, N) in shapes:
-    for algo in (2, 1):
+    for algo in (3, 2, 1):
         rc, ms, gbs, tf = run(M, K, N, algo)
-        print("M=%d K=%d N=%d algo=%s rc=%d: %.3f ms  %.0f GB/s  %.1f TFLOP/s  dbg=%s" % (M, K, N, {1: 'simt', 2: 'tc'}[algo], rc, ms, gbs, tf, os.environ.get('SLOIKA_B200_GEMM_DBG', '0')))
+        print("M=%d K=%d N=%d algo=%s rc=%d: %.3f ms  %.0f GB/s  %.1f TFLOP/s  dbg=%s" % (M, K, N, {1: 'simt', 2: 'tc', 3: 'tc_f16'}[algo], rc, ms, gbs, tf, os.environ.get('SLOIKA_B200_GEMM_DBG', '0')))
