@@ -216,30 +216,16 @@ gru_h16_kernel(const float *__restrict__ vI, long ldv, const float *__restrict__
             if (b_base + b < B) dst[b * VLD + c] = __ldg(vI + ((long)t * B + b_base + b) * ldv + c);
         }
     };
-    // aligned (128-bit) work split: vI row b = vq + 2k (k = 0..3), float4 column vc; h row yb, float4 column yc
-    // (io_n = 2*HP threads; 3H/4 < HP and 8 * (HP/4) = io_n); derived from the thread index on the spot so that
-    // nothing is held in registers across the matrix products
-    auto stage_vi_fast = [&](int t, int slot, int it) {               // role-1 threads, cp.async
-        if (t < 0 || t >= T) return;
+    auto stage_vi_slow = [&](int t, int slot, int it) {               // role-1 threads, rows not 16-byte aligned:
+        if (t < 0 || t >= T) return;                                   // 4-byte async copies, <= 2 columns per thread and row
         float *dst = vbuf + slot * BT * VLD;
         const float *src = vI + ((long)t * B + b_base) * ldv;
-        if (!vec_vi) {                       // rows not 16-byte aligned: 4-byte async copies, <= 2 columns per thread and row
-            const int c0 = it, c1 = it + io_n;                         // io_n = 2*HP >= 2*H, so 3H < 2*io_n
+        const int c0 = it, c1 = it + io_n;                             // io_n = 2*HP >= 2*H, so 3H < 2*io_n
 #pragma unroll
-            for (int b = 0; b < BT; b++) {
-                if (b_base + b < B) {
-                    if (c0 < (int)H3) cp_async4(dst + b * VLD + c0, src + b * ldv + c0);
-                    if (c1 < (int)H3) cp_async4(dst + b * VLD + c1, src + b * ldv + c1);
-                }
-            }
-            return;
-        }
-        const int vq = it / HP, vc = it - vq * HP;
-        if (4 * vc < (int)H3) {
-#pragma unroll
-            for (int k = 0; k < BT / 2; k++) {
-                const int b = vq + 2 * k;
-                if (b_base + b < B) cp_async16(dst + b * VLD + 4 * vc, src + b * ldv + 4 * vc);
+        for (int b = 0; b < BT; b++) {
+            if (b_base + b < B) {
+                if (c0 < (int)H3) cp_async4(dst + b * VLD + c0, src + b * ldv + c0);
+                if (c1 < (int)H3) cp_async4(dst + b * VLD + c1, src + b * ldv + c1);
             }
         }
     };
@@ -250,28 +236,13 @@ gru_h16_kernel(const float *__restrict__ vI, long ldv, const float *__restrict__
             if (b_base + b < B) y[((long)t * B + b_base + b) * ldy + j] = src[b * P + j];
         }
     };
-    auto store_h_fast = [&](int t, int slot, int it) {                // role-1 threads
-        const float *src = Hf + slot * BT * P;
+    auto store_h_slow = [&](int t, int slot, int it) {                // role-1 threads, unaligned rows: one column per
+        const float *src = Hf + slot * BT * P;                         // thread and row, coalesced 4-byte stores
         float *dst = y + ((long)t * B + b_base) * ldy;
-        if (!vec_y) {                        // unaligned rows: one column per thread and row, coalesced 4-byte stores
-            if (it < H) {
+        if (it < H) {
 #pragma unroll
-                for (int b = 0; b < BT; b++)
-                    if (b_base + b < B) dst[(long)b * ldy + it] = src[b * P + it];
-            }
-            return;
-        }
-        const int yb = it / (HP / 4), yc = it - yb * (HP / 4);
-        if (4 * yc < H && b_base + yb < B) {
-            float *d = dst + (long)yb * ldy + 4 * yc;
-            const float *sp = src + yb * P + 4 * yc;
-            if (4 * yc + 3 < H) {
-                *reinterpret_cast<float4 *>(d) = *reinterpret_cast<const float4 *>(sp);
-            } else {                         // last, partial quad of a row whose width is not a multiple of 4
-                d[0] = sp[0];
-                if (4 * yc + 1 < H) d[1] = sp[1];
-                if (4 * yc + 2 < H) d[2] = sp[2];
-            }
+            for (int b = 0; b < BT; b++)
+                if (b_base + b < B) dst[(long)b * ldy + it] = src[b * P + it];
         }
     };
 
@@ -341,6 +312,20 @@ gru_h16_kernel(const float *__restrict__ vI, long ldv, const float *__restrict__
             bar_sync(0, NTHREADS);
         }
     } else {
+        // I/O state of this thread for the aligned (128-bit) paths, advanced by one time step per iteration:
+        // vI rows b = vq + 2k (k = 0..3), float4 column vc, of step t + 2*tstep; h row yb, float4 column yc, of
+        // step t - tstep (io_n = 2*HP threads; 3H/4 < HP and 8 * (HP/4) = io_n)
+        const int vq = io_tid / HP, vc = io_tid - vq * HP;
+        unsigned vmask = 0;
+        if (vec_vi && 4 * vc < (int)H3)
+            for (int k = 0; k < BT / 2; k++)
+                if (b_base + vq + 2 * k < B) vmask |= 1u << k;
+        const float *vptr = vI + ((long)(t + 2 * tstep) * B + b_base + vq) * ldv + 4 * vc;
+        const int vdst = vq * VLD + 4 * vc;
+        const int yb = io_tid / (HP / 4), yc = io_tid - yb * (HP / 4);
+        const int ymode = !(vec_y && 4 * yc < H && b_base + yb < B) ? 0 : (4 * yc + 3 < H ? 2 : 1);   // none / partial / full quad
+        float *yptr = y + ((long)(t - tstep) * B + b_base + yb) * ldy + 4 * yc;
+        const int ysrc = yb * P + 4 * yc;
         for (int s = 0; s < T; s++, t += tstep) {
             const int slot = s & 1;
             const float *vrow = vbuf + (s % 3) * BT * VLD;
@@ -368,11 +353,34 @@ gru_h16_kernel(const float *__restrict__ vI, long ldv, const float *__restrict__
             Cx[jt * 32 + lane] = make_float4(cpart[0], cpart[1], cpart[2], cpart[3]);
             bar_arrive(2 + jt, 64);
             // HBM traffic: vI two steps ahead (slot read last in step s-1), h_{t-1} (complete since the last barrier) out
-            int it = io_tid;
-            if constexpr (WIDE) { it = (int)threadIdx.x - NT * 32; asm volatile("" : "+r"(it)); }
-            stage_vi_fast(t + 2 * tstep, (s + 2) % 3, it);
+            if (vec_vi) {
+                const int tn = t + 2 * tstep;
+                if (vmask != 0 && tn >= 0 && tn < T) {
+                    float *dst = vbuf + ((s + 2) % 3) * BT * VLD + vdst;
+#pragma unroll
+                    for (int k = 0; k < BT / 2; k++)
+                        if (vmask & (1u << k)) cp_async16(dst + 2 * k * VLD, vptr + (long)(2 * k) * ldv);
+                }
+                vptr += (long)tstep * B * ldv;
+            } else {
+                stage_vi_slow(t + 2 * tstep, (s + 2) % 3, io_tid);
+            }
             cp_async_commit();
-            if (s > 0) store_h_fast(t - tstep, slot ^ 1, it);
+            if (vec_y) {
+                if (s > 0 && ymode != 0) {
+                    const float *sp = Hf + (slot ^ 1) * BT * P + ysrc;
+                    if (ymode == 2) {
+                        *reinterpret_cast<float4 *>(yptr) = *reinterpret_cast<const float4 *>(sp);
+                    } else {                 // last, partial quad of a row whose width is not a multiple of 4
+                        yptr[0] = sp[0];
+                        if (4 * yc + 1 < H) yptr[1] = sp[1];
+                        if (4 * yc + 2 < H) yptr[2] = sp[2];
+                    }
+                }
+                yptr += (long)tstep * B * ldy;
+            } else if (s > 0) {
+                store_h_slow(t - tstep, slot ^ 1, io_tid);
+            }
             cp_async_wait_1();               // vI of step s+1 (issued one step ago) has landed
             bar_sync(0, NTHREADS);
         }
