@@ -31,7 +31,7 @@ namespace gemm_tc {
 
 constexpr int BM = 128;            // rows per tile (UMMA M)
 constexpr int KB = 32;             // k elements per K block (one 128-byte swizzle row)
-constexpr int MAX_STAGES = 8;      // smem stages of (hi, lo) x-tiles (as many as fit)
+constexpr int MAX_STAGES = 12;     // smem stages of x-tiles (as many as fit)
 constexpr int NACC = 2;            // TMEM accumulator stages
 constexpr int THREADS = 448;        // 14 warps: 0-3 + 10-13 epilogue, 4 TMA, 5 MMA, 6-9 transform
 constexpr int A_TILE_BYTES = BM * KB * 4;        // 16 KB
@@ -57,7 +57,7 @@ struct Params {
 __host__ __device__ inline size_t smem_bytes(int BN, int nkb, int stages, bool f16)
 {
     size_t w = (size_t)2 * nkb * BN * (f16 ? 64 : 128);    // W_hi + W_lo
-    size_t a = (size_t)stages * 2 * A_TILE_BYTES;          // (hi, lo) per stage
+    size_t a = (size_t)stages * (f16 ? 1 : 2) * A_TILE_BYTES;   // tf32: (hi, lo) per stage; f16: hi16 | lo16 in place of the raw tile
     size_t stg = (size_t)8 * 32 * STG_LD * 4;              // epilogue transpose buffers (one per epilogue warp)
     size_t misc = (size_t)BN * 4 + 512;                    // bias slice + barriers
     return w + a + stg + misc + 1024;                      // + alignment slack
@@ -77,9 +77,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params p)
     constexpr int WROW = F16 ? 64 : 128;                                  // bytes of one weight row per K block
     uint8_t *Whi = smem;
     uint8_t *Wlo = Whi + (size_t)nkb * BN * WROW;
-    uint8_t *Abase = Wlo + (size_t)nkb * BN * WROW;                       // stage s: hi at 2s, lo at 2s+1
-                                                                          // (F16: raw at 2s, hi16 | lo16 halves of 2s+1)
-    float *stg_all = reinterpret_cast<float *>(Abase + (size_t)STAGES * 2 * A_TILE_BYTES);
+    constexpr int STAGE_BYTES = (F16 ? 1 : 2) * A_TILE_BYTES;
+    uint8_t *Abase = Wlo + (size_t)nkb * BN * WROW;                       // stage s: raw tile, converted in place to hi; lo behind it
+                                                                          // (F16: raw tile replaced by hi16 | lo16, 8 KB each)
+    float *stg_all = reinterpret_cast<float *>(Abase + (size_t)STAGES * STAGE_BYTES);
     float *bias_s = stg_all + 8 * 32 * STG_LD;
     uint64_t *bars = reinterpret_cast<uint64_t *>(bias_s + BN);
     uint64_t *full_raw = bars;                     // [STAGES] TMA -> transform
@@ -137,7 +138,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params p)
                     const uint32_t ph = (it / STAGES) & 1;
                     tc::mbar_wait(&empty[s], ph ^ 1);
                     tc::mbar_arrive_expect_tx(&full_raw[s], A_TILE_BYTES);
-                    tc::tma_load_2d(Abase + (size_t)(2 * s) * A_TILE_BYTES, &tmap_x, &full_raw[s], kb * KB, (int)(mt * BM));
+                    tc::tma_load_2d(Abase + (size_t)s * STAGE_BYTES, &tmap_x, &full_raw[s], kb * KB, (int)(mt * BM));
                 }
             }
         }
@@ -159,7 +160,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params p)
                     tc::tc_fence_after();
                     const int krem = p.K - kb * KB;
                     if constexpr (F16) {
-                        const uint32_t a_hi = tc::smem_u32(Abase + (size_t)(2 * s + 1) * A_TILE_BYTES);
+                        const uint32_t a_hi = tc::smem_u32(Abase + (size_t)s * STAGE_BYTES);
                         const uint32_t a_lo = a_hi + A_TILE_BYTES / 2;
                         const uint32_t b_hi = tc::smem_u32(Whi) + (uint32_t)kb * (uint32_t)(BN * 64);
                         const uint32_t b_lo = tc::smem_u32(Wlo) + (uint32_t)kb * (uint32_t)(BN * 64);
@@ -177,7 +178,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params p)
                         tc::umma_commit(&empty[s]);
                         continue;
                     }
-                    const uint32_t a_hi = tc::smem_u32(Abase + (size_t)(2 * s) * A_TILE_BYTES);
+                    const uint32_t a_hi = tc::smem_u32(Abase + (size_t)s * STAGE_BYTES);
                     const uint32_t a_lo = a_hi + A_TILE_BYTES;
                     const uint32_t b_hi = tc::smem_u32(Whi) + (uint32_t)kb * (uint32_t)(BN * 128);
                     const uint32_t b_lo = tc::smem_u32(Wlo) + (uint32_t)kb * (uint32_t)(BN * 128);
@@ -209,8 +210,11 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params p)
                 tc::mbar_wait(&full_raw[s], ph);
                 if constexpr (F16) {
                     // thread -> (row r, 32-byte pair p of the raw 128-byte row): 8 fp32 in, 8 fp16 hi + 8 fp16 lo out
-                    const uint8_t *raw = Abase + (size_t)(2 * s) * A_TILE_BYTES;
-                    uint8_t *h16 = Abase + (size_t)(2 * s + 1) * A_TILE_BYTES;
+                    // in place: every thread first pulls its 8 x 4 floats into registers, the four warps meet on a
+                    // named barrier, then the fp16 tiles overwrite the raw one (a 16 KB stage instead of 32 KB
+                    // doubles the number of TMA loads in flight)
+                    const uint8_t *raw = Abase + (size_t)s * STAGE_BYTES;
+                    uint8_t *h16 = Abase + (size_t)s * STAGE_BYTES;
                     float4 va[4], vb[4];
 #pragma unroll
                     for (int i = 0; i < 4; i++) {
@@ -219,6 +223,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params p)
                         va[i] = *reinterpret_cast<const float4 *>(raw + rb + (((2 * pp) ^ (r & 7)) << 4));
                         vb[i] = *reinterpret_cast<const float4 *>(raw + rb + (((2 * pp + 1) ^ (r & 7)) << 4));
                     }
+                    asm volatile("bar.sync 3, 128;" ::: "memory");
 #pragma unroll
                     for (int i = 0; i < 4; i++) {
                         const int q = tt + 128 * i, r = q >> 2, pp = q & 3;
@@ -240,8 +245,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params p)
                     tc::mbar_arrive(&full_split[s]);
                     continue;
                 }
-                float4 *hi = reinterpret_cast<float4 *>(Abase + (size_t)(2 * s) * A_TILE_BYTES);
-                float4 *lo = reinterpret_cast<float4 *>(Abase + (size_t)(2 * s + 1) * A_TILE_BYTES);
+                float4 *hi = reinterpret_cast<float4 *>(Abase + (size_t)s * STAGE_BYTES);
+                float4 *lo = reinterpret_cast<float4 *>(Abase + (size_t)s * STAGE_BYTES + A_TILE_BYTES);
 #pragma unroll
                 for (int i = 0; i < ((p.dbg & 1) ? 0 : A_TILE_BYTES / 16 / 128); i++) {
                     const int c = tt + 128 * i;
@@ -486,8 +491,16 @@ int launch(const float *x, long ldx, const float *W, const float *bias, float *y
     long per = sms / n_slices;
     if (per > m_tiles) per = m_tiles;
     p.ctas_per_slice = (int)per;
+    // Pipeline depth (measured sweep, tools/gemm_bench.py SHAPES=sweep): with few slices a deeper ring of x tiles
+    // hides more HBM latency (best at ~5); with many slices (softmax logits: write dominated, every x tile is
+    // re-read by each slice's CTA out of L2) a deep ring lets the slices drift apart and costs up to 25 %.
+    const int want_stages = n_slices >= 4 ? 3 : 5;
     int stages = 3;
-    while (stages < MAX_STAGES && smem_bytes(BN, nkb, stages + 1, f16) <= 227 * 1024) stages++;
+    while (stages < want_stages && stages < MAX_STAGES && smem_bytes(BN, nkb, stages + 1, f16) <= 227 * 1024) stages++;
+    {
+        const char *cap = getenv("SLOIKA_B200_GEMM_STAGES");       // tuning experiments
+        if (cap && atoi(cap) >= 2 && atoi(cap) <= MAX_STAGES && smem_bytes(BN, nkb, atoi(cap), f16) <= 227 * 1024) stages = atoi(cap);
+    }
     p.stages = stages;
     const size_t smem = smem_bytes(BN, nkb, stages, f16);
     const unsigned grid = (unsigned)(n_slices * p.ctas_per_slice);

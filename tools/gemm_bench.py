@@ -24,9 +24,17 @@ def run(M, K, N, algo, reps=5):
 shapes = [(819200, 96, 288), (819200, 96, 1025), (819200, 128, 336), (819200, 144, 336)]
 if os.environ.get("SHAPES") == "one":
     shapes = [(2048000, 128, 336)]
+elif os.environ.get("SHAPES") == "sweep":
+    shapes = [(819200, 96, 288), (819200, 96, 1025), (2048000, 128, 330), (2048000, 110, 426), (2048000, 142, 330),
+              (2048000, 110, 1025), (819200, 128, 336), (819200, 112, 432), (819200, 144, 336), (819200, 112, 1025),
+              (2048000, 32, 288), (2048000, 192, 128), (2048000, 128, 1025)]
+elif os.environ.get("SHAPES") == "bench":
+    shapes = [(819200, 96, 288), (819200, 96, 1025)]
 elif os.environ.get("SHAPES") == "rGr":
     shapes = [(2048000, 128, 330), (2048000, 110, 426), (2048000, 142, 330), (2048000, 128, 336), (2048000, 112, 432), (2048000, 110, 1025)]
 for (M, K, N) in shapes:
-    for algo in (3, 2, 1):
+    for algo in ((3,) if os.environ.get('ALGOS') == 'f16' else (3, 2, 1)):
         rc, ms, gbs, tf = run(M, K, N, algo)
+        if os.environ.get('TERSE'):
+            print("%d %d %d %s %.3f" % (M, K, N, os.environ.get('SLOIKA_B200_GEMM_STAGES', '-'), ms)); continue
         print("M=%d K=%d N=%d algo=%s rc=%d: %.3f ms  %.0f GB/s  %.1f TFLOP/s  dbg=%s" % (M, K, N, {1: 'simt', 2: 'tc', 3: 'tc_f16'}[algo], rc, ms, gbs, tf, os.environ.get('SLOIKA_B200_GEMM_DBG', '0')))
