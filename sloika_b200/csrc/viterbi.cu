@@ -230,7 +230,7 @@ viterbi_k1024_kernel(const float *__restrict__ post, long ld_t, long ld_b, const
         float tot = r < n_slices ? s * expf(m - mx) : 0.0f;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-        if (r == 0) ms_s[i & 1] = make_float2(mx, __frcp_rn(tot));      // (row max, 1 / row sum)
+        if (r == 0) ms_s[i & 1] = make_float2(-(mx * SLOIKA_LOG2E + lg2_ftz(tot)), 0.0f);
     };
     // raw row values of event i for this thread: 4 k-mer columns + the stay column
     const float *rowp = pb;                                           // advanced by ld_t per event
@@ -253,8 +253,9 @@ viterbi_k1024_kernel(const float *__restrict__ post, long ld_t, long ld_b, const
             // fused path: softmax (exp(t - m) * 1/rowsum), min_prob floor and log with the MUFU ex2 / lg2
             // approximations (|error| ~1e-6 on a log-posterior, inside what libm-vs-device logf already allows);
             // branch free, ~10 instructions per value instead of ~60
-            const float pr = ex2_ftz((v - ms.x) * SLOIKA_LOG2E) * ms.y;           // v <= row max: argument <= 0
-            return lg2_ftz(__fadd_rn(__fadd_rn(c0, __fmul_rn(c1, pr)), VIT_ETA)) * SLOIKA_LN2;
+            // ms = (-(m * log2e + log2 rowsum), unused): posterior = 2^(v*log2e + ms.x), 5 instructions per value
+            const float pr = ex2_ftz(fmaf(v, SLOIKA_LOG2E, ms.x));
+            return lg2_ftz(fmaf(c1, pr, c0)) * SLOIKA_LN2;             // c0 carries min_prob + 1e-10 on this path
         }
         return logf(__fadd_rn(__fadd_rn(c0, __fmul_rn(c1, v)), VIT_ETA));
     };
@@ -503,7 +504,9 @@ extern "C" int sloika_viterbi_logits_fwd(const float *logits, long ld_t, long ld
     if (nbase != 4 || klen != 5) return SLOIKA_ERR_UNSUPPORTED;          // K = 1024 specialisation only
     if ((ld_t & 3) != 0 || (ld_b & 3) != 0 || ((uintptr_t)logits & 15) != 0) return SLOIKA_ERR_UNSUPPORTED;
     if (!tb_ws || ws_bytes < sloika_viterbi_workspace_bytes(T, B, nbase, klen)) return SLOIKA_ERR_WORKSPACE;
-    const float c0 = (float)min_prob, c1 = (float)(1.0 - min_prob), sp = (float)skip_pen;
+    // on this path the kernel evaluates log(c0 + c1 * p) with one fused multiply-add: c0 carries the + 1e-10 of
+    // decode.prepare_post (decode.py:36) as well
+    const float c0 = (float)min_prob + 1e-10f, c1 = (float)(1.0 - min_prob), sp = (float)skip_pen;
     viterbi_k1024_kernel<IN_LOGITS><<<B, 256, 0, (cudaStream_t)stream>>>(
         logits, ld_t, ld_b, reinterpret_cast<const float2 *>(stats), n_slices, lengths, T, B, sp, c0, c1,
         logits_skip_threshold(c0, c1), (uint8_t *)tb_ws, path_out, path_len, score_out);
