@@ -183,6 +183,11 @@ __device__ __forceinline__ void cp_async16_v(void *smem_dst, const void *gsrc) {
     const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void cp_async4_v(void *smem_dst, const void *gsrc) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait0_v() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_commit_v() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait1_v() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
@@ -200,7 +205,14 @@ viterbi_k1024_kernel(const float *__restrict__ post, long ld_t, long ld_b, const
     __shared__ float red_v[8];
     __shared__ int red_i[8];
     __shared__ int s_best, s_state;
-    __shared__ __align__(16) uint8_t tb_s2[8 * 1024];   // second traceback chunk buffer of the backtrace
+    // the next event's row, staged with cp.async: no registers are held across the event (at 32 registers per
+    // thread they used to spill, which made every event wait on its own prefetch) and the HBM latency is fully
+    // asynchronous.  [0, K) k-mer columns, [K] stay column.  The storage doubles as the second traceback chunk
+    // buffer of the backtrace.
+    constexpr int XROW = K + 4;
+    __shared__ __align__(16) float xrow_s[2][XROW];
+    uint8_t *tb_s2 = reinterpret_cast<uint8_t *>(&xrow_s[0][0]);
+    static_assert(sizeof(float) * 2 * XROW >= 8 * 1024, "xrow_s doubles as a traceback chunk buffer");
 
     const int b = blockIdx.x;
     const int r = threadIdx.x;
@@ -232,20 +244,26 @@ viterbi_k1024_kernel(const float *__restrict__ post, long ld_t, long ld_b, const
         for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
         if (r == 0) ms_s[i & 1] = make_float2(-(mx * SLOIKA_LOG2E + lg2_ftz(tot)), 0.0f);
     };
-    // raw row values of event i for this thread: 4 k-mer columns + the stay column
+    // stage the row of the next event (this thread: its own 4 k-mer columns; thread 0 also the stay column)
     const float *rowp = pb;                                           // advanced by ld_t per event
-    auto fetch = [&](int i, float (&x)[4], float &x0) {
+    const bool vec_rows = MODE == IN_LOGITS && (ld_t & 3) == 0 && (ld_b & 3) == 0 && (((uintptr_t)post & 15) == 0);
+    auto stage_row = [&](int buf) {
+        float *dst = xrow_s[buf];
         const float *row = rowp;
         rowp += ld_t;
         if (MODE == IN_LOGITS) {
-            const float4 q = __ldg(reinterpret_cast<const float4 *>(row) + r);
-            x[0] = q.x; x[1] = q.y; x[2] = q.z; x[3] = q.w;
-            x0 = __ldg(row + K);
+            if (vec_rows) cp_async16_v(dst + 4 * r, row + 4 * r);
+            else {
+#pragma unroll
+                for (int c = 0; c < 4; c++) cp_async4_v(dst + 4 * r + c, row + 4 * r + c);
+            }
+            if (r == 0) cp_async4_v(dst + K, row + K);
         } else {
-            x[0] = __ldg(row + 1 + 4 * r); x[1] = __ldg(row + 2 + 4 * r);
-            x[2] = __ldg(row + 3 + 4 * r); x[3] = __ldg(row + 4 + 4 * r);
-            x0 = __ldg(row);
+#pragma unroll
+            for (int c = 0; c < 4; c++) cp_async4_v(dst + 4 * r + c, row + 1 + 4 * r + c);
+            if (r == 0) cp_async4_v(dst + K, row);
         }
+        cp_async_commit_v();
     };
     auto lpost_of = [&](float v, float2 ms) -> float {
         if (MODE == IN_LOG) return v;
@@ -260,26 +278,29 @@ viterbi_k1024_kernel(const float *__restrict__ post, long ld_t, long ld_b, const
         return logf(__fadd_rn(__fadd_rn(c0, __fmul_rn(c1, v)), VIT_ETA));
     };
 
-    float xn[4], xn0;
     row_stats(0);
-    fetch(0, xn, xn0);
+    stage_row(0);
+    cp_async_wait0_v();
     __syncthreads();
     {
         const float2 ms = ms_s[0];
+        const float4 q = reinterpret_cast<const float4 *>(xrow_s[0])[r];
         float4 v0;
-        v0.x = lpost_of(xn[0], ms); v0.y = lpost_of(xn[1], ms); v0.z = lpost_of(xn[2], ms); v0.w = lpost_of(xn[3], ms);
+        v0.x = lpost_of(q.x, ms); v0.y = lpost_of(q.y, ms); v0.z = lpost_of(q.z, ms); v0.w = lpost_of(q.w, ms);
         reinterpret_cast<float4 *>(vbuf[0])[r] = v0;             // v_0 = lpost[0][1:]   (decode.py:57)
     }
-    if (nev > 1) { row_stats(1); fetch(1, xn, xn0); }
+    if (nev > 1) { row_stats(1); stage_row(1); }
+    cp_async_wait0_v();
     __syncthreads();
 
     int cur = 0;
     unsigned *tbp = reinterpret_cast<unsigned *>(tbb) + r;             // traceback word of this thread, advanced per event
     for (int i = 1; i < nev; i++) {
-        float x[4] = {xn[0], xn[1], xn[2], xn[3]};
-        const float x0 = xn0;
+        const float4 xq = reinterpret_cast<const float4 *>(xrow_s[i & 1])[r];
+        const float x[4] = {xq.x, xq.y, xq.z, xq.w};
+        const float x0 = xrow_s[i & 1][K];
         const float2 ms = ms_s[i & 1];
-        if (i + 1 < nev) { row_stats(i + 1); fetch(i + 1, xn, xn0); }   // next event, off the critical path
+        if (i + 1 < nev) { row_stats(i + 1); stage_row((i + 1) & 1); }  // next event, asynchronous
         const float *p = vbuf[cur];
         // step: first maximum over a of p[a*256 + r]; published as (value, 4*a) for the skip search
         float ss = p[r];
@@ -331,6 +352,7 @@ viterbi_k1024_kernel(const float *__restrict__ post, long ld_t, long ld_b, const
         tbp += K / 4;
         *tbp = packed;
         cur ^= 1;
+        cp_async_wait0_v();                                          // the next row has landed (issued an event ago)
         __syncthreads();
     }
 
