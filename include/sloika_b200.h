@@ -163,6 +163,29 @@ int sloika_viterbi_logits_fwd(const float *logits, long ld_t, long ld_b, const f
                               double min_prob, void *tb_ws, size_t ws_bytes, int32_t *path_out, int32_t *path_len,
                               float *score_out, void *stream);
 
+/*
+ * Remap decode: transducer.map_to_sequence -- sloika/transducer.py:14-73 -- with its
+ * native helper viterbi_helpers.slip_update -- sloika/viterbi_helpers.pyx:12-35 -- batched, one CTA per read
+ * (reference callers: sloika/tools/chunkify_raw.py:262-274, sloika/batch.py:141-155, one read per call).
+ *   trans: [T,B,nstate] transducer posteriors, element (t,b,s) at trans[t*ld_t + b*ld_b + s], column 0 = stay;
+ *          is_log != 0: already log-scaled (`log=True`), else the kernel takes logf (`log=False`)
+ *   nev int32 [B] (NULL = T): events per read; seq int32 [B][ld_seq]: state columns of the reference sequence;
+ *   npos int32 [B] (NULL = P): positions per read, 3 <= npos <= P <= 65535 (and P small enough for the on-chip
+ *          score vectors: 24 P bytes <= 200 KB, else SLOIKA_ERR_UNSUPPORTED)
+ *   slip / has_slip: slip penalty >= 0; has_slip == 0 reproduces the reference's slip=None, which runs the slip
+ *          move with a NaN penalty (np.float32(None)) and returns a NaN score
+ *   prior_initial / prior_final: float64 [B][ld_prior] or NULL (util.geometric_prior's dtype; added in double)
+ *   ws: sloika_remap_workspace_bytes(T,B,P) bytes (uint16 traceback)
+ *   path_out int32 [B][T]: position of every event (first nev[b] entries); score_out float32 [B]
+ * sloika_slip_update_fwd is slip_update alone (n >= 3; from_pos is int64 like the reference's np.int).
+ */
+size_t sloika_remap_workspace_bytes(int T, int B, int P);
+int sloika_remap_fwd(const float *trans, long ld_t, long ld_b, const int32_t *nev, int T, int B, int nstate,
+                     const int32_t *seq, long ld_seq, const int32_t *npos, int P, double slip, int has_slip,
+                     const double *prior_initial, const double *prior_final, long ld_prior, int is_log,
+                     void *ws, size_t ws_bytes, int32_t *path_out, float *score_out, void *stream);
+int sloika_slip_update_fwd(const float *x, int n, float slip, float *from_score, long long *from_pos, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -18,8 +18,8 @@ def lib():
     global _LIB
     if _LIB is None:
         path = os.path.join(_HERE, '_build', 'liboracle.so')
-        src = os.path.join(_HERE, 'viterbi_ref.c')
-        if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(src):
+        srcs = [os.path.join(_HERE, f) for f in ('viterbi_ref.c', 'remap_ref.c')]
+        if not os.path.exists(path) or os.path.getmtime(path) < max(os.path.getmtime(f) for f in srcs):
             build()
         _LIB = ctypes.CDLL(path)
         _LIB.sloika_oracle_viterbi_batch.restype = ctypes.c_int
@@ -46,3 +46,34 @@ def viterbi_batch(lpost, lengths=None, klen=5, nbase=4, skip_pen=0.0, nthreads=N
     if rc != 0:
         raise RuntimeError("oracle viterbi failed")
     return score, [paths[b, :plen[b]].tolist() for b in range(B)]
+
+
+def slip_update(x, slip):
+    """viterbi_helpers.slip_update through the C restatement: (from_score float32, from_pos int64)."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    fs = np.zeros(len(x), dtype=np.float32)
+    fp = np.zeros(len(x), dtype=np.int64)
+    lib().sloika_oracle_slip_update(x.ctypes.data_as(ctypes.c_void_p), ctypes.c_long(len(x)), ctypes.c_float(slip),
+                                    fs.ctypes.data_as(ctypes.c_void_p), fp.ctypes.data_as(ctypes.c_void_p))
+    return fs, fp
+
+
+def remap_batch(lt, seq, nev=None, npos=None, slip=None, prior0=None, prior1=None, nthreads=None):
+    """lt [T, B, S] float32 LOG transducer, seq [B, P] int32 state columns -> (scores [B], paths [B, T] int32)."""
+    lt = np.ascontiguousarray(lt, dtype=np.float32)
+    seq = np.ascontiguousarray(seq, dtype=np.int32)
+    T, B, S = lt.shape
+    P = seq.shape[1]
+    opt = lambda a, dt: None if a is None else np.ascontiguousarray(a, dtype=dt)
+    nev, npos, prior0, prior1 = opt(nev, np.int32), opt(npos, np.int32), opt(prior0, np.float64), opt(prior1, np.float64)
+    ptr = lambda a: None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+    paths = np.zeros((B, T), dtype=np.int32)
+    score = np.zeros(B, dtype=np.float32)
+    fn = lib().sloika_oracle_remap_batch
+    fn.restype = ctypes.c_int
+    rc = fn(ptr(lt), ctypes.c_long(T), ctypes.c_long(B), ctypes.c_long(S), ptr(nev), ptr(seq), ctypes.c_long(P), ptr(npos),
+            ctypes.c_float(float('nan') if slip is None else slip), ptr(prior0), ptr(prior1),
+            ctypes.c_int(nthreads or os.cpu_count() or 1), ptr(paths), ptr(score))
+    if rc != 0:
+        raise RuntimeError("oracle remap failed")
+    return score, paths

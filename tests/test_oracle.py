@@ -6,7 +6,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import scaled_signal
+from conftest import GOLDEN, scaled_signal
 from oracle import cbind, decode_ref, forward_ref, host_ref
 
 
@@ -132,3 +132,62 @@ def test_float64_twin_bounds_float32_error(pretrained, reads_daq):
     p32 = forward_ref.run(desc, x, np.float32)
     p64 = forward_ref.run(desc, x, np.float64)
     assert np.abs(p32 - p64).max() < 2e-5
+
+
+# ------------------------------------------------------------------ remap decode
+def _remap_cases():
+    g = np.load(os.path.join(GOLDEN, 'remap_cases.npz'))
+    with open(os.path.join(GOLDEN, 'remap_cases.json')) as fh:
+        meta = json.load(fh)
+    return g, meta
+
+
+def _same_score(a, b):
+    return np.float32(a) == np.float32(b) or (np.isnan(a) and np.isnan(b))
+
+
+def test_remap_oracles_match_reference_goldens():
+    """oracle/remap_ref.py and oracle/remap_ref.c reproduce, bit for bit, what the reference's own
+    transducer.map_to_sequence / viterbi_helpers.slip_update returned (tools/make_golden_remap.py), including the
+    known-answer recipe of test/unit/test_viterbi.py and the NaN behaviour of slip=None."""
+    from oracle import cbind, remap_ref
+    g, meta = _remap_cases()
+    kinds = set()
+    for m in meta:
+        k = m['key']
+        kinds.add(m['kind'])
+        if m['kind'] == 'slip_update':
+            for fn in (remap_ref.slip_update, cbind.slip_update):
+                fs, fp = fn(g[k + '_x'], m['slip'])
+                assert np.array_equal(fs, g[k + '_score']) and np.array_equal(fp, g[k + '_pos']), k
+            continue
+        p0 = g[k + '_prior0'] if k + '_prior0' in g else None
+        p1 = g[k + '_prior1'] if k + '_prior1' in g else None
+        s, p = remap_ref.map_to_sequence(g[k + '_trans'], g[k + '_seq'], m['slip'], p0, p1, m['log'])
+        assert np.array_equal(p, g[k + '_path']) and _same_score(s, g[k + '_score']), k
+        lt = g[k + '_trans'] if m['log'] else np.log(g[k + '_trans'])
+        s, p = cbind.remap_batch(lt[:, None, :], g[k + '_seq'][None], slip=m['slip'],
+                                 prior0=None if p0 is None else p0[None], prior1=None if p1 is None else p1[None])
+        assert np.array_equal(p[0], g[k + '_path']) and _same_score(s[0], g[k + '_score']), k
+    assert kinds == {'slip_update', 'map_to_sequence'}
+
+
+def test_slip_update_reference_unit_test_recipe():
+    """test/unit/test_viterbi.py:13-33 restated: the helper equals the plain-Python recurrence on the seeded input."""
+    from oracle import cbind
+    np.random.seed(0xdeadbeef)
+    x = np.random.normal(size=10).astype(np.float32)
+    slip = 5.0
+    y1s, y1i = cbind.slip_update(x, slip)
+    y2s = np.zeros(len(x), dtype=np.float32)
+    y2i = np.zeros(len(x), dtype=np.int64)
+    y2s[0] = y2s[1] = -1e38
+    y2s[2] = x[0] - slip
+    for j in range(3, len(x)):
+        if y2s[j - 1] >= x[j - 2]:
+            y2s[j], y2i[j] = y2s[j - 1], y2i[j - 1]
+        else:
+            y2s[j], y2i[j] = x[j - 2], j - 2
+        y2s[j] -= slip
+    np.testing.assert_almost_equal(y1s, y2s)
+    np.testing.assert_equal(y1i, y2i)
