@@ -171,7 +171,7 @@ int sloika_viterbi_logits_fwd(const float *logits, long ld_t, long ld_b, const f
  *          is_log != 0: already log-scaled (`log=True`), else the kernel takes logf (`log=False`)
  *   nev int32 [B] (NULL = T): events per read; seq int32 [B][ld_seq]: state columns of the reference sequence;
  *   npos int32 [B] (NULL = P): positions per read, 3 <= npos <= P <= 65535 (and P small enough for the on-chip
- *          score vectors: 24 P bytes <= 200 KB, else SLOIKA_ERR_UNSUPPORTED)
+ *          score vectors: 24 P + 8 nstate bytes <= 200 KB, else SLOIKA_ERR_UNSUPPORTED)
  *   slip / has_slip: slip penalty >= 0; has_slip == 0 reproduces the reference's slip=None, which runs the slip
  *          move with a NaN penalty (np.float32(None)) and returns a NaN score
  *   prior_initial / prior_final: float64 [B][ld_prior] or NULL (util.geometric_prior's dtype; added in double)

@@ -27,9 +27,29 @@
 namespace sloika {
 namespace remap {
 
-constexpr int THREADS = 64;
-constexpr int TB_CHUNK = 8;            // traceback rows staged per backtrace step: 8 * P * 2 bytes <= the 16 P bytes of e + nxt + fs
+constexpr int MAX_THREADS = 256;       // 64 threads per read for chunk-sized sequences, 256 for long ones
+constexpr int MAX_SEG = 32;            // segments of the slip scan (threads 0..nseg-1): 16 or 32; the walk over them is
+                                       // sequential, so few and long beats many and short (measured)
+constexpr int TB_CHUNK = 8;            // traceback rows staged per backtrace step: 8 * P * 2 bytes = the 16 P bytes of nxt .. src
 
+__device__ __forceinline__ void cp_async4_r(void *smem_dst, const void *gsrc) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_r() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait0_r() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// How the running maximum of slip_update is parallelised without changing a bit of it.  Sequentially
+//     F[j] = (F[j-1] >= x[j-2] ? F[j-1] : x[j-2]) - slip,       source kept on ties.
+// Rounded subtraction of a constant is monotone, so F[j] is the maximum over the candidates k <= j-2 of x[k] with slip
+// subtracted (j-1-k) times, each with its own roundings.  Cut the positions in segments: every thread scans ONE
+// segment as if nothing came before it (L, "local"); the value carried into a segment decays by one subtraction
+// per position for as long as it is still >= every new x it meets (exactly the comparisons the sequential code makes
+// while that candidate is its running best); where it survives it overrides L, and the first time it loses, the
+// sequential code and the local scan both switch to that same x and agree from there on.  One thread walks the
+// segments in order and applies the carries: usually a handful of positions each, at worst one subtract + compare
+// per position.
+template <int THREADS, int NSEG>
 __global__ void __launch_bounds__(THREADS)
 remap_kernel(const float *__restrict__ trans, long ld_t, long ld_b, const int32_t *__restrict__ nev_p, int T, int nstate,
              const int32_t *__restrict__ seq, long ld_seq, const int32_t *__restrict__ npos_p, int P, float slip,
@@ -43,7 +63,10 @@ remap_kernel(const float *__restrict__ trans, long ld_t, long ld_b, const int32_
     float *fs = e + P;                                     // [P] slip_update scores
     uint16_t *fp = reinterpret_cast<uint16_t *>(fs + P);   // [P] slip_update sources
     uint16_t *src = fp + P;                                // [P] stay / step source
-    int32_t *sq = reinterpret_cast<int32_t *>(src + P);     // [P] the sequence (fp + src = 4 P bytes: stays 4-byte aligned)
+    int32_t *sq = reinterpret_cast<int32_t *>(src + P);    // [P] the sequence (fp + src = 4 P bytes: stays 4-byte aligned)
+    float *rowbuf = reinterpret_cast<float *>(sq + P);     // [2][nstate] transducer rows, staged one event ahead
+    __shared__ float seg_f[MAX_SEG];                       // end state of every local scan
+    __shared__ int seg_p[MAX_SEG];
     __shared__ int s_pos;
 
     const int b = blockIdx.x, tid = threadIdx.x;
@@ -55,43 +78,39 @@ remap_kernel(const float *__restrict__ trans, long ld_t, long ld_b, const int32_
     }
     const float *tr = trans + (long)b * ld_b;
     uint16_t *tbb = tb + (size_t)b * (size_t)T * (size_t)P;
-    auto lval = [&](const float *row, int col) -> float {
-        const float v = __ldg(row + col);
-        return is_log ? v : logf(v);
+    auto stage_row = [&](int i) {                          // row i -> rowbuf[i & 1] (asynchronous)
+        const float *row = tr + (long)i * ld_t;
+        float *dst = rowbuf + (i & 1) * nstate;
+        for (int c = tid; c < nstate; c += THREADS) cp_async4_r(dst + c, row + c);
+        cp_async_commit_r();
     };
+    auto lval = [&](const float *row, int col) -> float { return is_log ? row[col] : logf(row[col]); };
 
+    stage_row(0);
     for (int j = tid; j < npos; j += THREADS) sq[j] = __ldg(seq + (long)b * ld_seq + j);
+    cp_async_wait0_r();
     __syncthreads();
+    if (nev > 1) stage_row(1);
     {   // transducer.py:41-44
-        const float stay0 = lval(tr, 0);
+        const float stay0 = lval(rowbuf, 0);
         for (int j = tid; j < npos; j += THREADS) {
             const float p = prior0 ? (float)(0.0 + prior0[(long)b * ld_prior + j]) : 0.0f;
-            prev[j] = __fadd_rn(p, fmaxf(lval(tr, sq[j]), stay0));
+            prev[j] = __fadd_rn(p, fmaxf(lval(rowbuf, sq[j]), stay0));
         }
     }
+    cp_async_wait0_r();
     __syncthreads();
 
+    // segments of the positions 3 .. npos-1 for the local scans
+    const int seg_len = (max(npos - 3, 0) + NSEG - 1) / NSEG;
+    const int seg_a = 3 + tid * seg_len, seg_b = tid < NSEG ? min(seg_a + seg_len, npos) : 0;
+
     for (int i = 1; i < nev; i++) {
-        const float *row = tr + (long)i * ld_t;
-        if (tid == 0) {
-            // slip_update (viterbi_helpers.pyx:22-33), sequential: value chain = compare/select + one subtraction
-            fs[0] = -1e38f; fs[1] = -1e38f;
-            fp[0] = 0; fp[1] = 0;
-            float f = __fsub_rn(prev[0], slip);
-            int pos = 0;
-            fs[2] = f; fp[2] = 0;
-            for (int j = 3; j < npos; j++) {
-                const float x = prev[j - 2];
-                const bool keep = f >= x;                   // tie keeps the older source; NaN takes the new one
-                pos = keep ? pos : j - 2;
-                f = __fsub_rn(keep ? f : x, slip);
-                fs[j] = f;
-                fp[j] = (uint16_t)pos;
-            }
-        } else {
-            // stay / step (transducer.py:48-55) by the other 63 threads, meanwhile
+        const float *row = rowbuf + (i & 1) * nstate;
+        // ---- stay / step (transducer.py:48-55): threads NSEG.. ----
+        if (tid >= NSEG) {
             const float stay = lval(row, 0);
-            for (int j = tid - 1; j < npos; j += THREADS - 1) {
+            for (int j = tid - NSEG; j < npos; j += THREADS - NSEG) {
                 const float em = lval(row, sq[j]);
                 e[j] = em;
                 float c = __fadd_rn(prev[j], stay);
@@ -104,16 +123,63 @@ remap_kernel(const float *__restrict__ trans, long ld_t, long ld_b, const int32_
                 src[j] = (uint16_t)s;
             }
         }
+        // ---- slip_update (viterbi_helpers.pyx:22-33): local scan of this thread's segment, meanwhile ----
+        if (seg_a < seg_b) {
+            float f = __fsub_rn(prev[seg_a - 2], slip);
+            int pos = seg_a - 2;
+            fs[seg_a] = f; fp[seg_a] = (uint16_t)pos;
+            for (int j = seg_a + 1; j < seg_b; j++) {
+                const float x = prev[j - 2];
+                const bool keep = f >= x;                   // tie keeps the older source; NaN takes the new one
+                pos = keep ? pos : j - 2;
+                f = __fsub_rn(keep ? f : x, slip);
+                fs[j] = f;
+                fp[j] = (uint16_t)pos;
+            }
+            seg_f[tid] = f;
+            seg_p[tid] = pos;
+        }
         __syncthreads();
+        if (i + 1 < nev && tid != 0) stage_row(i + 1);      // the row buffer of event i-1 is free: next row, asynchronously
+        if (tid == 0) {
+            // ---- carries across the segments, in order ----
+            float cf = __fsub_rn(prev[0], slip);            // F[2]
+            int cp = 0;
+            fs[0] = -1e38f; fs[1] = -1e38f; fp[0] = 0; fp[1] = 0;
+            fs[2] = cf; fp[2] = 0;
+            for (int a = 3, t = 0; a < npos; a += seg_len, t++) {
+                const int bnd = min(a + seg_len, npos);
+                float d = cf;
+                bool alive = true;
+                for (int j = a; j < bnd; j++) {
+                    alive = d >= prev[j - 2];               // the comparison the sequential code makes at j
+                    if (!alive) break;
+                    d = __fsub_rn(d, slip);
+                    fs[j] = d;
+                    fp[j] = (uint16_t)cp;
+                }
+                if (alive) cf = d;                          // still the running best at the end of the segment
+                else { cf = seg_f[t]; cp = seg_p[t]; }      // lost inside it: the local scan's end state is the truth
+            }
+            if (i + 1 < nev) {                              // thread 0's share of the row staging
+                const float *rown = tr + (long)(i + 1) * ld_t;
+                float *dst = rowbuf + ((i + 1) & 1) * nstate;
+                for (int c = 0; c < nstate; c += THREADS) cp_async4_r(dst + c, rown + c);
+                cp_async_commit_r();
+            }
+        }
+        __syncthreads();
+        // ---- slip (transducer.py:56-60) ----
         uint16_t *tbi = tbb + (size_t)i * P;
-        for (int j = tid; j < npos; j += THREADS) {         // slip (transducer.py:56-60)
+        for (int j = tid; j < npos; j += THREADS) {
             const float from = __fadd_rn(fs[j], e[j]);
             float c = nxt[j];
             uint16_t s = src[j];
             if (!(from <= c)) { c = from; s = fp[j]; }      // tie -> no slip; NaN -> slip (np.where(from <= c, ...))
-            prev[j] = c;                                    // every read of prev for this event happened before the barrier
+            prev[j] = c;
             tbi[j] = s;
         }
+        cp_async_wait0_r();
         __syncthreads();
     }
 
@@ -183,10 +249,10 @@ extern "C" size_t sloika_remap_workspace_bytes(int T, int B, int P)
     return sizeof(uint16_t) * (size_t)T * (size_t)B * (size_t)P;
 }
 
-static size_t remap_smem_bytes(int P)
+static size_t remap_smem_bytes(int P, int nstate)
 {
-    // prev, nxt, e, fs (float) + fp, src (uint16, padded) + sq (int32)
-    return (size_t)P * (4 * 4 + 2 * 2 + 4) + 8;
+    // prev, nxt, e, fs (float) + fp, src (uint16) + sq (int32) + two staged transducer rows
+    return (size_t)P * (4 * 4 + 2 * 2 + 4) + (size_t)2 * nstate * 4 + 16;
 }
 
 extern "C" int sloika_remap_fwd(const float *trans, long ld_t, long ld_b, const int32_t *nev, int T, int B, int nstate,
@@ -198,15 +264,22 @@ extern "C" int sloika_remap_fwd(const float *trans, long ld_t, long ld_b, const 
     if (has_slip && !(slip >= 0.0)) return SLOIKA_ERR_ARG;              // transducer.py:26
     if ((prior_initial || prior_final) && ld_prior < P) return SLOIKA_ERR_ARG;
     if (P > 65535) return SLOIKA_ERR_UNSUPPORTED;                       // uint16 traceback
-    const size_t smem = remap_smem_bytes(P);
+    const size_t smem = remap_smem_bytes(P, nstate);
     if (smem > 200 * 1024) return SLOIKA_ERR_UNSUPPORTED;               // sequence too long for the on-chip score vectors
     if (!ws || ws_bytes < sloika_remap_workspace_bytes(T, B, P)) return SLOIKA_ERR_WORKSPACE;
-    cudaError_t err = cudaFuncSetAttribute(remap::remap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (err != cudaSuccess) return (int)err;
     const float pen = has_slip ? (float)slip : nanf("");                // np.float32(None) is NaN in the reference
-    remap::remap_kernel<<<B, remap::THREADS, smem, (cudaStream_t)stream>>>(
-        trans, ld_t, ld_b, nev, T, nstate, seq, ld_seq, npos, P, pen, prior_initial, prior_final, ld_prior, is_log,
-        static_cast<uint16_t *>(ws), path_out, score_out);
+#define REMAP_LAUNCH(TH, NS)                                                                                          \
+    {                                                                                                                \
+        cudaError_t err = cudaFuncSetAttribute(remap::remap_kernel<TH, NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                               (int)smem);                                                           \
+        if (err != cudaSuccess) return (int)err;                                                                     \
+        remap::remap_kernel<TH, NS><<<B, TH, smem, (cudaStream_t)stream>>>(                                          \
+            trans, ld_t, ld_b, nev, T, nstate, seq, ld_seq, npos, P, pen, prior_initial, prior_final, ld_prior, is_log, \
+            static_cast<uint16_t *>(ws), path_out, score_out);                                                       \
+    }
+    if (P <= 1024) REMAP_LAUNCH(64, 16)                                 // chunk-sized sequences: many small CTAs per SM
+    else REMAP_LAUNCH(remap::MAX_THREADS, remap::MAX_SEG)               // long sequences: more threads per read
+#undef REMAP_LAUNCH
     SLOIKA_RETURN_LAUNCH_STATUS();
 }
 

@@ -25,7 +25,7 @@ def _device_of(t):
 
 
 def map_to_sequence_batch(trans, sequences, nev=None, slip=None, prior_initial=None, prior_final=None, log=True,
-                          return_device=False):
+                          return_device=False, timing=None):
     """Map a batch of reads.
 
     :param trans: `[T, B, nstate]` float32 transducer posteriors (ndarray or torch CUDA tensor, any row strides);
@@ -36,6 +36,7 @@ def map_to_sequence_batch(trans, sequences, nev=None, slip=None, prior_initial=N
     :param slip: slip penalty >= 0, or None -- which, as in the reference, runs slips with a NaN penalty
     :param prior_initial, prior_final: lists / `[B, P]` arrays of float64 priors, or None
     :param log: `trans` is already log-scaled
+    :param timing: optional dict; receives `kernel_ms` (CUDA events around the launch, synchronises)
 
     :returns: (scores float32 [B], list of B int32 path arrays) or the device tensors (scores, paths [B, T])
     """
@@ -85,11 +86,18 @@ def map_to_sequence_batch(trans, sequences, nev=None, slip=None, prior_initial=N
         ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=dev)
         paths = torch.zeros((B, T), dtype=torch.int32, device=dev)
         score = torch.empty(B, dtype=torch.float32, device=dev)
+        if timing is not None:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
         cabi.check(lib.sloika_remap_fwd(
             cabi.ptr(trans), ld_t, ld_b, cabi.ptr(nev_d), T, B, S, cabi.ptr(seq_d), P, cabi.ptr(npos_d), P,
             0.0 if slip is None else float(slip), 0 if slip is None else 1, cabi.ptr(p0), cabi.ptr(p1), P,
             1 if log else 0, cabi.ptr(ws), nbytes, cabi.ptr(paths), cabi.ptr(score), cabi.stream_ptr(dev)),
             'map_to_sequence')
+        if timing is not None:
+            ev1.record()
+            torch.cuda.synchronize(dev)
+            timing['kernel_ms'] = ev0.elapsed_time(ev1)
     if return_device:
         return score, paths
     score_h, paths_h = score.cpu().numpy(), paths.cpu().numpy()
