@@ -14,6 +14,6 @@ def install_as_sloika():
     import sys
     sys.modules.setdefault('sloika', sys.modules[__name__])
     for sub in ('config', 'variables', 'activation', 'conv', 'layers', 'module_tools', 'decode',
-                'bio', 'maths', 'basecall', 'helpers'):
+                'bio', 'maths', 'basecall', 'helpers', 'batch', 'util', 'fast5', 'transducer', 'viterbi_helpers'):
         mod = importlib.import_module('sloika_b200.' + sub)
         sys.modules.setdefault('sloika.' + sub, mod)
