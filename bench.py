@@ -367,7 +367,7 @@ def run_b200_arm(args):
                        4.0 * net.size * (T // stride_of(net)) * B / 1e9)},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(x_host.numel() * 4),
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": wall_e2e / args.steps},
-        "gpu_launches": launches,
+        "gpu_launches": launches * world,          # kernels of this repo enqueued in the timed region, all ranks
         "roofline": roofline,
         "kernels": breakdown,
         "paper_roofline_samples_per_s": paper,
