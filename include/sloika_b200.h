@@ -186,6 +186,18 @@ int sloika_remap_fwd(const float *trans, long ld_t, long ld_b, const int32_t *ne
                      void *ws, size_t ws_bytes, int32_t *path_out, float *score_out, void *stream);
 int sloika_slip_update_fwd(const float *x, int n, float slip, float *from_score, long long *from_pos, void *stream);
 
+/*
+ * Best path -> base sequence: bio.kmers_to_sequence -- sloika/bio.py:228-237
+ * (max_overlap :160-178, reduce_kmers :208-225) -- as SeqPrinter.write applies it to a read's k-mer states
+ * (sloika/basecall.py:141-149), batched, one CTA per read.
+ *   path int32 [B][ld_path]: k-mer states (sloika_viterbi_*'s path_out); path_len int32 [B]
+ *   always_move != 0: a k-mer followed by itself is a move of klen letters (transducer models), else a stay
+ *   alphabet: nbase device bytes ("ACGT"); out: [B][ld_out] bytes, ld_out >= klen * max(path_len); out_len int32 [B]
+ */
+int sloika_path_to_bases_fwd(const int32_t *path, long ld_path, const int32_t *path_len, int B, int klen, int nbase,
+                             int always_move, const char *alphabet, char *out, long ld_out, int32_t *out_len,
+                             void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -52,12 +52,22 @@ def prepare_signal(signal, trim, open_pore_fraction):
     return ((signal - np.median(signal)) / mad(signal)).astype(sloika_dtype)
 
 
-def basecall_signals(signals, kmer_len=5, min_prob=1e-5, skip=0.0, nbase=4, network=None):
+class CalledPath(list):
+    """A best path (list of k-mer states) that also carries the base sequence assembled on the device
+    (`decode.paths_to_sequences`); `SeqPrinter.write` uses it instead of spelling the k-mers on the host."""
+    sequence = None
+    assembly = None          # (kmer_len, alphabet, always_move) the sequence was assembled with
+
+
+def basecall_signals(signals, kmer_len=5, min_prob=1e-5, skip=0.0, nbase=4, network=None, assemble=None):
     """Forward + Viterbi for a batch of normalised whole-read signals (list of 1-D float32 arrays).
 
     Reads are packed into one padded `[Tmax, B, 1]` batch with per-read lengths; every kernel honours
     the lengths, so each read sees exactly the computation it would see alone (`basecall.py:117-119`
     feeds one read per call).  Returns a list of `(score, path)`.
+
+    :param assemble: optional `(alphabet, always_move)`: also assemble the base sequences on the device
+        (`bio.kmers_to_sequence`, bio.py:228-237); paths are then `CalledPath` lists with `.sequence` set
     """
     import torch
     net = network if network is not None else calc_post
@@ -72,8 +82,22 @@ def basecall_signals(signals, kmer_len=5, min_prob=1e-5, skip=0.0, nbase=4, netw
         host[:len(s), b] = torch.from_numpy(np.ascontiguousarray(s, dtype=np.float32))
     x = host.to(dev, non_blocking=True).unsqueeze(2)
     out = net.forward_device(x, torch.from_numpy(lens).to(dev), fused_decode=(kmer_len == 5 and nbase == 4))
-    score, paths = decode.viterbi_batch(out, None, klen=kmer_len, skip_pen=skip, min_prob=min_prob, nbase=nbase)
-    return list(zip(score.tolist(), paths))
+    if assemble is None:
+        score, paths = decode.viterbi_batch(out, None, klen=kmer_len, skip_pen=skip, min_prob=min_prob, nbase=nbase)
+        return list(zip(score.tolist(), paths))
+    alphabet, always_move = assemble
+    if isinstance(alphabet, bytes):
+        alphabet = alphabet.decode('ascii')
+    score, paths_d, plen_d = decode.viterbi_batch(out, None, klen=kmer_len, skip_pen=skip, min_prob=min_prob,
+                                                  nbase=nbase, return_device=True)
+    seqs = decode.paths_to_sequences(paths_d, plen_d, kmer_len, alphabet, always_move=always_move)
+    paths_h, plen_h = paths_d.cpu().numpy(), plen_d.cpu().numpy()
+    calls = []
+    for b, sc in enumerate(score.cpu().numpy().tolist()):
+        path = CalledPath(paths_h[b, :plen_h[b]].tolist())
+        path.sequence, path.assembly = seqs[b], (kmer_len, alphabet, bool(always_move))
+        calls.append((sc, path))
+    return calls
 
 
 def basecall_chunks(x_host, kmer_len=5, min_prob=1e-5, skip=0.0, nbase=4, network=None):
@@ -143,7 +167,8 @@ def raw_batch(fast5_file_names, trim=(200, 10), open_pore_fraction=0, kmer_len=5
         names.append(sn)
         signals.append(sig)
         slots.append(i)
-    calls = basecall_signals(signals, kmer_len=kmer_len, min_prob=min_prob, skip=skip, nbase=len(alphabet))
+    calls = basecall_signals(signals, kmer_len=kmer_len, min_prob=min_prob, skip=skip, nbase=len(alphabet),
+                             assemble=(alphabet, transducer))
     for i, sn, sig, (score, path) in zip(slots, names, signals, calls):
         results[i] = (sn, np.float32(score), path, len(sig))
     return results
@@ -179,7 +204,10 @@ class SeqPrinter(object):
             self.fh.close()
 
     def write(self, read_name, score, call, nev):
-        seq = bio.states_to_sequence(call, self.kmer_len, self.alphabet, always_move=self.transducer)
+        if getattr(call, 'assembly', None) == (self.kmer_len, self.alphabet, bool(self.transducer)):
+            seq = call.sequence                  # assembled on the device with the same conventions
+        else:
+            seq = bio.states_to_sequence(call, self.kmer_len, self.alphabet, always_move=self.transducer)
         self.fh.write(">{} score {:.0f}, {} {} to {} bases\n".format(read_name, score,
                                                                      nev, self.datatype, len(seq)))
         self.fh.write(seq + '\n')

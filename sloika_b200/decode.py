@@ -142,3 +142,45 @@ def viterbi(post, klen, skip_pen=0.0, log=False, nbase=4):
         post3 = post.unsqueeze(1)
     score, paths = viterbi_batch(post3, None, klen=klen, skip_pen=skip_pen, min_prob=0.0, nbase=nbase, log=log)
     return score[0], paths[0]
+
+
+def paths_to_sequences(paths, path_len, kmer_len=5, alphabet='ACGT', always_move=True):
+    """Base sequences of a batch of best paths, assembled on the device.
+
+    Same strings as `bio.kmers_to_sequence([kmers[s] for s in path], always_move)` (`bio.py:228-237`), which
+    `SeqPrinter.write` computes per read on the host (`basecall.py:141-149`).
+
+    :param paths: int32 `[B, T]` k-mer states (device tensor from `viterbi_batch(..., return_device=True)`, or array)
+    :param path_len: int32 `[B]` valid entries per read
+    :param always_move: transducer convention -- a k-mer followed by itself is a move, not a stay
+
+    :returns: list of B `str`
+    """
+    import torch
+    lib = cabi.load()
+    if isinstance(alphabet, bytes):
+        alphabet = alphabet.decode('ascii')
+    if not isinstance(paths, torch.Tensor):
+        paths = torch.as_tensor(np.ascontiguousarray(paths, dtype=np.int32))
+    if not isinstance(path_len, torch.Tensor):
+        path_len = torch.as_tensor(np.ascontiguousarray(path_len, dtype=np.int32))
+    dev = paths.device if paths.is_cuda else torch.device('cuda', torch.cuda.current_device())
+    paths = paths.to(dev, dtype=torch.int32).contiguous()
+    path_len = path_len.to(dev, dtype=torch.int32).contiguous()
+    B, T = paths.shape
+    if B == 0:
+        return []
+    ld_out = max(1, kmer_len * T)
+    with torch.cuda.device(dev):
+        alpha = torch.tensor(list(alphabet.encode('ascii')), dtype=torch.uint8, device=dev)
+        out = torch.empty((B, ld_out), dtype=torch.uint8, device=dev)
+        out_len = torch.empty(B, dtype=torch.int32, device=dev)
+        from sloika_b200.engine import launch
+        launch('path_to_bases', 1, lib.sloika_path_to_bases_fwd,
+               cabi.ptr(paths), paths.stride(0), cabi.ptr(path_len), B, kmer_len, len(alphabet),
+               1 if always_move else 0, cabi.ptr(alpha), cabi.ptr(out), ld_out, cabi.ptr(out_len),
+               cabi.stream_ptr(dev))
+    lens = out_len.cpu().numpy()
+    width = int(lens.max()) if B else 0
+    chars = out[:, :max(width, 1)].cpu().numpy()
+    return [chars[b, :lens[b]].tobytes().decode('ascii') for b in range(B)]

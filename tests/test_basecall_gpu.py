@@ -2,6 +2,7 @@
 Viterbi + sequence assembly against the golden basecalls made with the reference's decode.py/bio.py
 on the oracle's float32 posteriors (tools/make_golden.py)."""
 import io
+import json
 import os
 
 import numpy as np
@@ -10,7 +11,7 @@ import torch
 
 from conftest import scaled_signal
 from oracle import decode_ref, forward_ref, host_ref
-from sloika_b200 import basecall, decode
+from sloika_b200 import basecall, bio, decode
 
 pytestmark = pytest.mark.gpu
 NAMES = ['read{}'.format(i) for i in range(1, 9)]
@@ -86,3 +87,53 @@ def test_decode_post_dropin(calls, read_basecalls, pretrained):
     score, path = basecall.decode_post(ref_post, 5, True, True, 1e-5, 0.0, None, nbase=4)
     s_ref, p_ref = decode_ref.decode_post(ref_post, 5, 1e-5, skip=0.0)
     assert path == p_ref and abs(score - s_ref) < 1e-2
+
+
+# ------------------------------------------------------------------ row f3: best path -> bases on the device
+def test_paths_to_sequences_matches_reference_vectors(golden_dir, read_basecalls):
+    """`decode.paths_to_sequences` (csrc/bases.cu) returns the very strings the reference's
+    `bio.kmers_to_sequence` produced (tests/golden/bio_cases.json, made by importing the reference), for stays
+    allowed and always_move, and for the golden basecalls of the bundled reads."""
+    with open(os.path.join(golden_dir, 'bio_cases.json')) as fh:
+        cases = json.load(fh)
+    for flag in (False, True):
+        sel = [(p, s) for p, (am, s) in zip(cases['paths'], cases['seqs']) if am == flag]
+        if not sel:
+            continue
+        width = max(len(p) for p, _ in sel)
+        arr = np.zeros((len(sel), width), dtype=np.int32)
+        for b, (p, _) in enumerate(sel):
+            arr[b, :len(p)] = p
+        got = decode.paths_to_sequences(arr, [len(p) for p, _ in sel], 5, 'ACGT', always_move=flag)
+        assert got == [s for _, s in sel]
+    names = sorted(read_basecalls)
+    width = max(len(read_basecalls[n]['path']) for n in names)
+    arr = np.zeros((len(names), width), dtype=np.int32)
+    for b, n in enumerate(names):
+        arr[b, :len(read_basecalls[n]['path'])] = read_basecalls[n]['path']
+    got = decode.paths_to_sequences(arr, [len(read_basecalls[n]['path']) for n in names], 5, b'ACGT', always_move=True)
+    assert got == [read_basecalls[n]['seq'] for n in names]
+
+
+def test_paths_to_sequences_random_against_host_assembly():
+    """Other alphabets / k-mer lengths, empty and single-state paths, long paths spanning many thread blocks."""
+    rng = np.random.default_rng(3)
+    for klen, alphabet in ((5, 'ACGT'), (3, 'ACGT'), (3, 'ACGTZ'), (1, 'AC'), (6, 'ACGT')):
+        nst = len(alphabet) ** klen
+        lens = [0, 1, 2, 7, 300, 5000]
+        arr = np.zeros((len(lens), max(lens)), dtype=np.int32)
+        for b, n in enumerate(lens):
+            walk = rng.integers(0, nst, size=n)
+            # make most transitions genuine overlaps so that all move lengths occur
+            for i in range(1, n):
+                r = rng.random()
+                if r < 0.3:
+                    walk[i] = walk[i - 1]
+                elif r < 0.8:
+                    m = int(rng.integers(1, klen + 1))
+                    walk[i] = (walk[i - 1] * len(alphabet) ** m + rng.integers(0, len(alphabet) ** m)) % nst
+            arr[b, :n] = walk
+        for always_move in (True, False):
+            got = decode.paths_to_sequences(arr, lens, klen, alphabet, always_move=always_move)
+            want = [bio.states_to_sequence(arr[b, :n], klen, alphabet, always_move=always_move) for b, n in enumerate(lens)]
+            assert got == want
