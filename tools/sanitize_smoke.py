@@ -1,0 +1,47 @@
+"""Small invocations of every kernel family, meant to be run under compute-sanitizer:
+
+    compute-sanitizer --tool memcheck  python tools/sanitize_smoke.py
+    compute-sanitizer --tool racecheck python tools/sanitize_smoke.py
+"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+from sloika_b200 import decode, transducer, zoo
+
+DEV = torch.device('cuda:0')
+
+
+def main():
+    np.random.seed(1)
+    torch.manual_seed(1)
+    # conv + GRU (narrow, reverse and forward) + f16/tf32 GEMMs + softmax + fused Viterbi, ragged batch
+    net = zoo.raw_rgrgr().compile()
+    x = torch.randn((640, 9, 1), device=DEV)
+    lens = torch.tensor([640, 1, 7, 640, 333, 12, 300, 500, 5], dtype=torch.int32, device=DEV)
+    for lengths in (None, lens):
+        out = net.forward_device(x, lengths, fused_decode=True)
+        score, paths, plen = decode.viterbi_batch(out, None, min_prob=1e-5, return_device=True)
+        decode.paths_to_sequences(paths, plen, 5, 'ACGT', True)
+        post = net.forward_device(x, lengths)
+        decode.viterbi_batch(post, None, min_prob=1e-5)
+    # wide GRU kernels (H = 110 / 142) and the elu -> tf32 GEMM path
+    for build in (zoo.raw_rGr, zoo.pretrained_like):
+        net = build().compile()
+        out = net.forward_device(torch.randn((400, 5, 1), device=DEV), None, fused_decode=True)
+        decode.viterbi_batch(out, None, min_prob=1e-5)
+    # remap decode, both launch geometries
+    rng = np.random.default_rng(2)
+    for T, B, S, P in ((60, 5, 65, 40), (40, 3, 65, 1100)):
+        lt = torch.log_softmax(torch.randn((T, B, S), device=DEV), dim=-1)
+        seqs = [rng.integers(1, S, size=int(n)) for n in rng.integers(3, P + 1, size=B)]
+        transducer.map_to_sequence_batch(lt, seqs, slip=5.0)
+    torch.cuda.synchronize()
+    print("sanitize smoke done")
+
+
+if __name__ == '__main__':
+    main()
