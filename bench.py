@@ -248,8 +248,15 @@ def run_b200_arm(args):
         out = calc_post.forward_device(x_dev, fused_decode=True)
         return decode.viterbi_batch(out, None, klen=5, skip_pen=0.0, min_prob=1e-5, return_device=True)
 
-    def step_e2e():
-        return basecall.basecall_chunks(x_host, kmer_len=5, min_prob=1e-5, skip=0.0, network=calc_post)
+    def run_e2e(steps):
+        """`steps` batches through the public host-buffer API (`basecall.basecall_chunk_stream`): every batch is copied
+        from pinned host memory to the device and its scores / paths / lengths are copied back, all inside the timed
+        region; the copies of neighbouring batches overlap the kernels (software pipeline of depth 2)."""
+        res = None
+        for res in basecall.basecall_chunk_stream((x_host for _ in range(steps)), kmer_len=5, min_prob=1e-5, skip=0.0,
+                                                  network=calc_post):
+            pass
+        return res
 
     def barrier():
         torch.cuda.synchronize()
@@ -294,9 +301,12 @@ def run_b200_arm(args):
     ms_dev = max_over_ranks(ms_dev)
 
     # ---- end-to-end timing through the host-buffer API (e2e): H2D + D2H inside, wall clock on host ----
-    for _ in range(2):
-        step_e2e()
-    _, wall_e2e, res_e2e = timed(step_e2e, args.steps)
+    run_e2e(2)
+    barrier()
+    wall0 = time.perf_counter()
+    res_e2e = run_e2e(args.steps)
+    barrier()
+    wall_e2e = (time.perf_counter() - wall0) * 1e3
     wall_e2e = max_over_ranks(wall_e2e)
     clocks = sampler.stop() if sampler else None
 

@@ -120,6 +120,65 @@ def basecall_chunks(x_host, kmer_len=5, min_prob=1e-5, skip=0.0, nbase=4, networ
     return score.cpu().numpy(), paths.cpu().numpy(), plen.cpu().numpy()
 
 
+def basecall_chunk_stream(batches, kmer_len=5, min_prob=1e-5, skip=0.0, nbase=4, network=None):
+    """`basecall_chunks` over a stream of host batches, software-pipelined: the host->device copy of batch k+1 and
+    the device->host copy of batch k-1's results run on their own CUDA streams while the kernels of batch k execute.
+
+    :param batches: iterable of float32 torch CPU tensors `[T, B]` / `[T, B, 1]` (pinned memory for real overlap)
+    :returns: generator of (scores float32[B], paths int32[B, T'], path_len int32[B]) NumPy arrays, in input order
+    """
+    import torch
+    net = network if network is not None else calc_post
+    if net is None:
+        raise RuntimeError("init_worker() has not been called")
+    dev = net.device
+    compute = torch.cuda.current_stream(dev)
+    h2d, d2h = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    x_dev = [None, None]
+    compute_done = [None, None]            # event: kernels of the batch that last used input buffer k % 2 have finished
+    pending = None                         # (host result tensors, copy-out event, device tensors kept alive)
+
+    def finish(item):
+        host, ev, _keep = item
+        ev.synchronize()
+        return tuple(t.numpy() for t in host)
+
+    for k, xh in enumerate(batches):
+        if xh.dim() == 2:
+            xh = xh.unsqueeze(2)
+        slot = k % 2
+        with torch.cuda.stream(h2d):
+            if compute_done[slot] is not None:
+                h2d.wait_event(compute_done[slot])          # the buffer's previous batch has been consumed
+            if x_dev[slot] is None or x_dev[slot].shape != xh.shape:
+                x_dev[slot] = torch.empty(xh.shape, dtype=torch.float32, device=dev)
+            x_dev[slot].copy_(xh, non_blocking=True)
+            copied = torch.cuda.Event()
+            copied.record(h2d)
+        compute.wait_event(copied)
+        out = net.forward_device(x_dev[slot], fused_decode=(kmer_len == 5 and nbase == 4))
+        res = decode.viterbi_batch(out, None, klen=kmer_len, skip_pen=skip, min_prob=min_prob, nbase=nbase,
+                                   return_device=True)
+        done = torch.cuda.Event()
+        done.record(compute)
+        compute_done[slot] = done
+        with torch.cuda.stream(d2h):
+            d2h.wait_event(done)
+            host = []
+            for t in res:
+                t.record_stream(d2h)
+                buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+                buf.copy_(t, non_blocking=True)
+                host.append(buf)
+            out_ev = torch.cuda.Event()
+            out_ev.record(d2h)
+        if pending is not None:
+            yield finish(pending)                           # batch k-1, while batch k runs
+        pending = (host, out_ev, res)
+    if pending is not None:
+        yield finish(pending)
+
+
 def _read_raw(fast5_file_name):
     from sloika_b200.fast5 import Fast5
     with Fast5(fast5_file_name) as f5:

@@ -137,3 +137,23 @@ def test_paths_to_sequences_random_against_host_assembly():
             got = decode.paths_to_sequences(arr, lens, klen, alphabet, always_move=always_move)
             want = [bio.states_to_sequence(arr[b, :n], klen, alphabet, always_move=always_move) for b, n in enumerate(lens)]
             assert got == want
+
+
+def test_chunk_stream_equals_per_batch_calls():
+    """The software-pipelined host-buffer API returns, in order, exactly what `basecall_chunks` returns batch by batch
+    (input double-buffering and asynchronous copy-out must not mix batches up), including a shape change mid-stream."""
+    from sloika_b200 import zoo
+    np.random.seed(8)
+    net = zoo.raw_rgrgr().compile()
+    gen = torch.Generator().manual_seed(8)
+    batches = [torch.randn((1000, 24), generator=gen).pin_memory() for _ in range(4)]
+    batches.append(torch.randn((600, 7), generator=gen).pin_memory())
+    batches.append(torch.randn((1000, 24), generator=gen).pin_memory())
+    streamed = list(basecall.basecall_chunk_stream(iter(batches), network=net))
+    assert len(streamed) == len(batches)
+    for xh, (score, paths, plen) in zip(batches, streamed):
+        s1, p1, l1 = basecall.basecall_chunks(xh, network=net)
+        assert np.array_equal(score, s1) and np.array_equal(plen, l1)
+        for b in range(len(l1)):
+            assert np.array_equal(paths[b, :l1[b]], p1[b, :l1[b]])
+    assert list(basecall.basecall_chunk_stream(iter([]), network=net)) == []
