@@ -51,6 +51,7 @@ struct Params {
     int stages;       // smem pipeline depth
     int vec_out;      // rows of y are 16-byte aligned: 128-bit stores
     int direct;       // vec_out && store rows straight from registers (no smem transpose)
+    int tma_out;      // vec_out: 32 x 32 output boxes leave through cp.async.bulk.tensor stores (tmap_y)
     int dbg;          // timing experiments only (SLOIKA_B200_GEMM_DBG): 1 no split math, 2 no stores, 4 no MMA
 };
 
@@ -68,7 +69,7 @@ __host__ __device__ inline size_t smem_bytes(int BN, int nkb, int stages, bool f
 // callers that know |x| and |W| stay far below the fp16 range (bounded activations): see sloika_linear_fwd_ex.
 template <int ACT, bool STATS, bool F16>
 __global__ void __launch_bounds__(THREADS, 1)
-gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params p)
+gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_y, const Params p)
 {
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment for the 128-byte swizzle; plain pointer arithmetic keeps the shared address space
@@ -102,7 +103,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params p)
         for (int a = 0; a < NACC; a++) { tc::mbar_init(&tmem_full[a], 1); tc::mbar_init(&tmem_empty[a], 256); }
         tc::mbar_fence_init();
     }
-    if (warp == 4 && lane == 0) tc::tma_prefetch_desc(&tmap_x);
+    if (warp == 4 && lane == 0) { tc::tma_prefetch_desc(&tmap_x); tc::tma_prefetch_desc(&tmap_y); }
     if (warp == 5) tc::tmem_alloc(tmem_base_s, TMEM_COLS);
     // weights of this slice: split into hi / lo and stored K-major, 128-byte swizzled, zero padded
     for (int e = tid; e < BN * nkb * KB; e += THREADS) {
@@ -171,6 +172,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params p)
                             const uint64_t dal = tc::umma_desc_sw64_kmajor(a_lo + ks * 32);
                             const uint64_t dbh = tc::umma_desc_sw64_kmajor(b_hi + ks * 32);
                             const uint64_t dbl = tc::umma_desc_sw64_kmajor(b_lo + ks * 32);
+                            if (p.dbg & 4) continue;
                             tc::umma_f16_ss(d_tmem, dah, dbh, idesc, (kb | ks) != 0);
                             tc::umma_f16_ss(d_tmem, dal, dbh, idesc, true);
                             tc::umma_f16_ss(d_tmem, dah, dbl, idesc, true);
@@ -215,6 +217,11 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params p)
                     // doubles the number of TMA loads in flight)
                     const uint8_t *raw = Abase + (size_t)s * STAGE_BYTES;
                     uint8_t *h16 = Abase + (size_t)s * STAGE_BYTES;
+                    if (p.dbg & 1) {                                // timing experiments: no split at all
+                        tc::fence_proxy_async();
+                        tc::mbar_arrive(&full_split[s]);
+                        continue;
+                    }
                     float4 va[4], vb[4];
 #pragma unroll
                     for (int i = 0; i < 4; i++) {
@@ -270,6 +277,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params p)
         const int eg = warp < 4 ? 0 : 1;
         const int lq = warp & 3;
         float *stg = stg_all + (eg * 4 + lq) * 32 * STG_LD;
+        // TMA-store path: a dense 32 x 32 fp32 box per warp in the SWIZZLE_128B layout (1024-byte aligned)
+        uint8_t *stg_t = reinterpret_cast<uint8_t *>(stg_all) + (eg * 4 + lq) * 4096;
         const int nchunks = (BN + 31) / 32;
         uint32_t tile = 0;
         for (long mt = cta_in_slice; mt < m_tiles; mt += p.ctas_per_slice, tile++) {
@@ -293,6 +302,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params p)
                     tc::mbar_arrive(&tmem_empty[a]);
                     released = true;
                 }
+                if (p.tma_out) {                                 // the previous box of this warp has left shared memory
+                    if (lane == 0) tc::bulk_wait_read();
+                    __syncwarp();
+                }
                 // thread = row: bias + activation
                 float o[32];
 #pragma unroll
@@ -303,8 +316,21 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params p)
                         o[i + 1] = apply_act_t<ACT>(__uint_as_float(v[i + 1]) + b4.y);
                         o[i + 2] = apply_act_t<ACT>(__uint_as_float(v[i + 2]) + b4.z);
                         o[i + 3] = apply_act_t<ACT>(__uint_as_float(v[i + 3]) + b4.w);
-                        if (!p.direct)
+                        if (p.tma_out)
+                            *reinterpret_cast<float4 *>(stg_t + lane * 128 + ((((i >> 2) ^ lane) & 7) << 4)) =
+                                make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
+                        else if (!p.direct)
                             *reinterpret_cast<float4 *>(&stg[lane * STG_LD + i]) = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
+                    }
+                }
+                if (p.tma_out) {
+                    // one elected lane hands the box to the TMA engine: no shared-memory read-back, no store
+                    // instructions, columns >= N and rows >= M are clipped by the tensor map
+                    tc::fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0 && !(p.dbg & 2)) {
+                        tc::tma_store_2d(stg_t, &tmap_y, n0 + c0, (int)row0);
+                        tc::bulk_commit();
                     }
                 }
                 if (p.direct && !(p.dbg & 2)) {
@@ -359,7 +385,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params p)
                     }
                 }
                 __syncwarp();
-                if (!p.direct && !(p.dbg & 2)) {
+                if (!p.direct && !p.tma_out && !(p.dbg & 2)) {
                     if (p.vec_out) {
                         // 8 lanes x float4 cover the 32 columns of one row: 4 rows (4 x 128 B) per instruction
                         const int cq = (lane & 7) * 4, rsub = lane >> 3;
@@ -404,6 +430,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmap_x, const Params p)
                 if (m < p.M) p.stats[(m * p.n_slices + slice) * 2 + eg] = make_float2(m_run, s_run);
             }
         }
+        if (p.tma_out && lane == 0) tc::bulk_wait_all();         // every box has been written before the CTA retires
     }
 
     tc::tc_fence_before();
@@ -440,13 +467,14 @@ int plan_slices(int K, int N, int *bn_out, bool f16)
 {
     if (K <= 0 || K > 256 || N <= 0) return 0;
     const int nkb = (K + KB - 1) / KB;
+    // slice widths are multiples of 32 columns: the epilogue works in 32-column boxes (TMA stores clip at N)
     int bn_max = 256;
     const char *bn_env = getenv("SLOIKA_B200_GEMM_BN");
-    if (bn_env && atoi(bn_env) >= 16) bn_max = atoi(bn_env) / 16 * 16;
-    while (bn_max >= 16 && smem_bytes(bn_max, nkb, 3, f16) > 227 * 1024) bn_max -= 16;
-    if (bn_max < 16) return 0;
+    if (bn_env && atoi(bn_env) >= 32) bn_max = atoi(bn_env) / 32 * 32;
+    while (bn_max >= 32 && smem_bytes(bn_max, nkb, 3, f16) > 227 * 1024) bn_max -= 32;
+    if (bn_max < 32) return 0;
     const int n_slices = (N + bn_max - 1) / bn_max;
-    if (bn_out) *bn_out = ((N + n_slices - 1) / n_slices + 15) / 16 * 16;
+    if (bn_out) *bn_out = ((N + n_slices - 1) / n_slices + 31) / 32 * 32;
     return n_slices;
 }
 
@@ -485,6 +513,16 @@ int launch(const float *x, long ldx, const float *W, const float *bias, float *y
     p.vec_out = ((ldy & 3) == 0) && (((uintptr_t)y & 15) == 0);
     const char *direct = getenv("SLOIKA_B200_GEMM_DIRECT");
     p.direct = (p.vec_out && direct && atoi(direct) != 0) ? 1 : 0;
+    CUtensorMap tmap_y = tmap;                                 // placeholder when the TMA-store path is off
+    p.tma_out = 0;
+    if (p.vec_out && !p.direct && !getenv("SLOIKA_B200_GEMM_NO_TMA_OUT")) {
+        const cuuint64_t ydim[2] = {(cuuint64_t)N, (cuuint64_t)M};
+        const cuuint64_t ystride[1] = {(cuuint64_t)ldy * 4};
+        const cuuint32_t ybox[2] = {32, 32};
+        if (enc(&tmap_y, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, y, ydim, ystride, ybox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
+            p.tma_out = 1;
+    }
     const char *dbg = getenv("SLOIKA_B200_GEMM_DBG");
     p.dbg = dbg ? atoi(dbg) : 0;
     const long m_tiles = (M + BM - 1) / BM;
@@ -508,7 +546,7 @@ int launch(const float *x, long ldx, const float *W, const float *bias, float *y
     {                                                                                                         \
         cudaError_t err = cudaFuncSetAttribute(KERN, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
         if (err != cudaSuccess) return (int)err;                                                              \
-        KERN<<<grid, THREADS, smem, st>>>(tmap, p);                                                           \
+        KERN<<<grid, THREADS, smem, st>>>(tmap, tmap_y, p);                                                           \
     }
 #define LAUNCH_ACT(A)                                                                                         \
     case A:                                                                                                   \
