@@ -348,7 +348,7 @@ def run_b200_arm(args):
     traffic = None
     try:
         if args.workload == 'raw_rgrgr' and B == BATCH_PER_GPU and T == CHUNK_LEN:
-            with open(os.path.join(ROOT, 'profiles', 'r1i_traffic.json')) as fh:
+            with open(os.path.join(ROOT, 'profiles', 'r1j_traffic.json')) as fh:
                 traffic = json.load(fh).get(dominant)
     except Exception:
         traffic = None
