@@ -60,6 +60,11 @@ int sloika_b200_device_info(int *sm_count, int *cc_major, int *cc_minor);
 int sloika_conv1d_fwd(const float *x, const float *W, const float *bias, float *y, long ldy,
                       const int32_t *lengths, int T, int B, int Cin, int Cout, int winlen, int stride,
                       int pad_l, int pad_r, int act, void *stream);
+/* Same, and additionally folds max |y| into *absmax (atomic max; the caller zeroes it first; NULL = off): lets the next
+ * layer pick the cheaper operand format for outputs that are not bounded by construction (elu). */
+int sloika_conv1d_fwd_ex(const float *x, const float *W, const float *bias, float *y, long ldy,
+                      const int32_t *lengths, int T, int B, int Cin, int Cout, int winlen, int stride,
+                      int pad_l, int pad_r, int act, float *absmax, void *stream);
 
 /*
  * FeedForward.run -- sloika/layers.py:157-158:  y = act( x . W' + bias )
@@ -83,6 +88,12 @@ int sloika_linear_fwd(const float *x, long ldx, const float *W, const float *bia
 #define SLOIKA_GEMM_TC_F16 3
 int sloika_linear_fwd_ex(const float *x, long ldx, const float *W, const float *bias, float *y, long ldy,
                          long M, int K, int N, int act, int algo, void *stream);
+/* The same product with the operand format chosen ON THE DEVICE from a range report of the producer: `absmax` points
+ * to one float holding max |x| (sloika_conv1d_fwd_ex writes it).  Both tensor-core forms are enqueued; the fp16-split one
+ * runs if *absmax < limit, else the tf32-split one -- no host synchronisation.  Returns SLOIKA_ERR_UNSUPPORTED when the
+ * tensor-core kernel cannot take the shape (use sloika_linear_fwd then). */
+int sloika_linear_fwd_gated(const float *x, long ldx, const float *W, const float *bias, float *y, long ldy,
+                            long M, int K, int N, int act, const float *absmax, float limit, void *stream);
 
 /*
  * Softmax.run -- sloika/layers.py:309-314:

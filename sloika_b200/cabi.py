@@ -23,6 +23,8 @@ EXPORTS = {
     'sloika_b200_strerror': (ctypes.c_char_p, [_i]),
     'sloika_b200_device_info': (_i, [_p, _p, _p]),
     'sloika_conv1d_fwd': (_i, [_p, _p, _p, _p, _l, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
+    'sloika_conv1d_fwd_ex': (_i, [_p, _p, _p, _p, _l, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
+    'sloika_linear_fwd_gated': (_i, [_p, _l, _p, _p, _p, _l, _l, _i, _i, _i, _p, ctypes.c_float, _p]),
     'sloika_linear_fwd': (_i, [_p, _l, _p, _p, _p, _l, _l, _i, _i, _i, _p]),
     'sloika_linear_fwd_ex': (_i, [_p, _l, _p, _p, _p, _l, _l, _i, _i, _i, _i, _p]),
     'sloika_softmax_fwd': (_i, [_p, _l, _p, _p, _p, _l, _l, _i, _i, _p]),

@@ -20,7 +20,7 @@ template <int WIN>
 __global__ void __launch_bounds__(256, 2)
 conv1d_raw_kernel(const float *__restrict__ x, const float *__restrict__ W, const float *__restrict__ bias,
                   float *__restrict__ y, long ldy, const int32_t *__restrict__ lengths, int T, int B, int Cout,
-                  int stride, int pad_l, int Tout, int TT, int BT, int act)
+                  int stride, int pad_l, int Tout, int TT, int BT, int act, unsigned *__restrict__ absmax_bits)
 {
     extern __shared__ float xs[];                    // [rows][BT]
     const int b0 = blockIdx.x * BT;
@@ -58,6 +58,7 @@ conv1d_raw_kernel(const float *__restrict__ x, const float *__restrict__ W, cons
     __syncthreads();
     if (bl >= bq) return;
 
+    float amax = 0.0f;                               // max |y| of this thread (for the optional range report)
     for (int tl = 0; tl < TT; tl++) {
         const int t = t0 + tl;
         if (t >= Tout) break;
@@ -80,7 +81,14 @@ conv1d_raw_kernel(const float *__restrict__ x, const float *__restrict__ W, cons
             acc.w = apply_act(acc.w, act);
             float *yp = y + ((long)t * B + bg) * ldy + 4 * c4;
             __stcs(reinterpret_cast<float4 *>(yp), acc);     // streamed once, read by the next layer
+            amax = fmaxf(amax, fmaxf(fmaxf(fabsf(acc.x), fabsf(acc.y)), fmaxf(fabsf(acc.z), fabsf(acc.w))));
         }
+    }
+    if (absmax_bits) {
+        // non-negative floats order like their bit patterns; a NaN has the largest pattern, so it also reads as "huge"
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(__activemask(), amax, o));
+        if ((threadIdx.x & 31) == 0) atomicMax(absmax_bits, __float_as_uint(amax));
     }
 }
 
@@ -89,7 +97,8 @@ conv1d_raw_kernel(const float *__restrict__ x, const float *__restrict__ W, cons
 __global__ void conv1d_generic_kernel(const float *__restrict__ x, const float *__restrict__ W,
                                       const float *__restrict__ bias, float *__restrict__ y, long ldy,
                                       const int32_t *__restrict__ lengths, int T, int B, int Cin, int Cout,
-                                      int winlen, int stride, int pad_l, int Tout, int act)
+                                      int winlen, int stride, int pad_l, int Tout, int act,
+                                      unsigned *__restrict__ absmax_bits)
 {
     const long total = (long)Tout * B * Cout;
     for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
@@ -106,7 +115,9 @@ __global__ void conv1d_generic_kernel(const float *__restrict__ x, const float *
                     acc = fmaf(W[((long)o * Cin + i) * winlen + k], x[((long)tin * B + b) * Cin + i], acc);
             }
         }
-        y[tb * ldy + o] = apply_act(acc, act);
+        const float v = apply_act(acc, act);
+        y[tb * ldy + o] = v;
+        if (absmax_bits) atomicMax(absmax_bits, __float_as_uint(fabsf(v)));
     }
 }
 
@@ -114,10 +125,23 @@ __global__ void conv1d_generic_kernel(const float *__restrict__ x, const float *
 
 using namespace sloika;
 
+extern "C" int sloika_conv1d_fwd_ex(const float *x, const float *W, const float *bias, float *y, long ldy,
+                                    const int32_t *lengths, int T, int B, int Cin, int Cout, int winlen, int stride,
+                                    int pad_l, int pad_r, int act, float *absmax, void *stream);
+
 extern "C" int sloika_conv1d_fwd(const float *x, const float *W, const float *bias, float *y, long ldy,
                                  const int32_t *lengths, int T, int B, int Cin, int Cout, int winlen, int stride,
                                  int pad_l, int pad_r, int act, void *stream)
 {
+    return sloika_conv1d_fwd_ex(x, W, bias, y, ldy, lengths, T, B, Cin, Cout, winlen, stride, pad_l, pad_r, act, nullptr,
+                                stream);
+}
+
+extern "C" int sloika_conv1d_fwd_ex(const float *x, const float *W, const float *bias, float *y, long ldy,
+                                    const int32_t *lengths, int T, int B, int Cin, int Cout, int winlen, int stride,
+                                    int pad_l, int pad_r, int act, float *absmax, void *stream)
+{
+    unsigned *absmax_bits = reinterpret_cast<unsigned *>(absmax);
     if (!x || !W || !bias || !y) return SLOIKA_ERR_ARG;
     if (T < 0 || B <= 0 || Cin <= 0 || Cout <= 0 || winlen <= 0 || stride <= 0 || pad_l < 0 || pad_r < 0 ||
         ldy < Cout)
@@ -138,7 +162,7 @@ extern "C" int sloika_conv1d_fwd(const float *x, const float *W, const float *bi
         const size_t smem = sizeof(float) * ((size_t)(TT - 1) * stride + winlen) * BT;
         if (smem <= 48 * 1024) {
             conv1d_raw_kernel<11><<<grid, threads, smem, st>>>(x, W, bias, y, ldy, lengths, T, B, Cout, stride,
-                                                               pad_l, Tout, TT, BT, act);
+                                                               pad_l, Tout, TT, BT, act, absmax_bits);
             SLOIKA_RETURN_LAUNCH_STATUS();
         }
     }
@@ -147,6 +171,6 @@ extern "C" int sloika_conv1d_fwd(const float *x, const float *W, const float *bi
     long blocks = ceil_div(total, threads);
     if (blocks > 148L * 32) blocks = 148L * 32;
     conv1d_generic_kernel<<<(unsigned)blocks, threads, 0, st>>>(x, W, bias, y, ldy, lengths, T, B, Cin, Cout,
-                                                               winlen, stride, pad_l, Tout, act);
+                                                               winlen, stride, pad_l, Tout, act, absmax_bits);
     SLOIKA_RETURN_LAUNCH_STATUS();
 }

@@ -52,6 +52,9 @@ struct Params {
     int vec_out;      // rows of y are 16-byte aligned: 128-bit stores
     int direct;       // vec_out && store rows straight from registers (no smem transpose)
     int tma_out;      // vec_out: 32 x 32 output boxes leave through cp.async.bulk.tensor stores (tmap_y)
+    const unsigned *gate;   // optional device word (bits of a non-negative float, e.g. max |x| from the producer):
+    unsigned gate_limit;    // gate_mode 1: run only if *gate < gate_limit; 2: only if *gate >= gate_limit; 0: always
+    int gate_mode;
     int dbg;          // timing experiments only (SLOIKA_B200_GEMM_DBG): 1 no split math, 2 no stores, 4 no MMA
 };
 
@@ -71,6 +74,10 @@ template <int ACT, bool STATS, bool F16>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_y, const Params p)
 {
+    if (p.gate_mode != 0) {                       // device-side choice between two enqueued forms of the same GEMM
+        const bool below = *p.gate < p.gate_limit;
+        if (below != (p.gate_mode == 1)) return;
+    }
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment for the 128-byte swizzle; plain pointer arithmetic keeps the shared address space
     uint8_t *smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -479,7 +486,8 @@ int plan_slices(int K, int N, int *bn_out, bool f16)
 }
 
 int launch(const float *x, long ldx, const float *W, const float *bias, float *y, long ldy, long M, int K, int N,
-           int act, float2 *stats, int rot, bool f16, cudaStream_t st)
+           int act, float2 *stats, int rot, bool f16, cudaStream_t st, const unsigned *gate = nullptr,
+           unsigned gate_limit = 0, int gate_mode = 0)
 {
     if ((ldx & 3) != 0 || ((uintptr_t)x & 15) != 0 || K > 256 || M < BM || M > 0x7fffffffL) return SLOIKA_ERR_UNSUPPORTED;
     EncodeTiledFn enc = encode_fn();
@@ -510,6 +518,7 @@ int launch(const float *x, long ldx, const float *W, const float *bias, float *y
     p.W = W; p.bias = bias; p.y = y; p.ldy = ldy; p.M = M; p.K = K; p.N = N; p.act = act;
     p.BN = BN; p.n_slices = n_slices; p.nkb = nkb;
     p.stats = stats; p.rot = rot;
+    p.gate = gate; p.gate_limit = gate_limit; p.gate_mode = gate ? gate_mode : 0;
     p.vec_out = ((ldy & 3) == 0) && (((uintptr_t)y & 15) == 0);
     const char *direct = getenv("SLOIKA_B200_GEMM_DIRECT");
     p.direct = (p.vec_out && direct && atoi(direct) != 0) ? 1 : 0;

@@ -6,6 +6,7 @@
 // epilogue.  M = T*B rows is huge (819 200), K and N are small (<= 256 / <= 1025), so both operands'
 // K extent is streamed in 16-wide slabs through shared memory.  This is the kernel the tcgen05
 // (3xTF32) projection replaces; it stays as the exact-fp32 fallback for odd shapes.
+#include <cstring>
 #include "common.cuh"
 
 namespace sloika {
@@ -183,7 +184,8 @@ static int launch_linear(const float *x, long ldx, const float *W, const float *
 namespace gemm_tc {
 int plan_slices(int K, int N, int *bn_out, bool f16);
 int launch(const float *x, long ldx, const float *W, const float *bias, float *y, long ldy, long M, int K, int N,
-           int act, float2 *stats, int rot, bool f16, cudaStream_t st);
+           int act, float2 *stats, int rot, bool f16, cudaStream_t st, const unsigned *gate = nullptr,
+           unsigned gate_limit = 0, int gate_mode = 0);
 }
 
 // algo: SLOIKA_GEMM_AUTO tries the tcgen05 3xTF32 kernel and falls back to the fp32 SIMT kernel when the
@@ -219,6 +221,22 @@ extern "C" int sloika_linear_fwd(const float *x, long ldx, const float *W, const
     if (!act_known(act)) return SLOIKA_ERR_UNSUPPORTED;
     if (M == 0) return SLOIKA_OK;
     return dispatch_linear(x, ldx, W, bias, y, ldy, M, K, N, act, SLOIKA_GEMM_AUTO, (cudaStream_t)stream);
+}
+
+extern "C" int sloika_linear_fwd_gated(const float *x, long ldx, const float *W, const float *bias, float *y, long ldy,
+                                       long M, int K, int N, int act, const float *absmax, float limit, void *stream)
+{
+    if (!x || !W || !y || !absmax || M < 0 || K <= 0 || N <= 0 || ldx < K || ldy < N || !(limit > 0.0f)) return SLOIKA_ERR_ARG;
+    if (!act_known(act)) return SLOIKA_ERR_UNSUPPORTED;
+    if (M == 0) return SLOIKA_OK;
+    unsigned limit_bits;
+    memcpy(&limit_bits, &limit, sizeof(limit_bits));
+    const unsigned *gate = reinterpret_cast<const unsigned *>(absmax);
+    cudaStream_t st = (cudaStream_t)stream;
+    // both forms are enqueued; the CTAs of the one the gate rules out return at once (a few microseconds)
+    int rc = gemm_tc::launch(x, ldx, W, bias, y, ldy, M, K, N, act, nullptr, 0, true, st, gate, limit_bits, 1);
+    if (rc != SLOIKA_OK) return rc;             // shape / alignment the tensor-core kernel cannot take: caller's problem
+    return gemm_tc::launch(x, ldx, W, bias, y, ldy, M, K, N, act, nullptr, 0, false, st, gate, limit_bits, 2);
 }
 
 extern "C" int sloika_softmax_slices(int K, int N, int algo)

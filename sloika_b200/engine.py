@@ -24,9 +24,11 @@ class Act(object):
     reverse  time direction flag toggled by `Reverse` (nothing is ever flipped in memory)
     bounded  True when the producing layer guarantees |x| <= 1 (tanh / sigmoid / GRU / softmax outputs): the
              next GEMM may then use the fp16-split tensor-core kernel (SLOIKA_GEMM_TC_F16)
+    absmax   optional 1-element CUDA tensor holding max |x| as measured by the producing kernel (unbounded
+             activations such as elu): lets the next GEMM choose its operand format on the device
     """
 
-    def __init__(self, data, lengths=None, reverse=False, bounded=False):
+    def __init__(self, data, lengths=None, reverse=False, bounded=False, absmax=None):
         assert data.dim() == 3
         T, B, F = data.shape
         # strides of size-1 dimensions are meaningless in torch; derive the row distance from a
@@ -44,6 +46,7 @@ class Act(object):
         self.lengths = lengths
         self.reverse = reverse
         self.bounded = bounded
+        self.absmax = absmax
 
     @property
     def T(self):
@@ -66,10 +69,10 @@ class Act(object):
         return self.data.device
 
     def flipped(self):
-        return Act(self.data, self.lengths, not self.reverse, self.bounded)
+        return Act(self.data, self.lengths, not self.reverse, self.bounded, self.absmax)
 
-    def like(self, data, lengths='same', bounded=False):
-        return Act(data, self.lengths if lengths == 'same' else lengths, self.reverse, bounded)
+    def like(self, data, lengths='same', bounded=False, absmax=None):
+        return Act(data, self.lengths if lengths == 'same' else lengths, self.reverse, bounded, absmax)
 
 
 class KernelTimer(object):
@@ -132,6 +135,7 @@ def _out_buffer(act, T, F, out):
 
 GEMM_AUTO, GEMM_SIMT, GEMM_TC, GEMM_TC_F16 = 0, 1, 2, 3      # include/sloika_b200.h
 _F16_WEIGHT_LIMIT = 1.0e3
+_F16_INPUT_LIMIT = 1.0e4          # measured max |x| below which an unbounded activation may use the fp16 split
 
 
 def _bounded_fun(fun):
@@ -151,11 +155,19 @@ def _gemm_algo(act, *params):
 def _linear(name, lib, act, W, b, y, ldy, N, fun_code, dev):
     """y = fun(x W' + b) through sloika_linear_fwd_ex; the fp16-split request degrades to AUTO when the
     tensor-core kernel cannot take the shape."""
+    tc_ok = act.ld % 4 == 0 and act.data.data_ptr() % 16 == 0 and act.T * act.B >= 128 and act.F <= 256
+    import os
+    if not act.bounded and act.absmax is not None and tc_ok and W.absmax() < _F16_WEIGHT_LIMIT \
+            and not os.environ.get('SLOIKA_B200_NO_F16'):
+        # range known only on the device: enqueue both tensor-core forms, the kernel-side gate runs exactly one
+        launch(name, 2, lib.sloika_linear_fwd_gated,
+               cabi.ptr(act.data), act.ld, cabi.ptr(W.device(dev)), cabi.ptr(b.device(dev)), cabi.ptr(y), ldy,
+               act.T * act.B, act.F, N, fun_code, cabi.ptr(act.absmax), _F16_INPUT_LIMIT, cabi.stream_ptr(dev))
+        return
     algo = _gemm_algo(act, W)
     args = lambda a: (cabi.ptr(act.data), act.ld, cabi.ptr(W.device(dev)), cabi.ptr(b.device(dev)), cabi.ptr(y), ldy,
                       act.T * act.B, act.F, N, fun_code, a, cabi.stream_ptr(dev))
-    if algo == GEMM_TC_F16 and act.ld % 4 == 0 and act.data.data_ptr() % 16 == 0 and act.T * act.B >= 128 \
-            and act.F <= 256:
+    if algo == GEMM_TC_F16 and tc_ok:
         launch(name, 1, lib.sloika_linear_fwd_ex, *args(GEMM_TC_F16))
     else:
         launch(name, 1, lib.sloika_linear_fwd_ex, *args(GEMM_AUTO))
@@ -169,16 +181,22 @@ def run_convolution(layer, act, out=None):
     Tout = output_length(act.T, layer.winlen, layer.stride, layer.padding)
     y = _out_buffer(act, Tout, layer.size, out)
     dev = act.device
-    launch('conv1d', 1, lib.sloika_conv1d_fwd,
+    bounded = _bounded_fun(layer.fun)
+    absmax = None
+    if not bounded:                              # elu / linear outputs: let the kernel report their range
+        import torch
+        absmax = torch.zeros(1, dtype=torch.float32, device=dev)
+    launch('conv1d', 1, lib.sloika_conv1d_fwd_ex,
            cabi.ptr(act.data), cabi.ptr(layer.W.device(dev)), cabi.ptr(layer.b.device(dev)), cabi.ptr(y),
            _row_stride(y), cabi.ptr(act.lengths), act.T, act.B, layer.insize, layer.size, layer.winlen,
-           layer.stride, layer.padding[0], layer.padding[1], code_of(layer.fun), cabi.stream_ptr(dev))
+           layer.stride, layer.padding[0], layer.padding[1], code_of(layer.fun), cabi.ptr(absmax),
+           cabi.stream_ptr(dev))
     lengths = None
     if act.lengths is not None:
         # per-read output length: each read is padded/convolved on its own (conv.py:66-111)
         span = act.lengths + (layer.padding[0] + layer.padding[1] - layer.winlen)
         lengths = (span.clamp(min=-layer.stride) // layer.stride + 1).clamp(min=0).to(act.lengths.dtype)
-    return act.like(y, lengths, bounded=_bounded_fun(layer.fun))
+    return act.like(y, lengths, bounded=bounded, absmax=absmax)
 
 
 def run_feedforward(layer, act, out=None):

@@ -76,7 +76,15 @@ def test_posteriors_of_real_read_within_bound(calls, golden_dir, pretrained):
     sig = signals[NAMES.index('read7')]
     post = net(sig[:, None, None])
     ref = forward_ref.run(pretrained.json(params=True), sig[:, None, None])
-    assert np.abs(post - ref).max() < 1e-4
+    # Whole reads: thousands of recurrent steps amplify float32 round-off, and two float32 implementations that sum in
+    # different orders drift apart by about as much as either drifts from exact arithmetic.  On this read the NumPy
+    # float32 oracle itself is 4.6e-4 (max abs) away from its float64 twin (tools/accuracy_probe.py,
+    # profiles/r1_accuracy_probe.txt).  Stated bounds: 2e-4 against the float32 oracle, and no further from the
+    # float64 result than 1.5x the float32 oracle's own distance (chunk-sized inputs keep the 1e-4 / 2e-5 bounds of
+    # test_kernels_gpu.py).
+    ref64 = forward_ref.run(pretrained.json(params=True), sig[:, None, None], np.float64)
+    assert np.abs(post - ref).max() < 2e-4
+    assert np.abs(post - ref64).max() < 1.5 * np.abs(ref - ref64).max() + 2e-5
 
 
 def test_decode_post_dropin(calls, read_basecalls, pretrained):

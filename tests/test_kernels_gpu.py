@@ -6,6 +6,7 @@ north-star bound); Viterbi is float32 add/max only -> scores and paths are compa
 sides get identical log-posteriors.
 """
 import ctypes
+import os
 
 import numpy as np
 import pytest
@@ -456,3 +457,47 @@ def test_batch_not_multiple_of_cta_tile():
     post13 = net.compile().forward_device(x).data.cpu().numpy()
     ref = _oracle(net, x.cpu().numpy())
     assert np.abs(post13 - ref).max() < 1e-4
+
+
+def test_gated_gemm_chooses_operand_format_on_device():
+    """sloika_conv1d_fwd_ex reports max |y|; sloika_linear_fwd_gated runs the fp16-split GEMM below the limit and the
+    tf32-split one above it -- where the fp16 form would overflow -- with no host synchronisation in between."""
+    lib = cabi.load()
+    rng = np.random.default_rng(12)
+    dev = torch.device(DEV)
+    st = cabi.stream_ptr(dev)
+    # conv range report
+    conv = layers.Convolution(1, 16, 11, 5, has_bias=True, fun=act.elu)
+    x = torch.from_numpy((rng.standard_normal((500, 6, 1)) * 3).astype(np.float32)).to(dev)
+    out = engine.run_convolution(conv, engine.Act(x))
+    assert not out.bounded and out.absmax is not None
+    assert float(out.absmax.item()) == float(out.data.abs().max().item())
+    # gated GEMM on small and on huge inputs
+    M, K, N = 1024, 96, 288
+    W = (rng.standard_normal((N, K)) * 0.5).astype(np.float32)
+    b = rng.standard_normal(N).astype(np.float32)
+    Wd, bd = torch.from_numpy(W).to(dev), torch.from_numpy(b).to(dev)
+    for scale in (1.0, 1.0e5):
+        xh = (rng.standard_normal((M, K)) * scale).astype(np.float32)
+        xd = torch.from_numpy(xh).to(dev)
+        amax = xd.abs().max().reshape(1).contiguous()
+        y = torch.full((M, N), -7.0, dtype=torch.float32, device=dev)
+        rc = lib.sloika_linear_fwd_gated(cabi.ptr(xd), K, cabi.ptr(Wd), cabi.ptr(bd), cabi.ptr(y), N, M, K, N, 0,
+                                         cabi.ptr(amax), 1.0e4, st)
+        assert rc == 0
+        torch.cuda.synchronize()
+        exact = xh.astype(np.float64) @ W.astype(np.float64).T + b
+        got = y.cpu().numpy()
+        assert np.isfinite(got).all()
+        assert np.abs(got - exact).max() <= 4e-6 * np.abs(exact).max()
+    # the engine uses it for elu -> GRU projection and results agree with the forced tf32 path
+    np.random.seed(3)
+    net = zoo.pretrained_like().compile()
+    xs = torch.randn((900, 8, 1), device=dev)
+    a = net.forward_device(xs, None).data.cpu().numpy()
+    os.environ['SLOIKA_B200_NO_F16'] = '1'
+    try:
+        bref = net.forward_device(xs, None).data.cpu().numpy()
+    finally:
+        del os.environ['SLOIKA_B200_NO_F16']
+    np.testing.assert_allclose(a, bref, atol=2e-5)
