@@ -195,7 +195,7 @@ template <int MODE>
 __global__ void __launch_bounds__(256, 7)      // 7 CTAs/SM: all 1024 reads of a batch resident in one wave on 148 SMs
 viterbi_k1024_kernel(const float *__restrict__ post, long ld_t, long ld_b, const float2 *__restrict__ stats, int n_slices,
                      const int32_t *__restrict__ lengths, int T, int B, float skip_pen, float c0, float c1,
-                     float skip_below, uint8_t *__restrict__ tb, int32_t *__restrict__ path_out,
+                     uint8_t *__restrict__ tb, int32_t *__restrict__ path_out,
                      int32_t *__restrict__ path_len, float *__restrict__ score_out)
 {
     constexpr int K = 1024, RS = 256, RK = 64;
@@ -440,14 +440,6 @@ viterbi_k1024_kernel(const float *__restrict__ post, long ld_t, long ld_b, const
     }
 }
 
-// d below which p = exp(d)/S (<= exp(d), S >= 1) cannot change min_prob + (1-min_prob)*p in float32
-static float logits_skip_threshold(float c0, float c1)
-{
-    if (!(c0 > 0.0f) || !(c1 > 0.0f)) return -INFINITY;
-    const float half_ulp = 0.5f * (nextafterf(c0, 2.0f * c0) - c0);
-    return logf(half_ulp / c1) - 0.5f;
-}
-
 static bool ipow_ok(int nbase, int klen, long *K)
 {
     long k = 1;
@@ -494,10 +486,10 @@ extern "C" int sloika_viterbi_fwd(const float *post, long ld_t, long ld_b, const
     if (nbase == 4 && K == 1024 && !getenv("SLOIKA_B200_VITERBI_GENERIC")) {
         if (mode == SLOIKA_VIT_POST)
             viterbi_k1024_kernel<IN_POST><<<B, 256, 0, st>>>(post, ld_t, ld_b, nullptr, 0, lengths, T, B, sp, c0, c1,
-                                                              -INFINITY, (uint8_t *)tb_ws, path_out, path_len, score_out);
+                                                              (uint8_t *)tb_ws, path_out, path_len, score_out);
         else
             viterbi_k1024_kernel<IN_LOG><<<B, 256, 0, st>>>(post, ld_t, ld_b, nullptr, 0, lengths, T, B, sp, c0, c1,
-                                                             -INFINITY, (uint8_t *)tb_ws, path_out, path_len, score_out);
+                                                             (uint8_t *)tb_ws, path_out, path_len, score_out);
         SLOIKA_RETURN_LAUNCH_STATUS();
     }
     if (nbase == 4) {
@@ -531,6 +523,6 @@ extern "C" int sloika_viterbi_logits_fwd(const float *logits, long ld_t, long ld
     const float c0 = (float)min_prob + 1e-10f, c1 = (float)(1.0 - min_prob), sp = (float)skip_pen;
     viterbi_k1024_kernel<IN_LOGITS><<<B, 256, 0, (cudaStream_t)stream>>>(
         logits, ld_t, ld_b, reinterpret_cast<const float2 *>(stats), n_slices, lengths, T, B, sp, c0, c1,
-        logits_skip_threshold(c0, c1), (uint8_t *)tb_ws, path_out, path_len, score_out);
+        (uint8_t *)tb_ws, path_out, path_len, score_out);
     SLOIKA_RETURN_LAUNCH_STATUS();
 }
