@@ -501,3 +501,37 @@ def test_gated_gemm_chooses_operand_format_on_device():
     finally:
         del os.environ['SLOIKA_B200_NO_F16']
     np.testing.assert_allclose(a, bref, atol=2e-5)
+
+
+@pytest.mark.parametrize('I,H,T,B,reverse,ragged', [(96, 96, 200, 16, False, False), (40, 110, 60, 5, True, True),
+                                                    (24, 64, 50, 9, False, True), (128, 144, 40, 8, True, False)])
+def test_gru_one_call_entry_point(I, H, T, B, reverse, ragged):
+    """`sloika_gru_fwd` (projection + recurrence behind one C call, dense vI workspace -- the form a foreign caller
+    binds) against the oracle; covers the dense, unaligned vI pitch (3H not a multiple of 4) of the recurrence."""
+    lib = cabi.load()
+    np.random.seed(I + H + T)
+    g = layers.Gru(I, H, init=_init(), has_bias=True)
+    g.sW.set_value(g.sW.get_value() * 4)
+    x = np.tanh(np.random.standard_normal((T, B, I))).astype(np.float32)
+    lengths = np.random.randint(1, T + 1, size=B).astype(np.int32) if ragged else None
+    dev = torch.device(DEV)
+    xd = torch.from_numpy(x).to(dev)
+    y = torch.full((T, B, H), 7.0, dtype=torch.float32, device=dev)
+    nbytes = lib.sloika_gru_workspace_bytes(T, B, H)
+    assert nbytes == T * B * 3 * H * 4
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    ld = None if lengths is None else torch.from_numpy(lengths).to(dev)
+    args = [cabi.ptr(xd), I, cabi.ptr(g.iW.device(dev)), cabi.ptr(g.sW.device(dev)), cabi.ptr(g.sW2.device(dev)),
+            cabi.ptr(g.b.device(dev)), cabi.ptr(y), H, cabi.ptr(ws), nbytes, cabi.ptr(ld), T, B, I, H,
+            1 if reverse else 0, 1, 2, cabi.stream_ptr(dev)]
+    assert lib.sloika_gru_fwd(*args) == 0
+    torch.cuda.synchronize()
+    got = y.cpu().numpy()
+    layer = layers.Reverse(g) if reverse else g
+    for b in range(B):
+        n = T if lengths is None else int(lengths[b])
+        ref = _oracle(layer, x[:n, b:b + 1])
+        assert np.abs(got[:n, b] - ref[:, 0]).max() < 5e-5, b
+        assert np.all(got[n:, b] == 0)
+    args[9] = nbytes - 4                                       # workspace too small
+    assert lib.sloika_gru_fwd(*args) == -3
