@@ -209,6 +209,23 @@ int sloika_path_to_bases_fwd(const int32_t *path, long ld_path, const int32_t *p
                              int always_move, const char *alphabet, char *out, long ld_out, int32_t *out_len,
                              void *stream);
 
+/*
+ * Raw-signal pre-processing: what basecall.raw_worker does to a read before the network --
+ * sloika/basecall.py:111-118 -- batch.trim_open_pore (sloika/batch.py:194-220), util.trim_array (util.py:94-99),
+ * (signal - median) / mad in float64 (sloika/maths.py:4-45), cast to float32 -- batched, one CTA per read, exact order
+ * statistics: the float32 result is bit-identical to the NumPy path.
+ *   signals: the reads' float64 samples back to back; offsets long [B+1]; max_len >= longest read
+ *   window: trim_open_pore's window (100 in the reference; 2..128), var_method 'mad'
+ *   ws: sloika_prepare_workspace_bytes(max_len, B, window) bytes
+ *   out: float32 [Tmax][ld_t] time-major batch, column b = read b, zero padded (Tmax >= max_len keeps everything)
+ *   out_len int32 [B]: samples kept; 0 = nothing left after trimming ("Read too short"); -1 = no window exceeds the
+ *            threshold (the reference raises there: empty `is_read`)
+ */
+size_t sloika_prepare_workspace_bytes(long max_len, int B, int window);
+int sloika_prepare_signal_fwd(const double *signals, const long *offsets, int B, long max_len, int trim_start,
+                              int trim_end, double open_pore_fraction, int window, void *ws, size_t ws_bytes,
+                              float *out, long ld_t, int Tmax, int32_t *out_len, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -10,7 +10,7 @@ import sys
 
 import numpy as np
 
-from sloika_b200 import bio, decode, util
+from sloika_b200 import bio, cabi, decode, util
 from sloika_b200.config import sloika_dtype
 from sloika_b200.maths import mad
 from sloika_b200.variables import nstate, DEFAULT_ALPHABET
@@ -52,6 +52,46 @@ def prepare_signal(signal, trim, open_pore_fraction):
     return ((signal - np.median(signal)) / mad(signal)).astype(sloika_dtype)
 
 
+def prepare_signals_device(signals, trim=(200, 10), open_pore_fraction=0, window_size=100, device=None):
+    """`prepare_signal` for a batch of raw reads on the device (`basecall.py:111-118` per read): open-pore trim, end
+    trim and median / MAD normalisation in float64 with exact order statistics, written straight into the padded
+    time-major batch the network consumes.  Bit-identical to the NumPy path.
+
+    :param signals: list of 1-D raw signals (any float / int dtype; used as float64 like the reference)
+    :returns: (x `[Tmax, B, 1]` float32 CUDA tensor, lengths int32 CUDA tensor `[B]`, lengths as a NumPy array);
+        length 0 = nothing left after trimming, -1 = the reference's `trim_open_pore` would raise (no window
+        stands out: `is_read` empty)
+    """
+    import torch
+    lib = cabi.load()
+    dev = device if device is not None else (calc_post.device if calc_post is not None else
+                                             torch.device('cuda', torch.cuda.current_device()))
+    B = len(signals)
+    lens = np.array([len(s) for s in signals], dtype=np.int64)
+    offsets = np.zeros(B + 1, dtype=np.int64)
+    np.cumsum(lens, out=offsets[1:])
+    flat = torch.empty(int(offsets[-1]), dtype=torch.float64).pin_memory()
+    flat_np = flat.numpy()
+    for b, s in enumerate(signals):
+        flat_np[offsets[b]:offsets[b + 1]] = s
+    max_len = int(lens.max()) if B else 0
+    with torch.cuda.device(dev):
+        sig_d = flat.to(dev, non_blocking=True)
+        off_d = torch.from_numpy(offsets).to(dev)
+        nbytes = lib.sloika_prepare_workspace_bytes(max_len, B, window_size)
+        ws = torch.empty(max(nbytes, 8), dtype=torch.uint8, device=dev)
+        x = torch.empty((max(max_len, 1), B), dtype=torch.float32, device=dev)
+        out_len = torch.empty(B, dtype=torch.int32, device=dev)
+        from sloika_b200.engine import launch
+        launch('prepare_signal', 1, lib.sloika_prepare_signal_fwd,
+               cabi.ptr(sig_d), cabi.ptr(off_d), B, max_len, int(trim[0]), int(trim[1]), float(open_pore_fraction),
+               int(window_size), cabi.ptr(ws), nbytes, cabi.ptr(x), B, max(max_len, 1), cabi.ptr(out_len),
+               cabi.stream_ptr(dev))
+        lens_h = out_len.cpu().numpy()
+    T = max(int(lens_h.max()), 1)
+    return x[:T].unsqueeze(2), out_len.clamp(min=0), lens_h
+
+
 class CalledPath(list):
     """A best path (list of k-mer states) that also carries the base sequence assembled on the device
     (`decode.paths_to_sequences`); `SeqPrinter.write` uses it instead of spelling the k-mers on the host."""
@@ -81,7 +121,16 @@ def basecall_signals(signals, kmer_len=5, min_prob=1e-5, skip=0.0, nbase=4, netw
     for b, s in enumerate(signals):
         host[:len(s), b] = torch.from_numpy(np.ascontiguousarray(s, dtype=np.float32))
     x = host.to(dev, non_blocking=True).unsqueeze(2)
-    out = net.forward_device(x, torch.from_numpy(lens).to(dev), fused_decode=(kmer_len == 5 and nbase == 4))
+    return basecall_prepared(x, torch.from_numpy(lens).to(dev), kmer_len, min_prob, skip, nbase, net, assemble)
+
+
+def basecall_prepared(x, lengths, kmer_len=5, min_prob=1e-5, skip=0.0, nbase=4, network=None, assemble=None):
+    """Forward + Viterbi for a padded device batch `x [Tmax, B, 1]` with per-read `lengths` (int32 CUDA tensor), e.g.
+    the output of `prepare_signals_device`.  Same results as `basecall_signals`."""
+    net = network if network is not None else calc_post
+    if net is None:
+        raise RuntimeError("init_worker() has not been called")
+    out = net.forward_device(x, lengths, fused_decode=(kmer_len == 5 and nbase == 4))
     if assemble is None:
         score, paths = decode.viterbi_batch(out, None, klen=kmer_len, skip_pen=skip, min_prob=min_prob, nbase=nbase)
         return list(zip(score.tolist(), paths))
@@ -211,7 +260,8 @@ def raw_batch(fast5_file_names, trim=(200, 10), open_pore_fraction=0, kmer_len=5
               bad=True, min_prob=1e-5, alphabet=DEFAULT_ALPHABET, skip=0.0, trans=None):
     """`raw_worker` over many files in one device batch; same result tuples, None for bad reads."""
     assert transducer, "only transducer models are supported"
-    names, signals, slots = [], [], []
+    import os
+    names, raws, slots = [], [], []
     results = [None] * len(fast5_file_names)
     for i, fn in enumerate(fast5_file_names):
         try:
@@ -219,17 +269,37 @@ def raw_batch(fast5_file_names, trim=(200, 10), open_pore_fraction=0, kmer_len=5
         except Exception as e:
             sys.stderr.write("Error getting raw data for file {}\n{!r}\n".format(fn, e))
             continue
-        sig = prepare_signal(signal, trim, open_pore_fraction)
-        if sig is None:
-            sys.stderr.write("Read too short in file {}\n".format(fn))
-            continue
         names.append(sn)
-        signals.append(sig)
+        raws.append(signal)
         slots.append(i)
-    calls = basecall_signals(signals, kmer_len=kmer_len, min_prob=min_prob, skip=skip, nbase=len(alphabet),
-                             assemble=(alphabet, transducer))
-    for i, sn, sig, (score, path) in zip(slots, names, signals, calls):
-        results[i] = (sn, np.float32(score), path, len(sig))
+    if not raws:
+        return results
+    if os.environ.get('SLOIKA_B200_HOST_PREP'):
+        # NumPy pre-processing, one read at a time (the reference's own path; kept for A/B checks)
+        keep, signals = [], []
+        for k, signal in enumerate(raws):
+            sig = prepare_signal(signal, trim, open_pore_fraction)
+            if sig is None:
+                sys.stderr.write("Read too short in file {}\n".format(fast5_file_names[slots[k]]))
+                continue
+            keep.append(k)
+            signals.append(sig)
+        calls = basecall_signals(signals, kmer_len=kmer_len, min_prob=min_prob, skip=skip, nbase=len(alphabet),
+                                 assemble=(alphabet, transducer))
+        for k, sig, (score, path) in zip(keep, signals, calls):
+            results[slots[k]] = (names[k], np.float32(score), path, len(sig))
+        return results
+    # trimming and normalisation on the device, for the whole batch at once
+    x, lens_d, lens_h = prepare_signals_device(raws, trim, open_pore_fraction)
+    if (lens_h < 0).any():
+        raise ValueError("zero-size array to reduction operation minimum which has no identity")   # trim_open_pore
+    calls = basecall_prepared(x, lens_d, kmer_len=kmer_len, min_prob=min_prob, skip=skip, nbase=len(alphabet),
+                              assemble=(alphabet, transducer))
+    for k, (score, path) in enumerate(calls):
+        if lens_h[k] == 0:
+            sys.stderr.write("Read too short in file {}\n".format(fast5_file_names[slots[k]]))
+            continue
+        results[slots[k]] = (names[k], np.float32(score), path, int(lens_h[k]))
     return results
 
 

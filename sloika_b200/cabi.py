@@ -40,6 +40,8 @@ EXPORTS = {
     'sloika_remap_workspace_bytes': (_z, [_i, _i, _i]),
     'sloika_remap_fwd': (_i, [_p, _l, _l, _p, _i, _i, _i, _p, _l, _p, _i, _d, _i, _p, _p, _l, _i, _p, _z, _p, _p, _p]),
     'sloika_slip_update_fwd': (_i, [_p, _i, ctypes.c_float, _p, _p, _p]),
+    'sloika_prepare_workspace_bytes': (_z, [_l, _i, _i]),
+    'sloika_prepare_signal_fwd': (_i, [_p, _p, _i, _l, _i, _i, _d, _i, _p, _z, _p, _l, _i, _p, _p]),
     'sloika_path_to_bases_fwd': (_i, [_p, _l, _p, _i, _i, _i, _i, _p, _p, _l, _p, _p]),
 }
 

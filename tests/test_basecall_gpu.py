@@ -165,3 +165,72 @@ def test_chunk_stream_equals_per_batch_calls():
         for b in range(len(l1)):
             assert np.array_equal(paths[b, :l1[b]], p1[b, :l1[b]])
     assert list(basecall.basecall_chunk_stream(iter([]), network=net)) == []
+
+
+# ------------------------------------------------------------------ row f2: pre-processing on the device
+def _host_prep(signals, trim, frac):
+    out = []
+    for s in signals:
+        try:
+            out.append(basecall.prepare_signal(np.asarray(s, dtype=np.float64), trim, frac))
+        except (ValueError, IndexError):              # empty `is_read` / no complete window: NumPy raises
+            out.append('raises')
+    return out
+
+
+def _check_prep(signals, trim=(200, 10), frac=0):
+    x, lens_d, lens_h = basecall.prepare_signals_device(signals, trim, frac, device=torch.device('cuda:0'))
+    xh = x.cpu().numpy()[:, :, 0]
+    want = _host_prep(signals, trim, frac)
+    for b, w in enumerate(want):
+        if isinstance(w, str):
+            assert lens_h[b] == -1
+        elif w is None:
+            assert lens_h[b] == 0
+        else:
+            assert lens_h[b] == len(w), (b, lens_h[b], len(w))
+            assert np.array_equal(xh[:len(w), b], w), b                 # bit-identical float32
+            assert np.all(xh[len(w):, b] == 0)
+    assert np.array_equal(lens_d.cpu().numpy(), np.maximum(lens_h, 0))
+
+
+def test_device_preprocessing_is_bit_identical_to_numpy(reads_daq):
+    read_daq = reads_daq
+    """trim_open_pore + trim_array + (x - median) / mad on the device (csrc/prepare.cu) against the NumPy path that
+    mirrors the reference (`basecall.prepare_signal`, pinned by tests/test_host.py): same lengths, same float32 bits,
+    on the bundled reads and on synthetic signals with ties, odd / even counts and degenerate cases."""
+    names = ['read{}'.format(i) for i in range(1, 9)]
+    real = [scaled_signal(read_daq, n) for n in names]
+    _check_prep(real)
+    _check_prep(real, trim=(0, 0), frac=0.3)
+    rng = np.random.default_rng(17)
+    synth = [rng.standard_normal(n) * 5 + 90 for n in (1000, 1001, 2550, 100, 399, 12345)]
+    synth.append(np.round(rng.standard_normal(3000) * 3) + 100)        # heavy ties in every window and overall
+    synth.append(np.concatenate([np.full(500, 200.0), rng.standard_normal(700) * 8 + 80, np.full(400, 200.0)]))   # open pore
+    synth.append(np.full(1000, 50.0))                                   # constant: the reference raises
+    synth.append(rng.standard_normal(250) + 10)                         # shorter than the end trims
+    synth.append(rng.standard_normal(60))                               # shorter than one window: raises
+    _check_prep(synth)
+    _check_prep(synth, trim=(50, 5), frac=0.5)
+    _check_prep(synth, trim=(0, 0), frac=0.07)
+
+
+def test_raw_batch_with_device_preprocessing_equals_host_preprocessing(tmp_path, reads_daq, pretrained, monkeypatch):
+    read_daq = reads_daq
+    from h5write import write_fast5
+    files = []
+    for i in (3, 7, 8):
+        name = 'read{}'.format(i)
+        offset, rng_, digi = read_daq[name + '_scaling']
+        fn = str(tmp_path / (name + '.fast5'))
+        write_fast5(fn, read_daq[name], float(offset), float(rng_), float(digi), read_number=i)
+        files.append(fn)
+    basecall.calc_post = pretrained.compile()
+    try:
+        dev_res = basecall.raw_batch(files)
+        monkeypatch.setenv('SLOIKA_B200_HOST_PREP', '1')
+        host_res = basecall.raw_batch(files)
+    finally:
+        basecall.calc_post = None
+    for a, b in zip(dev_res, host_res):
+        assert a[0] == b[0] and a[3] == b[3] and list(a[2]) == list(b[2]) and a[1] == b[1]
