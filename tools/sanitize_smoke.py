@@ -10,7 +10,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
 
-from sloika_b200 import decode, transducer, zoo
+from sloika_b200 import basecall, decode, transducer, zoo
 
 DEV = torch.device('cuda:0')
 
@@ -39,6 +39,10 @@ def main():
         lt = torch.log_softmax(torch.randn((T, B, S), device=DEV), dim=-1)
         seqs = [rng.integers(1, S, size=int(n)) for n in rng.integers(3, P + 1, size=B)]
         transducer.map_to_sequence_batch(lt, seqs, slip=5.0)
+    # pre-processing: ragged reads, ties, a read that trims to nothing, a percentile threshold
+    sigs = [rng.standard_normal(n) * 5 + 90 for n in (1000, 2550, 399, 250)] + [np.round(rng.standard_normal(1500) * 3) + 100]
+    for frac in (0, 0.3):
+        basecall.prepare_signals_device(sigs, (200, 10), frac, device=DEV)
     torch.cuda.synchronize()
     print("sanitize smoke done")
 
