@@ -52,6 +52,19 @@ def prepare_signal(signal, trim, open_pore_fraction):
     return ((signal - np.median(signal)) / mad(signal)).astype(sloika_dtype)
 
 
+_PINNED = {}
+
+
+def _pinned(tag, nelem, dtype):
+    """Grow-only pinned staging buffer (page-locked allocations cost milliseconds; batches come in a loop)."""
+    import torch
+    buf = _PINNED.get(tag)
+    if buf is None or buf.dtype != dtype or buf.numel() < nelem:
+        buf = torch.empty(max(int(nelem * 1.25), 1), dtype=dtype).pin_memory()
+        _PINNED[tag] = buf
+    return buf[:nelem]
+
+
 def prepare_signals_device(signals, trim=(200, 10), open_pore_fraction=0, window_size=100, device=None):
     """`prepare_signal` for a batch of raw reads on the device (`basecall.py:111-118` per read): open-pore trim, end
     trim and median / MAD normalisation in float64 with exact order statistics, written straight into the padded
@@ -70,13 +83,14 @@ def prepare_signals_device(signals, trim=(200, 10), open_pore_fraction=0, window
     lens = np.array([len(s) for s in signals], dtype=np.int64)
     offsets = np.zeros(B + 1, dtype=np.int64)
     np.cumsum(lens, out=offsets[1:])
-    flat = torch.empty(int(offsets[-1]), dtype=torch.float64).pin_memory()
+    flat = _pinned('raw', int(offsets[-1]), torch.float64)
     flat_np = flat.numpy()
     for b, s in enumerate(signals):
         flat_np[offsets[b]:offsets[b + 1]] = s
     max_len = int(lens.max()) if B else 0
     with torch.cuda.device(dev):
         sig_d = flat.to(dev, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()      # the staging buffer is reused by the next call
         off_d = torch.from_numpy(offsets).to(dev)
         nbytes = lib.sloika_prepare_workspace_bytes(max_len, B, window_size)
         ws = torch.empty(max(nbytes, 8), dtype=torch.uint8, device=dev)
@@ -117,10 +131,12 @@ def basecall_signals(signals, kmer_len=5, min_prob=1e-5, skip=0.0, nbase=4, netw
         return []
     dev = net.device
     lens = np.array([len(s) for s in signals], dtype=np.int32)
-    host = torch.zeros((int(lens.max()), len(signals)), dtype=torch.float32).pin_memory()
+    host = _pinned('signals', int(lens.max()) * len(signals), torch.float32).view(int(lens.max()), len(signals))
+    host.zero_()
     for b, s in enumerate(signals):
         host[:len(s), b] = torch.from_numpy(np.ascontiguousarray(s, dtype=np.float32))
     x = host.to(dev, non_blocking=True).unsqueeze(2)
+    torch.cuda.current_stream(dev).synchronize()          # the staging buffer is reused by the next call
     return basecall_prepared(x, torch.from_numpy(lens).to(dev), kmer_len, min_prob, skip, nbase, net, assemble)
 
 
