@@ -234,3 +234,41 @@ def test_raw_batch_with_device_preprocessing_equals_host_preprocessing(tmp_path,
         basecall.calc_post = None
     for a, b in zip(dev_res, host_res):
         assert a[0] == b[0] and a[3] == b[3] and list(a[2]) == list(b[2]) and a[1] == b[1]
+
+
+# ------------------------------------------------------------------ full benchmark size (BASELINE.json configs[2])
+def test_full_size_batch_properties():
+    """rgrgr at the benchmark's size (1024 chunks x 4000 samples): properties that do not need an oracle run of that
+    size -- determinism, independence of a chunk's result from the rest of the batch, posterior rows summing to one,
+    fused decode == decode of the materialised posteriors -- plus exact agreement with the C oracle's Viterbi on a
+    sample of the reads."""
+    from oracle import cbind
+    from sloika_b200 import zoo
+    np.random.seed(2)
+    net = zoo.raw_rgrgr().compile()
+    gen = torch.Generator(device='cuda:0').manual_seed(2)
+    x = torch.randn((4000, 1024, 1), generator=gen, device='cuda:0')
+    fused = net.forward_device(x, None, fused_decode=True)
+    s1, p1, l1 = decode.viterbi_batch(fused, None, min_prob=1e-5, return_device=True)
+    s2, p2, l2 = decode.viterbi_batch(net.forward_device(x, None, fused_decode=True), None, min_prob=1e-5,
+                                      return_device=True)
+    assert torch.equal(s1, s2) and torch.equal(l1, l2) and torch.equal(p1, p2)           # deterministic
+    assert int(l1.min()) >= 1 and int(l1.max()) <= 800
+    # a chunk's call does not depend on its neighbours in the batch (CTA tiles of 8 sequences / 128 GEMM rows)
+    for sel in (slice(0, 16), slice(1000, 1024), slice(517, 530)):
+        sub = net.forward_device(x[:, sel].contiguous(), None, fused_decode=True)
+        ss, ps, ls = decode.viterbi_batch(sub, None, min_prob=1e-5, return_device=True)
+        assert torch.equal(ss, s1[sel]) and torch.equal(ls, l1[sel]) and torch.equal(ps, p1[sel])
+    # materialised posteriors: rows sum to one, and decoding them gives the same paths as the fused path
+    post = net.forward_device(x, None)
+    rows = post.data.sum(dim=2)
+    assert float((rows - 1).abs().max()) < 1e-5
+    s3, p3, l3 = decode.viterbi_batch(post, None, min_prob=1e-5, return_device=True)
+    assert torch.equal(l3, l1) and torch.equal(p3, p1)
+    torch.testing.assert_close(s3, s1, rtol=1e-5, atol=1e-3)
+    # C oracle on a sample of reads, fed the device's own log-posteriors: exact paths and scores
+    idx = [0, 1, 255, 256, 511, 777, 1023]
+    lp = torch.log((1e-5 + (1.0 - 1e-5) * post.data[:, idx]) + 1e-10).contiguous()
+    sd, pd_ = decode.viterbi_batch(lp, None, log=True)
+    ref_s, ref_p = cbind.viterbi_batch(lp.cpu().numpy(), None)
+    assert np.array_equal(sd, ref_s) and pd_ == ref_p
