@@ -1,25 +1,30 @@
-// y = act(x . W' + bias) on the 5th-generation tensor cores with fp32-equivalent accuracy (3xTF32).
+// y = act(x . W' + bias) on the 5th-generation tensor cores with fp32-equivalent accuracy (three-product operand split).
 //
 // Used for the GRU input projection over all time steps (sloika/layers.py:1011: vI = x iW' + b),
 // FeedForward.run (layers.py:157-158) and the logits of Softmax.run (layers.py:310).
 // M = T*B rows is huge (819 200), K <= 256 and N <= ~1100 are small: the weights are tiny and stay
-// resident on chip, x is streamed exactly once per N slice, y is written once.  HBM-bound by design.
+// resident on chip, x is streamed once per N slice (re-reads hit L2), y is written once.  HBM-bound by design.
 //
-// Accuracy: the reference multiplies in float32.  Plain TF32 (10-bit mantissa) would put ~1e-3 of
-// error into the gate pre-activations, so every operand is split on chip into hi = top 19 bits and
-// lo = x - hi (exact), and three MMAs  hi.hi + lo.hi + hi.lo  are accumulated in fp32 in TMEM; the
-// dropped lo.lo term is 2^-22 relative.
+// Accuracy: the reference multiplies in float32.  Plain TF32 (10-bit mantissa) would put ~1e-3 of error into the gate
+// pre-activations, so every operand is split on chip into hi + lo and three MMAs  hi.hi + lo.hi + hi.lo  are
+// accumulated in fp32 in TMEM (the dropped lo.lo term is 2^-22 relative).  Two operand formats:
+//   tf32  hi = top 19 bits, lo = x - hi (exact); kind::tf32, K = 8 per MMA, SWIZZLE_128B tiles; any input
+//   f16   hi = fp16(x), lo = fp16(x - hi); kind::f16, K = 16 per MMA (twice the rate), SWIZZLE_64B tiles, half the
+//         shared memory per weight (wider slices); only for inputs known to be far inside the fp16 range
+//         (sloika_linear_fwd_ex / _gated decide; see include/sloika_b200.h)
 //
 // Structure (one persistent CTA per SM, 448 threads, warp specialised):
 //   grid = n_slices x ctas_per_slice; a CTA owns output columns [n0, n0 + BN) and walks m-tiles.
-//   prologue   all warps: W slice -> smem as W_hi / W_lo in the UMMA K-major SWIZZLE_128B layout
+//   prologue   all warps: W slice -> smem as W_hi / W_lo in the UMMA K-major swizzled layout
 //   warp 4     TMA producer: x tile [128 rows x 32 k] per stage (cp.async.bulk.tensor, SWIZZLE_128B)
-//   warps 6-9  transform: raw fp32 tile -> hi (in place) + lo, fence.proxy.async, signal
-//   warp 5     MMA issuer: 4 K-steps x 3 tcgen05.mma (M=128, N=BN, K=8) per stage, accumulators in
-//              TMEM (2 stages x BN columns); tcgen05.commit frees the smem stage / publishes the tile
-//   warps 0-3, 10-13  epilogue (two groups on alternate 32-column chunks): tcgen05.ld (thread = row),
-//              + bias, activation, optional softmax row statistics, transpose through smem,
-//              coalesced 128-bit row stores
+//   warps 6-9  transform: raw fp32 tile -> hi + lo (tf32: hi in place; f16: both in place of the raw tile, so a stage
+//              is 16 KB), fence.proxy.async, signal
+//   warp 5     MMA issuer: 3 tcgen05.mma (M=128, N=BN) per K step, accumulators in TMEM (2 stages x BN columns);
+//              tcgen05.commit frees the smem stage / publishes the tile
+//   warps 0-3, 10-13  epilogue (two groups on alternate 32-column chunks): tcgen05.ld (thread = row), + bias,
+//              activation, optional softmax row statistics, then the 32 x 32 box goes to a swizzled staging tile and
+//              out through a TMA store (cp.async.bulk.tensor shared -> global); rows whose pitch is not 16-byte
+//              aligned take the transposing LDS + STG path instead
 #include <cstdlib>
 #include <cuda_fp16.h>
 #include "common.cuh"
