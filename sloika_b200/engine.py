@@ -6,7 +6,7 @@ This replaces what Theano does for the reference (`Layer.compile`, `sloika/layer
 methods.  Every operator goes through the C ABI (`cabi`), on the current torch stream; torch is
 used for device memory, streams and nothing else.
 """
-import ctypes
+import os
 
 import numpy as np
 
@@ -145,7 +145,6 @@ def _bounded_fun(fun):
 def _gemm_algo(act, *params):
     """fp16-split tensor-core GEMM when the input is provably in [-1, 1] and the weights are far inside the
     fp16 range; otherwise let the library choose (tf32 split / SIMT).  SLOIKA_B200_NO_F16=1 disables it."""
-    import os
     if act.bounded and not os.environ.get('SLOIKA_B200_NO_F16') and \
             all(p.absmax() < _F16_WEIGHT_LIMIT for p in params):
         return GEMM_TC_F16
@@ -156,7 +155,6 @@ def _linear(name, lib, act, W, b, y, ldy, N, fun_code, dev):
     """y = fun(x W' + b) through sloika_linear_fwd_ex; the fp16-split request degrades to AUTO when the
     tensor-core kernel cannot take the shape."""
     tc_ok = act.ld % 4 == 0 and act.data.data_ptr() % 16 == 0 and act.T * act.B >= 128 and act.F <= 256
-    import os
     if not act.bounded and act.absmax is not None and tc_ok and W.absmax() < _F16_WEIGHT_LIMIT \
             and not os.environ.get('SLOIKA_B200_NO_F16'):
         # range known only on the device: enqueue both tensor-core forms, the kernel-side gate runs exactly one

@@ -16,7 +16,6 @@ single-read fast5 files use:
 Raw lengths of the bundled reads are pinned by the reference's `test/unit/test_fast5.py:99-110`.
 """
 import os
-import struct
 import zlib
 
 import numpy as np

@@ -10,7 +10,7 @@ import pytest
 import torch
 
 from conftest import scaled_signal
-from oracle import decode_ref, forward_ref, host_ref
+from oracle import decode_ref, forward_ref
 from sloika_b200 import basecall, bio, decode
 
 pytestmark = pytest.mark.gpu

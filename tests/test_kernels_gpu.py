@@ -5,7 +5,6 @@ pre-softmax activations in [-1, 1] (elu outputs: relative), 1e-4 max-abs on post
 north-star bound); Viterbi is float32 add/max only -> scores and paths are compared EXACTLY when both
 sides get identical log-posteriors.
 """
-import ctypes
 import os
 
 import numpy as np
