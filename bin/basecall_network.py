@@ -83,7 +83,8 @@ def build_parser():
     raw.add_argument('--alphabet', default='ACGT', help='Alphabet of the sequences')
     raw.add_argument('--compile', default=None, help='File output compiled model')
     raw.add_argument('--input_strand_list', default=None, type=existing, help='Strand summary file containing subset')
-    raw.add_argument('--jobs', default=1, metavar='n', type=positive_int, help='Accepted for compatibility')
+    raw.add_argument('--jobs', default=1, metavar='n', type=positive_int,
+                     help='Processes parsing fast5 files (the network itself runs on the GPU of this process)')
     raw.add_argument('--kmer_len', default=5, metavar='length', type=positive_int, help='Length of kmer')
     raw.add_argument('--limit', default=None, metavar='reads', type=positive_int, help='Limit number of reads to process')
     raw.add_argument('--min_prob', metavar='proportion', default=1e-5, type=proportion,
@@ -108,8 +109,10 @@ def main(argv=None):
     args = build_parser().parse_args(argv)
     if os.path.exists(args.compile or ''):
         raise RuntimeError("File/path for 'compile' exists, {}".format(args.compile))       # FileAbsent
+    from sloika_b200 import basecall
+    reader_pool = basecall.make_reader_pool(args.jobs)         # forked before CUDA is initialised
     import torch
-    from sloika_b200 import basecall, helpers, sharding
+    from sloika_b200 import helpers, sharding
     from sloika_b200.fast5 import iterate_fast5
 
     rank = int(os.environ.get('RANK', '0'))
@@ -135,7 +138,7 @@ def main(argv=None):
         results.extend(basecall.raw_batch(chunk, trim=tuple(args.trim), open_pore_fraction=args.open_pore_fraction,
                                           kmer_len=args.kmer_len, transducer=args.transducer, bad=args.bad,
                                           min_prob=args.min_prob, alphabet=args.alphabet, skip=args.skip,
-                                          trans=args.trans))
+                                          trans=args.trans, reader_pool=reader_pool))
     results = sharding.gather_results(mine, results, len(files))
     if rank == 0:
         for res in results:
@@ -147,6 +150,8 @@ def main(argv=None):
         dt = time.time() - t0
         t = 'Called {} bases in {:.1f} s ({:.1f} bases/s or {:.1f} {}/s)\n'
         sys.stderr.write(t.format(nbases, dt, nbases / dt, nevents / dt, args.datatype))
+    if reader_pool is not None:
+        reader_pool.close()
     if compiled_file != args.compile:
         os.remove(compiled_file)
     if world > 1:

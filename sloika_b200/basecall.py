@@ -250,6 +250,23 @@ def _read_raw(fast5_file_name):
         return f5.get_read(raw=True), f5.filename_short
 
 
+def _read_raw_safe(fast5_file_name):
+    """(signal, short name) or the exception raised by the reader (pool workers cannot write to our stderr in order)."""
+    try:
+        return _read_raw(fast5_file_name)
+    except Exception as e:                                   # reported by the caller like raw_worker does
+        return e
+
+
+def make_reader_pool(jobs):
+    """Process pool that parses fast5 files (pure-Python HDF5 reader: ~2 ms per read, the host-side bottleneck once
+    the rest runs on the device).  Create it BEFORE the first CUDA call: the workers are forked and never touch CUDA."""
+    if jobs is None or jobs <= 1:
+        return None
+    import multiprocessing
+    return multiprocessing.get_context('fork').Pool(jobs)
+
+
 def raw_worker(fast5_file_name, trim, open_pore_fraction, kmer_len, transducer, bad, min_prob,
                alphabet=DEFAULT_ALPHABET, skip=5.0, trans=None):
     """ Worker function for basecalling one fast5 file from raw data (`basecall.py:88-121`)
@@ -273,18 +290,22 @@ def raw_worker(fast5_file_name, trim, open_pore_fraction, kmer_len, transducer, 
 
 
 def raw_batch(fast5_file_names, trim=(200, 10), open_pore_fraction=0, kmer_len=5, transducer=True,
-              bad=True, min_prob=1e-5, alphabet=DEFAULT_ALPHABET, skip=0.0, trans=None):
-    """`raw_worker` over many files in one device batch; same result tuples, None for bad reads."""
+              bad=True, min_prob=1e-5, alphabet=DEFAULT_ALPHABET, skip=0.0, trans=None, reader_pool=None):
+    """`raw_worker` over many files in one device batch; same result tuples, None for bad reads.
+
+    :param reader_pool: optional `make_reader_pool(jobs)` pool that reads the files in parallel (`--jobs`)
+    """
     assert transducer, "only transducer models are supported"
     import os
     names, raws, slots = [], [], []
     results = [None] * len(fast5_file_names)
-    for i, fn in enumerate(fast5_file_names):
-        try:
-            signal, sn = _read_raw(fn)
-        except Exception as e:
-            sys.stderr.write("Error getting raw data for file {}\n{!r}\n".format(fn, e))
+    loaded = reader_pool.map(_read_raw_safe, fast5_file_names) if reader_pool is not None else \
+        [_read_raw_safe(fn) for fn in fast5_file_names]
+    for i, (fn, item) in enumerate(zip(fast5_file_names, loaded)):
+        if isinstance(item, Exception):
+            sys.stderr.write("Error getting raw data for file {}\n{!r}\n".format(fn, item))
             continue
+        signal, sn = item
         names.append(sn)
         raws.append(signal)
         slots.append(i)

@@ -71,6 +71,11 @@ def test_cli_end_to_end_matches_golden_fasta(fast5_dir, pretrained, read_basecal
     assert proc.returncode == 0, proc.stderr[-2000:]
     expect = ''.join(read_basecalls[n]['header'] + '\n' + read_basecalls[n]['seq'] + '\n' for n in sorted(NAMES))
     assert proc.stdout == expect
+    # --jobs: the files are parsed by a forked pool, same records in the same order
+    par = subprocess.run([sys.executable, os.path.join(ROOT, 'bin', 'basecall_network.py'), 'raw', '--batch', '3',
+                          '--jobs', '3', str(model), str(fast5_dir)], capture_output=True, text=True, timeout=600)
+    assert par.returncode == 0, par.stderr[-2000:]
+    assert par.stdout == expect and 'broken.fast5' in par.stderr
     assert 'Error getting raw data for file' in proc.stderr and 'broken.fast5' in proc.stderr
     nbases = sum(len(read_basecalls[n]['seq']) for n in NAMES)
     assert 'Called {} bases in'.format(nbases) in proc.stderr and 'samples/s' in proc.stderr

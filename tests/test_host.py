@@ -323,3 +323,27 @@ def test_prepare_post_matches_oracle():
     np.testing.assert_array_equal(decode.prepare_post(post, 1e-5), decode_ref.prepare_post(post, 1e-5))
     np.testing.assert_array_equal(decode.prepare_post(post, 1e-5, drop_bad=True),
                                   decode_ref.prepare_post(post, 1e-5, drop_bad=True))
+
+
+def test_reader_pool_reads_like_serial(tmp_path, reads_daq):
+    """`--jobs`: a forked pool parses fast5 files in parallel and hands back exactly what the serial reader does,
+    exceptions included (as values, so that the caller reports them in order)."""
+    from h5write import write_fast5
+    files = []
+    for i in (1, 4, 6):
+        name = 'read{}'.format(i)
+        offset, rng_, digi = reads_daq[name + '_scaling']
+        fn = str(tmp_path / (name + '.fast5'))
+        write_fast5(fn, reads_daq[name], float(offset), float(rng_), float(digi), read_number=i)
+        files.append(fn)
+    files.append(str(tmp_path / 'missing.fast5'))
+    serial = [basecall._read_raw_safe(f) for f in files]
+    pool = basecall.make_reader_pool(2)
+    try:
+        par = pool.map(basecall._read_raw_safe, files)
+    finally:
+        pool.close()
+    assert basecall.make_reader_pool(1) is None
+    for a, b in zip(serial[:3], par[:3]):
+        assert a[1] == b[1] and np.array_equal(a[0], b[0])
+    assert isinstance(serial[3], Exception) and isinstance(par[3], Exception)
