@@ -127,7 +127,8 @@ int sloika_softmax_normalise_fwd(float *logits, long ldl, const float *stats, in
  *   hbar = act(vI[2H:] + (r*h) sW2') ; h' = z*h + (1-z)*hbar
  *   x: T*B rows of I floats (ldx); iW [3H,I]; sW [2H,H]; sW2 [H,H]; b [3H]; y: T*B rows of H (ldy).
  *   ws: workspace of sloika_gru_workspace_bytes(T,B,H) bytes (holds vI for all steps).
- * Outputs at steps >= lengths[b] are written as zero.
+ * Outputs at steps >= lengths[b] are written as zero.  H <= 144 runs as one persistent kernel; wider layers run the scan
+ * step by step (two GEMMs + two gate kernels per step).
  */
 size_t sloika_gru_workspace_bytes(int T, int B, int H);
 int sloika_gru_fwd(const float *x, long ldx, const float *iW, const float *sW, const float *sW2,

@@ -318,9 +318,81 @@ int dispatch(const float *vI, long ldv, const float *sW, const float *sW2, float
              int H, int reverse, int act, int gate_act, cudaStream_t st);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Hidden sizes beyond what one SM can keep on chip (H > 144): the scan is run step by step -- two GEMMs
+// (h sW', (r*h) sW2': the tensor-core kernel when the batch is large enough, else the SIMT one) and two small
+// gate kernels per step, all enqueued on the caller's stream.  Same arithmetic as the persistent kernels
+// (Gru.step, sloika/layers.py:1010-1021); far slower (four launches per step), there so that the operator has
+// no size limit.  No shipped raw model is this wide.
+__global__ void gru_step_gates_kernel(const float *__restrict__ vI_t, long ldv, float *__restrict__ vS /* [B][2H] */,
+                                      const float *__restrict__ hprev, long ldh, float *__restrict__ rh /* [B][H] */,
+                                      int B, int H, int act_gate, bool first)
+{
+    const long n = (long)B * H;
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < n; e += (long)gridDim.x * blockDim.x) {
+        const int b = (int)(e / H), j = (int)(e - (long)b * H);
+        const float sz = first ? 0.0f : vS[(long)b * 2 * H + j], sr = first ? 0.0f : vS[(long)b * 2 * H + H + j];
+        const float z = apply_act(vI_t[(long)b * ldv + j] + sz, act_gate);
+        const float r = apply_act(vI_t[(long)b * ldv + H + j] + sr, act_gate);
+        const float h = first ? 0.0f : hprev[(long)b * ldh + j];
+        vS[(long)b * 2 * H + j] = z;                       // z parked where its pre-activation was
+        rh[(long)b * H + j] = r * h;
+    }
+}
+
+__global__ void gru_step_blend_kernel(const float *__restrict__ vI_t, long ldv, const float *__restrict__ vS,
+                                      const float *__restrict__ y2 /* [B][H] */, const float *__restrict__ hprev,
+                                      long ldh, float *__restrict__ y_t, long ldy, const int32_t *__restrict__ lengths,
+                                      int t, int T, int B, int H, int act, bool first)
+{
+    const long n = (long)B * H;
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < n; e += (long)gridDim.x * blockDim.x) {
+        const int b = (int)(e / H), j = (int)(e - (long)b * H);
+        const float z = vS[(long)b * 2 * H + j];
+        const float hbar = apply_act(vI_t[(long)b * ldv + 2 * H + j] + (first ? 0.0f : y2[(long)b * H + j]), act);
+        const float h = first ? 0.0f : hprev[(long)b * ldh + j];
+        float hn = z * h + (1.0f - z) * hbar;
+        const int len = lengths ? min(lengths[b], T) : T;
+        y_t[(long)b * ldy + j] = t < len ? hn : 0.0f;       // state stays 0 outside the read
+    }
+}
+
 }  // namespace sloika
 
 using namespace sloika;
+
+extern "C" int sloika_linear_fwd_ex(const float *x, long ldx, const float *W, const float *bias, float *y, long ldy,
+                                    long M, int K, int N, int act, int algo, void *stream);
+
+static int gru_stepwise(const float *vI, long ldv, const float *sW, const float *sW2, float *y, long ldy,
+                        const int32_t *lengths, int T, int B, int H, int reverse, int act, int gate_act, cudaStream_t st)
+{
+    float *ws = nullptr;                                         // vS [B][2H] | rh [B][H] | y2 [B][H], stream ordered
+    const size_t nfl = (size_t)B * 4 * H;
+    cudaError_t err = cudaMallocAsync(reinterpret_cast<void **>(&ws), nfl * sizeof(float), st);
+    if (err != cudaSuccess) return (int)err;
+    float *vS = ws, *rh = ws + (size_t)B * 2 * H, *y2 = rh + (size_t)B * H;
+    const long n = (long)B * H;
+    const unsigned blocks = (unsigned)(ceil_div(n, 256) > 148L * 16 ? 148L * 16 : ceil_div(n, 256));
+    int rc = SLOIKA_OK;
+    for (int s = 0; s < T && rc == SLOIKA_OK; s++) {
+        const int t = reverse ? T - 1 - s : s;
+        const int tp = reverse ? t + 1 : t - 1;                  // the step whose output is h_{t-1} of the scan
+        const bool first = s == 0;
+        const float *vI_t = vI + (long)t * B * ldv;
+        const float *hprev = first ? nullptr : y + (long)tp * B * ldy;
+        float *y_t = y + (long)t * B * ldy;
+        if (!first) rc = sloika_linear_fwd_ex(hprev, ldy, sW, nullptr, vS, 2L * H, B, H, 2 * H, SLOIKA_ACT_LINEAR, SLOIKA_GEMM_AUTO, st);
+        if (rc != SLOIKA_OK) break;
+        gru_step_gates_kernel<<<blocks, 256, 0, st>>>(vI_t, ldv, vS, hprev, ldy, rh, B, H, gate_act, first);
+        if (!first) rc = sloika_linear_fwd_ex(rh, H, sW2, nullptr, y2, H, B, H, H, SLOIKA_ACT_LINEAR, SLOIKA_GEMM_AUTO, st);
+        if (rc != SLOIKA_OK) break;
+        gru_step_blend_kernel<<<blocks, 256, 0, st>>>(vI_t, ldv, vS, y2, hprev, ldy, y_t, ldy, lengths, t, T, B, H, act, first);
+    }
+    cudaFreeAsync(ws, st);
+    if (rc != SLOIKA_OK) return rc;
+    SLOIKA_RETURN_LAUNCH_STATUS();
+}
 
 extern "C" int sloika_gru_recurrence_fwd(const float *vI, long ldv, const float *sW, const float *sW2, float *y, long ldy,
                                          const int32_t *lengths, int T, int B, int H, int reverse, int act,
@@ -356,7 +428,7 @@ extern "C" int sloika_gru_recurrence_fwd(const float *vI, long ldv, const float 
     if (H <= 128) GRU_CASE(128, 4, 1);
     if (H <= 144) GRU_CASE(144, 4, 2);
 #undef GRU_CASE
-    return SLOIKA_ERR_UNSUPPORTED;
+    return gru_stepwise(vI, ldv, sW, sW2, y, ldy, lengths, T, B, H, reverse, act, gate_act, st);
 }
 
 extern "C" size_t sloika_gru_workspace_bytes(int T, int B, int H)

@@ -257,9 +257,8 @@ def test_error_codes_surface_as_exceptions():
         decode.viterbi(np.zeros((4, 17), dtype=np.float32), 2)             # klen >= 3 (decode.py:50)
     with pytest.raises(AssertionError):
         decode.viterbi(np.zeros((4, 66), dtype=np.float32), 3)             # nstate mismatch (decode.py:52)
-    g = layers.Gru(8, 200, has_bias=True)                                   # H > 144: no kernel yet
-    with pytest.raises(cabi.SloikaB200Error):
-        _run(g, np.zeros((4, 2, 8), dtype=np.float32))
+    with pytest.raises(cabi.SloikaB200Error):                              # C-ABI error codes become exceptions
+        cabi.check(-2, 'unsupported thing')
 
 
 # ------------------------------------------------------------------ tcgen05 3xTF32 GEMM vs fp32 SIMT vs float64
@@ -534,3 +533,22 @@ def test_gru_one_call_entry_point(I, H, T, B, reverse, ragged):
         assert np.all(got[n:, b] == 0)
     args[9] = nbytes - 4                                       # workspace too small
     assert lib.sloika_gru_fwd(*args) == -3
+
+
+@pytest.mark.parametrize('I,H,T,B,reverse,ragged', [(24, 160, 40, 6, False, False), (32, 200, 30, 130, True, True),
+                                                    (16, 256, 25, 3, False, True)])
+def test_gru_wider_than_one_sm_runs_step_by_step(I, H, T, B, reverse, ragged):
+    """H > 144 does not fit the persistent kernels: the scan runs as per-step GEMMs + gate kernels (gru.cu,
+    `gru_stepwise`); same results as the oracle, ragged and reversed included (B = 130 takes the tensor-core GEMM)."""
+    np.random.seed(H + T)
+    g = layers.Gru(I, H, init=_init(), has_bias=True)
+    g.sW.set_value(g.sW.get_value() * 3)
+    layer = layers.Reverse(g) if reverse else g
+    x = np.tanh(np.random.standard_normal((T, B, I))).astype(np.float32)
+    lengths = list(np.random.randint(1, T + 1, size=B)) if ragged else None
+    got, _ = _run(layer, x, lengths)
+    for b in range(min(B, 12)):
+        n = T if lengths is None else int(lengths[b])
+        ref = _oracle(layer, x[:n, b:b + 1])
+        assert np.abs(got[:n, b] - ref[:, 0]).max() < 5e-5, b
+        assert np.all(got[n:, b] == 0)
