@@ -347,3 +347,21 @@ def test_reader_pool_reads_like_serial(tmp_path, reads_daq):
     for a, b in zip(serial[:3], par[:3]):
         assert a[1] == b[1] and np.array_equal(a[0], b[0])
     assert isinstance(serial[3], Exception) and isinstance(par[3], Exception)
+
+
+def test_seqprinter_uses_device_assembled_sequence_only_when_conventions_match(capsys):
+    """`CalledPath.sequence` (assembled on the device by raw_batch) is printed as is when it was built with the
+    printer's own (kmer_len, alphabet, transducer) conventions; otherwise the k-mers are spelled on the host."""
+    path = basecall.CalledPath([0, 1, 5, 5, 21])
+    host_seq = bio.states_to_sequence(path, 5, 'ACGT', always_move=True)
+    path.sequence, path.assembly = 'N' * 7, (5, 'ACGT', True)               # a marker no assembly would produce
+    printer = basecall.SeqPrinter(5, datatype='samples', transducer=True, alphabet='ACGT')
+    assert printer.write('r', -3.2, path, 100) == 7
+    other = basecall.SeqPrinter(5, datatype='samples', transducer=False, alphabet='ACGT')
+    n = other.write('r', -3.2, path, 100)
+    out = capsys.readouterr().out.splitlines()
+    assert out[0] == '>r score -3, 100 samples to 7 bases' and out[1] == 'NNNNNNN'
+    assert out[3] == bio.states_to_sequence(path, 5, 'ACGT', always_move=False) and n == len(out[3])
+    assert host_seq != 'NNNNNNN'
+    from sloika_b200 import transducer
+    assert transducer.argmax(3.0, 9.0, 1.0) == (1, 9.0)                      # transducer.py:9-11
