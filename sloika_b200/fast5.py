@@ -318,7 +318,14 @@ class H5File(object):
             elif fid == 2:
                 n = len(raw) // itemsize
                 arr = np.frombuffer(raw, dtype=np.uint8, count=n * itemsize)
-                raw = arr.reshape(itemsize, n).T.tobytes() + raw[n * itemsize:]
+                if itemsize == 2:
+                    # the raw DAQ signal (int16): byte planes recombined with contiguous vector operations, an
+                    # order of magnitude faster than the strided transpose
+                    words = arr[:n].astype('<u2')
+                    words |= arr[n:].astype('<u2') << 8
+                    raw = words.tobytes() + raw[n * itemsize:]
+                else:
+                    raw = arr.reshape(itemsize, n).T.tobytes() + raw[n * itemsize:]
             elif fid == 3:
                 raw = raw[:-4]          # fletcher32 checksum trailer
             else:
