@@ -133,12 +133,18 @@ def main(argv=None):
     nbases = nevents = 0
     t0 = time.time()
     results = []
-    for lo in range(0, len(mine), args.batch):
-        chunk = [files[i] for i in mine[lo:lo + args.batch]]
+    chunks = [[files[i] for i in mine[lo:lo + args.batch]] for lo in range(0, len(mine), args.batch)]
+    # with --jobs the files of the next batch are parsed by the pool while this batch is on the device
+    ahead = basecall.read_files(chunks[0], reader_pool, wait=False) if (reader_pool is not None and chunks) else None
+    for k, chunk in enumerate(chunks):
+        loaded = None
+        if ahead is not None:
+            loaded = ahead.get()
+            ahead = basecall.read_files(chunks[k + 1], reader_pool, wait=False) if k + 1 < len(chunks) else None
         results.extend(basecall.raw_batch(chunk, trim=tuple(args.trim), open_pore_fraction=args.open_pore_fraction,
                                           kmer_len=args.kmer_len, transducer=args.transducer, bad=args.bad,
                                           min_prob=args.min_prob, alphabet=args.alphabet, skip=args.skip,
-                                          trans=args.trans, reader_pool=reader_pool))
+                                          trans=args.trans, loaded=loaded))
     results = sharding.gather_results(mine, results, len(files))
     if rank == 0:
         for res in results:

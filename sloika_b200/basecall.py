@@ -258,6 +258,15 @@ def _read_raw_safe(fast5_file_name):
         return e
 
 
+def read_files(fast5_file_names, reader_pool=None, wait=True):
+    """(signal, short name) or the raised exception for every file; with a pool and `wait=False` an AsyncResult whose
+    `.get()` gives that list (lets the caller read the next batch while the current one is on the device)."""
+    if reader_pool is None:
+        return [_read_raw_safe(fn) for fn in fast5_file_names]
+    res = reader_pool.map_async(_read_raw_safe, fast5_file_names)
+    return res.get() if wait else res
+
+
 def make_reader_pool(jobs):
     """Process pool that parses fast5 files (pure-Python HDF5 reader: ~2 ms per read, the host-side bottleneck once
     the rest runs on the device).  Create it BEFORE the first CUDA call: the workers are forked and never touch CUDA."""
@@ -290,17 +299,19 @@ def raw_worker(fast5_file_name, trim, open_pore_fraction, kmer_len, transducer, 
 
 
 def raw_batch(fast5_file_names, trim=(200, 10), open_pore_fraction=0, kmer_len=5, transducer=True,
-              bad=True, min_prob=1e-5, alphabet=DEFAULT_ALPHABET, skip=0.0, trans=None, reader_pool=None):
+              bad=True, min_prob=1e-5, alphabet=DEFAULT_ALPHABET, skip=0.0, trans=None, reader_pool=None, loaded=None):
     """`raw_worker` over many files in one device batch; same result tuples, None for bad reads.
 
     :param reader_pool: optional `make_reader_pool(jobs)` pool that reads the files in parallel (`--jobs`)
+    :param loaded: optional result of `read_files(fast5_file_names, ...)` obtained earlier (prefetched by the caller
+        while the previous batch was on the device)
     """
     assert transducer, "only transducer models are supported"
     import os
     names, raws, slots = [], [], []
     results = [None] * len(fast5_file_names)
-    loaded = reader_pool.map(_read_raw_safe, fast5_file_names) if reader_pool is not None else \
-        [_read_raw_safe(fn) for fn in fast5_file_names]
+    if loaded is None:
+        loaded = read_files(fast5_file_names, reader_pool)
     for i, (fn, item) in enumerate(zip(fast5_file_names, loaded)):
         if isinstance(item, Exception):
             sys.stderr.write("Error getting raw data for file {}\n{!r}\n".format(fn, item))

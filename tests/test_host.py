@@ -340,9 +340,12 @@ def test_reader_pool_reads_like_serial(tmp_path, reads_daq):
     serial = [basecall._read_raw_safe(f) for f in files]
     pool = basecall.make_reader_pool(2)
     try:
-        par = pool.map(basecall._read_raw_safe, files)
+        par = basecall.read_files(files, pool)
+        later = basecall.read_files(files[:2], pool, wait=False).get()
     finally:
         pool.close()
+    assert len(later) == 2 and np.array_equal(later[1][0], serial[1][0])
+    assert [type(x) for x in basecall.read_files(files)] == [type(x) for x in serial]
     assert basecall.make_reader_pool(1) is None
     for a, b in zip(serial[:3], par[:3]):
         assert a[1] == b[1] and np.array_equal(a[0], b[0])
