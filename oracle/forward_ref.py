@@ -6,8 +6,10 @@ no code with the product's layer classes.  Tensors are `[time, batch, feature]` 
 `dtype=np.float32` reproduces the reference arithmetic type (`bin/basecall_network:5-7` pins
 floatX=float32); `dtype=np.float64` is the error-budget twin.
 
-Parity: Gru and Convolution are "parity unpinned" (no Theano here, no known-answer in the
-reference's tests); the other layers follow formulas pinned by `test/unit/test_layers.py:58-125`.
+Parity: PINNED.  `tools/make_golden_forward.py` executes the reference's own unmodified `sloika/layers.py`,
+`conv.py`, `activation.py` and model scripts (Theano's primitives supplied eagerly by `tools/theano_shim.py`)
+and stores their outputs in `tests/golden/forward_cases.npz` / `reads_forward.npz`; `tests/test_oracle.py`
+asserts that every function below reproduces them to 1e-6 (2e-5 over whole reads).
 """
 import numpy as np
 
@@ -113,6 +115,55 @@ def gru(desc, x, dtype, lengths=None):
     return out
 
 
+def lstm(desc, x, dtype):
+    """layers.py:677-697: LSTM with peepholes stepped from (out, state) = 0.  Stored parameters: `iW [4H, I]`,
+    `sW [4H, H]`, `b [4H]`, `p [3, H]`; the step reshapes the 4H pre-activations as `(H, 4)`, i.e. row
+    `4*j + g` belongs to unit j and gate g (0 = update input, 1 = update gate, 2 = forget gate, 3 = output gate)."""
+    H = desc['size']
+    iW = _arr(desc['params']['iW'], dtype).reshape(4 * H, -1)
+    sW = _arr(desc['params']['sW'], dtype).reshape(4 * H, H)
+    b = _arr(desc['params']['b'], dtype).reshape(4 * H)
+    p = _arr(desc['params']['p'], dtype).reshape(3, H)
+    fun = ACTIVATIONS[desc['activation']]
+    gate = ACTIVATIONS[desc['gate']]
+    T, B, _ = x.shape
+    out = np.zeros((B, H), dtype)
+    state = np.zeros((B, H), dtype)
+    res = np.empty((T, B, H), dtype)
+    vW_all = (x @ iW.T).astype(dtype)
+    for t in range(T):
+        sumW = ((vW_all[t] + out @ sW.T) + b).reshape(B, H, 4)
+        new_state = state * gate(sumW[:, :, 2] + state * p[1])
+        new_state = new_state + fun(sumW[:, :, 0]) * gate(sumW[:, :, 1] + state * p[0])
+        out = (fun(new_state) * gate(sumW[:, :, 3] + new_state * p[2])).astype(dtype)
+        state = new_state.astype(dtype)
+        res[t] = out
+    return res
+
+
+def window(desc, x, dtype):
+    """layers.py:346-351: zero-pad w//2 steps either side, concatenate the w shifted copies on the feature
+    axis: out[t, b, k*F + f] = xpad[t + k, b, f]."""
+    w = desc['w']
+    T, B, F = x.shape
+    pad = np.zeros((w // 2, B, F), dtype)
+    xpad = np.concatenate([pad, x, pad], axis=0)
+    return np.concatenate([xpad[k:k + T] for k in range(w)], axis=2)
+
+
+def with_params(arch, weights, prefix=''):
+    """Join an architecture (`json(params=False)`) with a flat `{dotted.name: raw array}` dict (the layout of
+    `sloika_b200.model_io.weights_of` and of the golden fixtures) into the description `run` takes."""
+    kind = arch['type']
+    if kind in ('serial', 'parallel'):
+        return dict(arch, sublayers=[with_params(a, weights, '{}{}.'.format(prefix, i))
+                                     for i, a in enumerate(arch['sublayers'])])
+    if kind == 'reverse':
+        return dict(arch, sublayer=with_params(arch['sublayer'], weights, prefix + '0.'))
+    names = [k[len(prefix):] for k in weights if k.startswith(prefix) and '.' not in k[len(prefix):]]
+    return dict(arch, params={n: weights[prefix + n] for n in names})
+
+
 def run(desc, x, dtype=np.float32):
     """Evaluate a JSON model description on `x` `[T, B, F]`."""
     dtype = np.dtype(dtype).type
@@ -134,6 +185,10 @@ def run(desc, x, dtype=np.float32):
         return softmax(desc, x, dtype)
     if kind == 'GRU':
         return gru(desc, x, dtype)
+    if kind == 'LSTM':
+        return lstm(desc, x, dtype)
+    if kind == 'window':
+        return window(desc, x, dtype)
     raise NotImplementedError("oracle has no restatement for layer type {!r}".format(kind))
 
 

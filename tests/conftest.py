@@ -71,3 +71,17 @@ def scaled_signal(daq_file, name):
 
 
 needs_reference = pytest.mark.skipif(not os.path.isdir(REFERENCE), reason="/root/reference not mounted")
+
+
+@pytest.fixture(scope='session')
+def forward_cases():
+    """Outputs of the reference's own layers.py / conv.py (tools/make_golden_forward.py): (meta, arrays)."""
+    data = np.load(os.path.join(GOLDEN, 'forward_cases.npz'))
+    with open(os.path.join(GOLDEN, 'forward_cases.json')) as fh:
+        meta = json.load(fh)
+    return meta, data
+
+
+def case_weights(data, name):
+    prefix = name + '/w/'
+    return {k[len(prefix):]: data[k] for k in data.files if k.startswith(prefix)}

@@ -72,6 +72,12 @@ def test_posteriors_of_real_read_within_bound(calls, golden_dir, pretrained):
         assert np.abs(post[:8, 0] - slices[name + '_head']).max() < 1e-4
         assert np.abs(post[-8:, 0] - slices[name + '_tail']).max() < 1e-4
         assert np.abs(post[:, 0].max(1) - slices[name + '_rowmax']).max() < 1e-4
+    # the same reads against what the reference's own layers.py computed (tools/make_golden_forward.py)
+    fwd = np.load(os.path.join(golden_dir, 'reads_forward.npz'))
+    for name in ('read7', 'read3'):
+        post = net(signals[NAMES.index(name)][:, None, None])
+        assert np.abs(post[fwd[name + '_rows'], 0] - fwd[name + '_post']).max() < 2e-4
+        assert np.abs(post[:, 0].max(1) - fwd[name + '_rowmax']).max() < 2e-4
     # full-matrix check against the live oracle on the shortest real read
     sig = signals[NAMES.index('read7')]
     post = net(sig[:, None, None])
@@ -266,6 +272,10 @@ def test_full_size_batch_properties():
     s3, p3, l3 = decode.viterbi_batch(post, None, min_prob=1e-5, return_device=True)
     assert torch.equal(l3, l1) and torch.equal(p3, p1)
     torch.testing.assert_close(s3, s1, rtol=1e-5, atol=1e-3)
+    # posteriors of 8 of the 1024 chunks against the (pinned) float32 oracle at the full chunk length: 1e-4
+    cols = [0, 7, 8, 300, 511, 512, 1000, 1023]
+    ref = forward_ref.run(net.network.json(params=True), x[:, cols].cpu().numpy())
+    assert float(np.abs(post.data[:, cols].cpu().numpy() - ref).max()) < 1e-4
     # C oracle on a sample of reads, fed the device's own log-posteriors: exact paths and scores
     idx = [0, 1, 255, 256, 511, 777, 1023]
     lp = torch.log((1e-5 + (1.0 - 1e-5) * post.data[:, idx]) + 1e-10).contiguous()

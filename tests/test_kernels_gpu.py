@@ -552,3 +552,42 @@ def test_gru_wider_than_one_sm_runs_step_by_step(I, H, T, B, reverse, ragged):
         ref = _oracle(layer, x[:n, b:b + 1])
         assert np.abs(got[:n, b] - ref[:, 0]).max() < 5e-5, b
         assert np.all(got[n:, b] == 0)
+
+
+# ------------------------------------------------------------------ the reference's own outputs (tools/make_golden_forward.py)
+_SUPPORTED = {'serial', 'parallel', 'reverse', 'convolution', 'GRU', 'feed-forward', 'softmax_old', 'LSTM', 'window'}
+
+
+def _types(arch):
+    out = {arch['type']}
+    for sub in arch.get('sublayers', []):
+        out |= _types(sub)
+    if 'sublayer' in arch:
+        out |= _types(arch['sublayer'])
+    return out
+
+
+def test_cuda_path_matches_reference_outputs(forward_cases):
+    """Every case of tests/golden/forward_cases.npz: the CUDA path against what the reference's unmodified
+    layers.py / conv.py computed (not against the oracle).  1e-4 max-abs on posteriors (north-star bound), 2e-5
+    on bounded hidden activations, 2e-5 relative on elu outputs."""
+    from conftest import case_weights
+    meta, data = forward_cases
+    ran = 0
+    for case in meta:
+        name = case['name']
+        assert _types(case['arch']) <= _SUPPORTED, name
+        net = zoo.from_weights(case['arch'], case_weights(data, name))
+        x = data[name + '/x']
+        ref = data[name + '/y']
+        got = net.compile()(x)
+        assert got.shape == ref.shape and got.dtype == np.float32, name
+        if ref.size == 0:
+            continue
+        err = np.abs(got - ref)
+        if name.startswith('model_') or name.startswith('softmax'):
+            assert err.max() < 1e-4, (name, float(err.max()))
+        else:
+            assert (err <= 2e-5 + 2e-5 * np.abs(ref)).all(), (name, float(err.max()))
+        ran += 1
+    assert ran >= 40

@@ -191,3 +191,34 @@ def test_slip_update_reference_unit_test_recipe():
         y2s[j] -= slip
     np.testing.assert_almost_equal(y1s, y2s)
     np.testing.assert_equal(y1i, y2i)
+
+
+# ---- forward pass: pinned to outputs of the reference's own source (tools/make_golden_forward.py) ----
+def test_forward_oracle_matches_reference_outputs(forward_cases):
+    """`forward_ref.run` == `network.run(x)` of the unmodified sloika/layers.py + conv.py, every case."""
+    from conftest import case_weights
+    meta, data = forward_cases
+    names = [c['name'] for c in meta]
+    for must in ('conv_1_96_w11_s5_elu', 'conv_12_32_w11_s5', 'gru_96_96', 'gru_128_110', 'gru_110_142', 'gru_128_112',
+                 'gru_112_144', 'gru_rev_96', 'gru_birnn_32_96', 'model_raw_0.98_rgrgr', 'model_raw_1.00_rGr',
+                 'model_bigger_raw_gru', 'lstm_12_64_peep1', 'window_4_w3'):
+        assert must in names
+    for case in meta:
+        name = case['name']
+        desc = forward_ref.with_params(case['arch'], case_weights(data, name))
+        got = forward_ref.run(desc, data[name + '/x'])
+        ref = data[name + '/y']
+        assert got.shape == ref.shape and got.dtype == np.float32, name
+        tol = 1e-5 if name == 'gru_sat' else 2e-6 if name.startswith('model_') else 1e-6
+        assert np.abs(got - ref).max() <= tol, (name, float(np.abs(got - ref).max()))
+
+
+def test_forward_oracle_whole_read_matches_reference(pretrained, reads_daq):
+    """models/pretrained.pkl on a bundled read: oracle posteriors vs the reference's (stored rows), 2e-5."""
+    fwd = np.load(os.path.join(GOLDEN, 'reads_forward.npz'))
+    desc = pretrained.json(params=True)
+    for name in ('read7', 'read5'):
+        x = host_ref.prepare_signal(scaled_signal(reads_daq, name))
+        post = forward_ref.run(desc, x)[:, 0]
+        assert np.abs(post[fwd[name + '_rows']] - fwd[name + '_post']).max() < 2e-5
+        assert np.abs(post.max(1) - fwd[name + '_rowmax']).max() < 2e-5
