@@ -127,8 +127,8 @@ int sloika_softmax_normalise_fwd(float *logits, long ldl, const float *stats, in
  *   hbar = act(vI[2H:] + (r*h) sW2') ; h' = z*h + (1-z)*hbar
  *   x: T*B rows of I floats (ldx); iW [3H,I]; sW [2H,H]; sW2 [H,H]; b [3H]; y: T*B rows of H (ldy).
  *   ws: workspace of sloika_gru_workspace_bytes(T,B,H) bytes (holds vI for all steps).
- * Outputs at steps >= lengths[b] are written as zero.  H <= 144 runs as one persistent kernel; wider layers run the scan
- * step by step (two GEMMs + two gate kernels per step).
+ * Outputs at steps >= lengths[b] are written as zero.  H <= 128 runs on tcgen05 with the weights in tensor memory, H <= 144 as a persistent mma.sync kernel; wider
+ * layers run the scan step by step (two GEMMs + two gate kernels per step).
  */
 size_t sloika_gru_workspace_bytes(int T, int B, int H);
 int sloika_gru_fwd(const float *x, long ldx, const float *iW, const float *sW, const float *sW2,
@@ -140,6 +140,13 @@ int sloika_gru_fwd(const float *x, long ldx, const float *iW, const float *sW, c
 int sloika_gru_recurrence_fwd(const float *vI, long ld_vi, const float *sW, const float *sW2, float *y, long ldy,
                               const int32_t *lengths, int T, int B, int H, int reverse, int act,
                               int gate_act, void *stream);
+/* Same, with a scheduling hint: seqs_in_flight = number of sequences the caller keeps on the device at once (this
+ * batch plus the batches it pipelines on other streams; 0 = just this call).  It only chooses how many sequences
+ * share a CTA of the tensor-memory kernel (spread over the SMs for latency, packed for throughput); results do
+ * not depend on it. */
+int sloika_gru_recurrence_fwd_ex(const float *vI, long ld_vi, const float *sW, const float *sW2, float *y, long ldy,
+                                 const int32_t *lengths, int T, int B, int H, int reverse, int act,
+                                 int gate_act, long seqs_in_flight, void *stream);
 
 /*
  * decode.prepare_post + decode.viterbi -- sloika/decode.py:21-36, :39-93 (called from
@@ -148,7 +155,8 @@ int sloika_gru_recurrence_fwd(const float *vI, long ld_vi, const float *sW, cons
  *   mode: SLOIKA_VIT_POST     post are probabilities; the kernel applies
  *                                 lpost = log( (min_prob + (1-min_prob)*post) + 1e-10 )   (float32)
  *         SLOIKA_VIT_LOG      post are already log-probabilities (`log=True`, decode.py:56)
- *   tb_ws: workspace of sloika_viterbi_workspace_bytes(T,B,nbase,klen) bytes (uint8 traceback)
+ *   tb_ws: workspace of sloika_viterbi_workspace_bytes(T,B,nbase,klen) bytes (traceback: uint16 per quad of states
+ *          for nbase 4, klen 5; uint8 per state otherwise)
  *   path_out int32 [B,T]: k-mer states of the best path with stays removed, left-aligned;
  *   path_len int32 [B]; score_out float32 [B] (= max_j v_T[j]).
  * skip_pen and min_prob are the reference's python floats (double); they are cast to float32 where

@@ -313,6 +313,10 @@ namespace gru4 {
 int dispatch(const float *vI, long ldv, const float *sW, const float *sW2, float *y, long ldy, const int32_t *lengths, int T,
              int B, int H, int reverse, int act, int gate_act, cudaStream_t st);
 }
+namespace gru5 {
+int dispatch(const float *vI, long ldv, const float *sW, const float *sW2, float *y, long ldy, const int32_t *lengths, int T,
+             int B, int H, int reverse, int act, int gate_act, long seqs_in_flight, cudaStream_t st);
+}
 namespace gru3 {
 int dispatch(const float *vI, long ldv, const float *sW, const float *sW2, float *y, long ldy, const int32_t *lengths, int T, int B,
              int H, int reverse, int act, int gate_act, cudaStream_t st);
@@ -398,15 +402,27 @@ extern "C" int sloika_gru_recurrence_fwd(const float *vI, long ldv, const float 
                                          const int32_t *lengths, int T, int B, int H, int reverse, int act,
                                          int gate_act, void *stream)
 {
+    return sloika_gru_recurrence_fwd_ex(vI, ldv, sW, sW2, y, ldy, lengths, T, B, H, reverse, act, gate_act, 0, stream);
+}
+
+extern "C" int sloika_gru_recurrence_fwd_ex(const float *vI, long ldv, const float *sW, const float *sW2, float *y, long ldy,
+                                            const int32_t *lengths, int T, int B, int H, int reverse, int act,
+                                            int gate_act, long seqs_in_flight, void *stream)
+{
     if (!vI || !sW || !sW2 || !y || T < 0 || B <= 0 || H <= 0 || ldy < H || ldv < 3L * H) return SLOIKA_ERR_ARG;
     if (!act_known(act) || !act_known(gate_act)) return SLOIKA_ERR_UNSUPPORTED;
     if (T == 0) return SLOIKA_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    {   // kernel generations, newest first (tanh / sigmoid, H <= 144): fp16x3 mma.sync kernel (gru_h16.cu), 3xTF32
-        // mma.sync kernel (gru_mma.cu); then the FFMA2 kernel of this file (any activation pair).
-        // SLOIKA_B200_GRU=v1|v3 caps the choice (A/B measurements, tests).
+    {   // kernel generations, newest first (tanh / sigmoid): tcgen05 kernel with the weights in tensor memory
+        // (gru_tc.cu, H <= 128), fp16x3 mma.sync kernel (gru_h16.cu, H <= 144), 3xTF32 mma.sync kernel (gru_mma.cu);
+        // then the FFMA2 kernel of this file (any activation pair).
+        // SLOIKA_B200_GRU=v1|v3|v4 caps the choice (A/B measurements, tests).
         const char *sel = getenv("SLOIKA_B200_GRU");
-        const int cap = (sel && sel[0] == 'v' && sel[1] >= '1' && sel[1] <= '4') ? sel[1] - '0' : 4;
+        const int cap = (sel && sel[0] == 'v' && sel[1] >= '1' && sel[1] <= '5') ? sel[1] - '0' : 5;
+        if (cap >= 5) {
+            const int rc = gru5::dispatch(vI, ldv, sW, sW2, y, ldy, lengths, T, B, H, reverse, act, gate_act, seqs_in_flight, st);
+            if (rc != SLOIKA_ERR_UNSUPPORTED) return rc;
+        }
         if (cap >= 4) {
             const int rc = gru4::dispatch(vI, ldv, sW, sW2, y, ldy, lengths, T, B, H, reverse, act, gate_act, st);
             if (rc != SLOIKA_ERR_UNSUPPORTED) return rc;

@@ -12,12 +12,14 @@
 // All nb states 'nb*r .. nb*r+nb-1' share the same step predecessor set (index r) so thread r owns
 // them: the step max stays in registers, the skip max is nb^2 conflict-free shared loads, v_{i-1} and
 // v_i ping-pong in shared memory (one __syncthreads per event).  Only 1 + nb + nb^2 traceback outcomes
-// exist per state, so the traceback is ONE BYTE per state per event (code 0 = stay, 1+a = step from a,
-// 1+nb+a = skip from a) in global memory -- 1 KB/event instead of the reference's 4 KB -- written as
-// coalesced words.  Arithmetic is float32 add/max in the reference's order, so given identical
+// exist per state, so the generic kernel's traceback is ONE BYTE per state per event (code 0 = stay, 1+a = step
+// from a, 1+nb+a = skip from a) in global memory -- 1 KB/event instead of the reference's 4 KB.  The K = 1024
+// kernel goes further: the move predecessor is common to the four states a thread owns, only "moved or
+// stayed" is per state, so a quad is one uint16 (bits 0-3 = moved flags, bits 4-8 = the shared code):
+// 512 bytes per event.  Arithmetic is float32 add/max in the reference's order, so given identical
 // log-posteriors scores and paths are bit-identical.
 //
-// HBM-bound: 4*(K+1) bytes of posterior read + K bytes of traceback written per event.
+// HBM-bound: 4*(K+1) bytes of posterior read + K/2 (K = 1024 kernel; K otherwise) bytes of traceback written per event.
 #include <cmath>
 #include <cstdlib>
 #include "common.cuh"
@@ -213,6 +215,7 @@ viterbi_k1024_kernel(const float *__restrict__ post, long ld_t, long ld_b, const
     __shared__ __align__(16) float xrow_s[2][XROW];
     uint8_t *tb_s2 = reinterpret_cast<uint8_t *>(&xrow_s[0][0]);
     static_assert(sizeof(float) * 2 * XROW >= 8 * 1024, "xrow_s doubles as a traceback chunk buffer");
+    constexpr int TBROW = K / 4;                     // uint16 traceback entries (one per quad of states) per event
 
     const int b = blockIdx.x;
     const int r = threadIdx.x;
@@ -222,7 +225,7 @@ viterbi_k1024_kernel(const float *__restrict__ post, long ld_t, long ld_b, const
         return;
     }
     const float *pb = post + (long)b * ld_b;
-    uint8_t *tbb = tb + (size_t)b * (size_t)T * (size_t)K;
+    uint16_t *tbb = reinterpret_cast<uint16_t *>(tb) + (size_t)b * (size_t)T * (size_t)TBROW;
 
     // softmax row statistics of event i -> ms_s[i & 1] (warp 0; visible after the next barrier)
     const float2 *stp = stats + (long)b * n_slices + r;               // advanced by B*n_slices per event
@@ -294,7 +297,7 @@ viterbi_k1024_kernel(const float *__restrict__ post, long ld_t, long ld_b, const
     __syncthreads();
 
     int cur = 0;
-    unsigned *tbp = reinterpret_cast<unsigned *>(tbb) + r;             // traceback word of this thread, advanced per event
+    uint16_t *tbp = tbb + r;                                          // traceback entry of this thread, advanced per event
     for (int i = 1; i < nev; i++) {
         const float4 xq = reinterpret_cast<const float4 *>(xrow_s[i & 1])[r];
         const float x[4] = {xq.x, xq.y, xq.z, xq.w};
@@ -339,18 +342,18 @@ viterbi_k1024_kernel(const float *__restrict__ post, long ld_t, long ld_b, const
         const unsigned code = use_step ? (1u + as) : (5u + ak);
         const float pj[4] = {pv.x, pv.y, pv.z, pv.w};
         float vo[4];
-        unsigned packed = 0;
+        unsigned packed = code << 4;
 #pragma unroll
         for (int c = 0; c < 4; c++) {
             const float move = __fadd_rn(lp[c], best);
             const float stay = __fadd_rn(pj[c], lp0);
             const bool mv = move > stay;                             // tie -> stay (decode.py:81)
             vo[c] = mv ? move : stay;
-            packed |= (mv ? code : 0u) << (8 * c);
+            packed |= (mv ? 1u : 0u) << c;
         }
         reinterpret_cast<float4 *>(vbuf[cur ^ 1])[r] = make_float4(vo[0], vo[1], vo[2], vo[3]);
-        tbp += K / 4;
-        *tbp = packed;
+        tbp += TBROW;
+        *tbp = (uint16_t)packed;
         cur ^= 1;
         cp_async_wait0_v();                                          // the next row has landed (issued an event ago)
         __syncthreads();
@@ -383,16 +386,19 @@ viterbi_k1024_kernel(const float *__restrict__ post, long ld_t, long ld_b, const
     }
     // ---- backtrace (decode.py:84-91).  The walk itself is sequential (one thread), but each step would
     // be a dependent ~1 us HBM access; instead the whole CTA streams the traceback rows backwards in chunks
-    // of 8 events through shared memory (cp.async, next chunk in flight while this one is walked). ----
+    // of 16 events through shared memory (cp.async, next chunk in flight while this one is walked). ----
     {
-        constexpr int CH = 8;
+        constexpr int CH = 16;
+        constexpr int ROWB = TBROW * 2;                                    // bytes per traceback row
         // two 8 KB chunk buffers: vbuf (free now that v_T has been reduced) and tb_s2
         uint8_t *bufs[2] = {reinterpret_cast<uint8_t *>(&vbuf[0][0]), tb_s2};
         auto issue = [&](int hi, int which) {                              // rows (hi-CH, hi], clipped at 1
             uint8_t *dst = bufs[which];
-            for (int e = r; e < CH * (K / 16); e += 256) {
-                const int row = hi - e / (K / 16);
-                if (row >= 1) cp_async16_v(dst + (size_t)e * 16, tbb + (size_t)row * K + (size_t)(e % (K / 16)) * 16);
+            for (int e = r; e < CH * (ROWB / 16); e += 256) {
+                const int row = hi - e / (ROWB / 16);
+                if (row >= 1)
+                    cp_async16_v(dst + (size_t)e * 16,
+                                 reinterpret_cast<const uint8_t *>(tbb + (size_t)row * TBROW) + (size_t)(e % (ROWB / 16)) * 16);
             }
             cp_async_commit_v();
         };
@@ -405,12 +411,13 @@ viterbi_k1024_kernel(const float *__restrict__ post, long ld_t, long ld_b, const
             cp_async_wait1_v();
             __syncthreads();
             if (r == 0) {
-                const uint8_t *src = bufs[which];
+                const uint16_t *src = reinterpret_cast<const uint16_t *>(bufs[which]);
                 int state = s_state, pos = s_best;
                 int32_t *out = path_out + (size_t)b * T;
                 for (int k = 0; k < CH && hi - k >= 1; k++) {
-                    const unsigned cd = src[k * K + state];
-                    if (cd != 0) {
+                    const unsigned e = src[k * TBROW + (state >> 2)];
+                    if ((e >> (state & 3)) & 1u) {
+                        const unsigned cd = e >> 4;
                         state = cd <= 4u ? (int)(cd - 1) * RS + (state >> 2) : (int)(cd - 5) * RK + (state >> 4);
                         out[--pos] = state;
                     }
@@ -451,6 +458,8 @@ static bool ipow_ok(int nbase, int klen, long *K)
     return true;
 }
 
+static bool use_k1024(int nbase, long K) { return nbase == 4 && K == 1024 && !getenv("SLOIKA_B200_VITERBI_GENERIC"); }
+
 }  // namespace sloika
 
 using namespace sloika;
@@ -459,6 +468,8 @@ extern "C" size_t sloika_viterbi_workspace_bytes(int T, int B, int nbase, int kl
 {
     long K;
     if (T < 0 || B < 0 || nbase < 2 || klen < 1 || !ipow_ok(nbase, klen, &K)) return 0;
+    // K = 1024 kernel: one uint16 per quad of states; generic kernel: one byte per state
+    if (use_k1024(nbase, K)) return (size_t)T * (size_t)B * (size_t)(K / 2);
     return (size_t)T * (size_t)B * (size_t)K;
 }
 
@@ -483,7 +494,7 @@ extern "C" int sloika_viterbi_fwd(const float *post, long ld_t, long ld_b, const
     long threads = K / nbase;
     threads = threads > 256 ? 256 : (threads < 32 ? 32 : ceil_div(threads, 32) * 32);
     cudaError_t err;
-    if (nbase == 4 && K == 1024 && !getenv("SLOIKA_B200_VITERBI_GENERIC")) {
+    if (use_k1024(nbase, K)) {
         if (mode == SLOIKA_VIT_POST)
             viterbi_k1024_kernel<IN_POST><<<B, 256, 0, st>>>(post, ld_t, ld_b, nullptr, 0, lengths, T, B, sp, c0, c1,
                                                               (uint8_t *)tb_ws, path_out, path_len, score_out);

@@ -124,6 +124,44 @@ def test_gru(I, H, T, B, reverse):
     assert np.abs(got - ref).max() < 5e-5
 
 
+@pytest.mark.parametrize('env', [{'SLOIKA_B200_GRU': 'v1'}, {'SLOIKA_B200_GRU': 'v3'}, {'SLOIKA_B200_GRU': 'v4'},
+                                 {'SLOIKA_B200_GRU_TC': '8,1'}, {'SLOIKA_B200_GRU_TC': '8,2'},
+                                 {'SLOIKA_B200_GRU_TC': '16,1'}, {'SLOIKA_B200_GRU_TC': '16,2'}])
+@pytest.mark.parametrize('I,H,T,B,reverse', [(96, 96, 90, 37, False), (40, 110, 50, 21, True), (20, 128, 40, 9, False),
+                                             (24, 48, 30, 50, True)])
+def test_gru_every_kernel_generation(env, I, H, T, B, reverse, monkeypatch):
+    """Each selectable recurrence kernel -- FFMA2 (v1), 3xTF32 mma.sync (v3), fp16x3 mma.sync (v4) and every
+    (sequences per group, groups per CTA) shape of the tcgen05 / tensor-memory kernel -- against the oracle, with a
+    ragged batch whose size is not a multiple of any CTA tile."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    np.random.seed(H + B)
+    g = layers.Gru(I, H, init=_init(), has_bias=True)
+    g.sW.set_value(g.sW.get_value() * 5)
+    g.sW2.set_value(g.sW2.get_value() * 5)
+    layer = layers.Reverse(g) if reverse else g
+    lengths = [int(v) for v in np.random.randint(1, T + 1, size=B)]
+    lengths[0] = T
+    x = np.tanh(np.random.standard_normal((T, B, I))).astype(np.float32)
+    got, _ = _run(layer, x, lengths)
+    for b in list(range(0, B, 5)) + [B - 1]:
+        n = lengths[b]
+        ref = _oracle(layer, x[:n, b:b + 1])
+        assert np.abs(got[:n, b] - ref[:, 0]).max() < 5e-5, (env, b)
+        assert np.all(got[n:, b] == 0)
+
+
+def test_gru_other_activation_pair_takes_the_generic_kernel():
+    """A GRU whose activations are not tanh / sigmoid (any `fun` / `gatefun` the constructor accepts, layers.py:965)
+    runs on the FFMA2 kernel of gru.cu."""
+    np.random.seed(4)
+    g = layers.Gru(12, 40, init=_init(), has_bias=True, fun=act.sigmoid, gatefun=act.tanh)
+    x = np.tanh(np.random.standard_normal((30, 6, 12))).astype(np.float32)
+    got = _run(g, x)[0]
+    ref = _oracle(g, x)
+    assert np.abs(got - ref).max() < 5e-5
+
+
 def test_gru_ragged_equals_per_read():
     np.random.seed(11)
     for reverse in (False, True):
@@ -573,11 +611,15 @@ def test_cuda_path_matches_reference_outputs(forward_cases):
     on bounded hidden activations, 2e-5 relative on elu outputs."""
     from conftest import case_weights
     meta, data = forward_cases
-    ran = 0
+    ran, bad = 0, []
     for case in meta:
         name = case['name']
         assert _types(case['arch']) <= _SUPPORTED, name
-        net = zoo.from_weights(case['arch'], case_weights(data, name))
+        try:
+            net = zoo.from_weights(case['arch'], case_weights(data, name))
+        except NotImplementedError as err:
+            bad.append((name, repr(err)))
+            continue
         x = data[name + '/x']
         ref = data[name + '/y']
         got = net.compile()(x)
@@ -586,8 +628,11 @@ def test_cuda_path_matches_reference_outputs(forward_cases):
             continue
         err = np.abs(got - ref)
         if name.startswith('model_') or name.startswith('softmax'):
-            assert err.max() < 1e-4, (name, float(err.max()))
+            ok = err.max() < 1e-4
         else:
-            assert (err <= 2e-5 + 2e-5 * np.abs(ref)).all(), (name, float(err.max()))
+            ok = (err <= 2e-5 + 2e-5 * np.abs(ref)).all()
+        if not ok:
+            bad.append((name, float(err.max())))
         ran += 1
+    assert not bad, bad
     assert ran >= 40
