@@ -43,6 +43,8 @@ def parse_args():
     ap.add_argument('--cpu-sample-chunks', type=int, default=None,
                     help='chunks in the bounded CPU sample (default: 384 once for cpu_baseline, 32 per step for --impl reference)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--in-flight', type=int, default=4,
+                    help='batches pipelined on separate CUDA streams (1 = one batch after the other)')
     return ap.parse_args()
 
 
@@ -243,6 +245,10 @@ def run_b200_arm(args):
     x_host = torch.randn((T, B, 1), generator=gen, dtype=torch.float32).pin_memory()
     x_dev = x_host.to(dev)
     samples_per_step = T * B
+    K = max(1, args.in_flight)
+    calc_post.prepare()
+    main = torch.cuda.current_stream(dev)
+    streams = basecall._pipeline_streams(dev, K)       # the streams the public API pipelines on (warm allocator pools)
 
     def step_device():
         out = calc_post.forward_device(x_dev, fused_decode=True)
@@ -251,10 +257,10 @@ def run_b200_arm(args):
     def run_e2e(steps):
         """`steps` batches through the public host-buffer API (`basecall.basecall_chunk_stream`): every batch is copied
         from pinned host memory to the device and its scores / paths / lengths are copied back, all inside the timed
-        region; the copies of neighbouring batches overlap the kernels (software pipeline of depth 2)."""
+        region; `in_flight` batches are pipelined, each on its own stream."""
         res = None
         for res in basecall.basecall_chunk_stream((x_host for _ in range(steps)), kmer_len=5, min_prob=1e-5, skip=0.0,
-                                                  network=calc_post):
+                                                  network=calc_post, in_flight=K):
             pass
         return res
 
@@ -271,37 +277,54 @@ def run_b200_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    def timed(step_fn, steps):
+    def timed(steps, in_flight):
+        """`steps` batches, `in_flight` of them pipelined: batch i runs on stream i % in_flight.  Device time from an
+        event all streams wait on to an event that waits on all streams."""
         start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        engine.set_batches_in_flight(in_flight)
         barrier()
-        wall0 = time.perf_counter()
-        start.record()
-        for _ in range(steps):
-            res = step_fn()
-        end.record()
+        start.record(main)
+        use = streams[:in_flight]
+        for st in use:
+            st.wait_event(start)
+        res = None
+        for i in range(steps):
+            with torch.cuda.stream(use[i % in_flight]):
+                res = step_device()
+        for st in use:
+            main.wait_stream(st)
+        end.record(main)
         barrier()
-        wall = (time.perf_counter() - wall0) * 1e3
-        return start.elapsed_time(end), wall, res
+        return start.elapsed_time(end), res
 
-    # ---- warm-up ----
-    for _ in range(max(args.warmup, 3)):
-        res = step_device()
-    barrier()
+    # ---- warm-up (every stream: allocator pools, kernel attributes) ----
+    timed(max(args.warmup, 3) * K, K)
 
-    # ---- device-resident timing (value) with per-kernel events ----
+    # ---- device-resident timing (value); per-kernel events are recorded on the launching streams ----
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
     engine.TIMER.reset()
     engine.TIMER.enabled = True
-    ms_dev, _, res = timed(step_device, args.steps)
+    ms_dev, res = timed(args.steps, K)
     engine.TIMER.enabled = False
     launches = engine.TIMER.launches
     kernel_ms = engine.TIMER.totals_ms()
     ms_dev = max_over_ranks(ms_dev)
 
+    # ---- the same step alone on the device (one batch in flight): latency of a batch, per-kernel times undisturbed ----
+    iso_steps = min(args.steps, 5)
+    timed(2, 1)
+    engine.TIMER.reset()
+    engine.TIMER.enabled = True
+    ms_single, _ = timed(iso_steps, 1)
+    engine.TIMER.enabled = False
+    kernel_ms_single = engine.TIMER.totals_ms()
+    ms_single = max_over_ranks(ms_single) / iso_steps
+    engine.set_batches_in_flight(K)
+
     # ---- end-to-end timing through the host-buffer API (e2e): H2D + D2H inside, wall clock on host ----
-    run_e2e(2)
+    run_e2e(2 * K)
     barrier()
     wall0 = time.perf_counter()
     res_e2e = run_e2e(args.steps)
@@ -336,11 +359,15 @@ def run_b200_arm(args):
     alg_by_kernel = {'conv1d': alg.get('conv1d', 0.0), 'gru_recurrence': alg.get('gru_layer', 0.0),
                      'gru_projection': 0.0, 'feedforward': alg.get('feedforward', 0.0),
                      'softmax': alg.get('softmax', 0.0), 'viterbi': alg.get('viterbi', 0.0)}
-    breakdown = {}
-    for name, (ms, calls) in kernel_ms.items():
-        nbytes = alg_by_kernel.get(name, 0.0) * samples_per_step * args.steps
-        breakdown[name] = {"ms_per_step": ms / args.steps, "calls_per_step": calls / args.steps,
-                           "algorithmic_GBps": (nbytes / (ms * 1e-3) / 1e9) if ms > 0 else None}
+    def table(kms, steps):
+        out = {}
+        for name, (ms, calls) in kms.items():
+            nbytes = alg_by_kernel.get(name, 0.0) * samples_per_step * steps
+            out[name] = {"ms_per_step": ms / steps, "calls_per_step": calls / steps,
+                         "algorithmic_GBps": (nbytes / (ms * 1e-3) / 1e9) if ms > 0 else None}
+        return out
+    breakdown = table(kernel_ms, args.steps)               # spans inside the pipelined region: they overlap each other
+    breakdown_single = table(kernel_ms_single, iso_steps)  # one batch in flight: undisturbed durations
     dominant = max(kernel_ms, key=lambda k: kernel_ms[k][0])
     dom_ms, dom_calls = kernel_ms[dominant]
     dom_bytes_per_launch = alg_by_kernel.get(dominant, 0.0) * samples_per_step * args.steps / dom_calls
@@ -348,14 +375,24 @@ def run_b200_arm(args):
     traffic = None
     try:
         if args.workload == 'raw_rgrgr' and B == BATCH_PER_GPU and T == CHUNK_LEN:
-            with open(os.path.join(ROOT, 'profiles', 'r1j_traffic.json')) as fh:
+            with open(os.path.join(ROOT, 'profiles', 'r2_traffic.json')) as fh:
                 traffic = json.load(fh).get(dominant)
     except Exception:
         traffic = None
     roofline = {"kernel": dominant, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peaks_src,
                 "algorithmic_bytes_per_launch": dom_bytes_per_launch,
-                "avg_launch_ms": dom_ms / dom_calls, "share_of_step": dom_ms / (ms_dev if world == 1 else sum(v[0] for v in kernel_ms.values()))}
+                "avg_launch_ms": dom_ms / dom_calls,
+                "share_of_kernel_time": dom_ms / sum(v[0] for v in kernel_ms.values())}
+    if 'gru_recurrence' in kernel_ms_single:
+        # the recurrence is bound by the latency of its dependent steps, not by HBM: say so on the line
+        net_layers = [l for l in getattr(net, 'layers', [])]
+        rec_ms, rec_calls = kernel_ms_single['gru_recurrence']
+        steps_per_launch = T // stride_of(net)
+        roofline["latency"] = {"kernel": "gru_recurrence", "us_per_time_step_one_batch": 1e3 * rec_ms / rec_calls / steps_per_launch,
+                               "us_per_time_step_pipelined": 1e3 * kernel_ms['gru_recurrence'][0] / kernel_ms['gru_recurrence'][1] / steps_per_launch,
+                               "time_steps_per_launch": steps_per_launch,
+                               "ncu": "profiles/r2_step_kernels_ncu.txt (warps active, issue active, tensor pipe)"}
     total_alg = sum(alg.values())
     paper = min(hbm_peak * 1e9 / total_alg, float(peaks.get('bf16_tflops_sustained', 1400.0)) * 1e12 / flops_per_sample(net))
 
@@ -372,6 +409,7 @@ def run_b200_arm(args):
         "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args), "chunks_per_gpu": B, "chunk_len": T, "stride": stride_of(net),
+                   "batches_in_flight": K, "value_excludes_h2d": True,
                    "sharding": "reads x{} (no collective)".format(world),
                    "l2": "working set per step (posteriors {:.2f} GB) exceeds L2; no flush needed".format(
                        4.0 * net.size * (T // stride_of(net)) * B / 1e9)},
@@ -380,6 +418,8 @@ def run_b200_arm(args):
         "gpu_launches": launches * world,          # kernels of this repo enqueued in the timed region, all ranks
         "roofline": roofline,
         "kernels": breakdown,
+        "single_batch": {"ms_per_step": ms_single, "value": samples_per_step * world / (ms_single * 1e-3),
+                         "kernels": breakdown_single},
         "paper_roofline_samples_per_s": paper,
         "frac_of_paper_roofline": value / world / paper,
         "cpu_baseline": cpu_baseline,

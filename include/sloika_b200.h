@@ -48,6 +48,11 @@ const char *sloika_b200_strerror(int code);
 /* Number of SMs / compute capability of the current device (host call, no kernel). */
 int sloika_b200_device_info(int *sm_count, int *cc_major, int *cc_minor);
 
+/* Scheduling option (process wide, not a numerical one): the largest number of SMs a tensor-core GEMM launch
+ * (sloika_linear_fwd*, sloika_softmax_logits_fwd, the projection inside sloika_gru_fwd) may occupy; 0 = all.  A caller
+ * that pipelines several batches on different streams sets it to the SMs its recurrence kernels leave free. */
+int sloika_b200_set_gemm_sm_budget(int sms);
+
 /*
  * Convolution.run  -- sloika/layers.py:417-419, sloika/conv.py:66-111
  *   y[t,b,o] = act( bias[o] + sum_i sum_k W[o,i,k] * xpad[t*stride + k, b, i] )

@@ -185,63 +185,83 @@ def basecall_chunks(x_host, kmer_len=5, min_prob=1e-5, skip=0.0, nbase=4, networ
     return score.cpu().numpy(), paths.cpu().numpy(), plen.cpu().numpy()
 
 
-def basecall_chunk_stream(batches, kmer_len=5, min_prob=1e-5, skip=0.0, nbase=4, network=None):
-    """`basecall_chunks` over a stream of host batches, software-pipelined: the host->device copy of batch k+1 and
-    the device->host copy of batch k-1's results run on their own CUDA streams while the kernels of batch k execute.
+_PIPELINE_STREAMS = {}        # device -> CUDA streams of the batch pipeline, kept so that their allocator pools stay warm
+
+
+def _pipeline_streams(dev, n):
+    import torch
+    have = _PIPELINE_STREAMS.setdefault(str(dev), [])
+    while len(have) < n:
+        have.append(torch.cuda.Stream(dev))
+    return have[:n]
+
+
+def basecall_chunk_stream(batches, kmer_len=5, min_prob=1e-5, skip=0.0, nbase=4, network=None, in_flight=4):
+    """`basecall_chunks` over a stream of host batches with `in_flight` batches on the device at once, each on its
+    own CUDA stream: its host->device copy, its kernels and the device->host copy of its results are ordered on that
+    stream, and the streams overlap one another -- copies under kernels, and the latency-bound recurrence kernels
+    (a batch of 1024 chunks occupies a quarter to a half of the SMs, `csrc/gru_tc.cu`) beside the bandwidth-bound
+    GEMM / Viterbi kernels of the neighbouring batches.
 
     :param batches: iterable of float32 torch CPU tensors `[T, B]` / `[T, B, 1]` (pinned memory for real overlap)
+    :param in_flight: number of batches pipelined (1 = strictly one after the other)
     :returns: generator of (scores float32[B], paths int32[B, T'], path_len int32[B]) NumPy arrays, in input order
     """
+    import collections
     import torch
+    from sloika_b200 import engine
     net = network if network is not None else calc_post
     if net is None:
         raise RuntimeError("init_worker() has not been called")
     dev = net.device
-    compute = torch.cuda.current_stream(dev)
-    h2d, d2h = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-    x_dev = [None, None]
-    compute_done = [None, None]            # event: kernels of the batch that last used input buffer k % 2 have finished
-    pending = None                         # (host result tensors, copy-out event, device tensors kept alive)
+    in_flight = max(1, int(in_flight))
+    net.prepare()
+    streams = _pipeline_streams(dev, in_flight)
+    x_dev = [None] * in_flight
+    host_bufs = [None] * in_flight         # pinned result buffers of a slot, reused (cudaHostAlloc synchronises the device)
+    pending = collections.deque()          # (host result tensors, copy-out event, device tensors kept alive)
+    caller = torch.cuda.current_stream(dev)
+    ready = torch.cuda.Event()
+    ready.record(caller)
 
     def finish(item):
         host, ev, _keep = item
         ev.synchronize()
-        return tuple(t.numpy() for t in host)
+        return tuple(t.numpy().copy() for t in host)            # the pinned buffers go back to their slot
 
-    for k, xh in enumerate(batches):
-        if xh.dim() == 2:
-            xh = xh.unsqueeze(2)
-        slot = k % 2
-        with torch.cuda.stream(h2d):
-            if compute_done[slot] is not None:
-                h2d.wait_event(compute_done[slot])          # the buffer's previous batch has been consumed
-            if x_dev[slot] is None or x_dev[slot].shape != xh.shape:
-                x_dev[slot] = torch.empty(xh.shape, dtype=torch.float32, device=dev)
-            x_dev[slot].copy_(xh, non_blocking=True)
-            copied = torch.cuda.Event()
-            copied.record(h2d)
-        compute.wait_event(copied)
-        out = net.forward_device(x_dev[slot], fused_decode=(kmer_len == 5 and nbase == 4))
-        res = decode.viterbi_batch(out, None, klen=kmer_len, skip_pen=skip, min_prob=min_prob, nbase=nbase,
-                                   return_device=True)
-        done = torch.cuda.Event()
-        done.record(compute)
-        compute_done[slot] = done
-        with torch.cuda.stream(d2h):
-            d2h.wait_event(done)
-            host = []
-            for t in res:
-                t.record_stream(d2h)
-                buf = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-                buf.copy_(t, non_blocking=True)
-                host.append(buf)
-            out_ev = torch.cuda.Event()
-            out_ev.record(d2h)
-        if pending is not None:
-            yield finish(pending)                           # batch k-1, while batch k runs
-        pending = (host, out_ev, res)
-    if pending is not None:
-        yield finish(pending)
+    saved = engine.BATCHES_IN_FLIGHT
+    engine.set_batches_in_flight(in_flight)
+    try:
+        for k, xh in enumerate(batches):
+            if xh.dim() == 2:
+                xh = xh.unsqueeze(2)
+            slot = k % in_flight
+            if len(pending) == in_flight:
+                yield finish(pending.popleft())                 # the batch that last used this stream and buffer
+            st = streams[slot]
+            with torch.cuda.stream(st):
+                if k < in_flight:
+                    st.wait_event(ready)                        # work the caller enqueued before us
+                if x_dev[slot] is None or x_dev[slot].shape != xh.shape:
+                    x_dev[slot] = torch.empty(xh.shape, dtype=torch.float32, device=dev)
+                x_dev[slot].copy_(xh, non_blocking=True)
+                out = net.forward_device(x_dev[slot], fused_decode=(kmer_len == 5 and nbase == 4))
+                res = decode.viterbi_batch(out, None, klen=kmer_len, skip_pen=skip, min_prob=min_prob, nbase=nbase,
+                                           return_device=True)
+                if host_bufs[slot] is None or any(b.shape != t.shape for b, t in zip(host_bufs[slot], res)):
+                    host_bufs[slot] = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in res]
+                host = host_bufs[slot]
+                for buf, t in zip(host, res):
+                    buf.copy_(t, non_blocking=True)
+                out_ev = torch.cuda.Event()
+                out_ev.record(st)
+            pending.append((host, out_ev, res))
+        while pending:
+            yield finish(pending.popleft())
+    finally:
+        engine.set_batches_in_flight(saved)
+        for st in streams:
+            caller.wait_stream(st)
 
 
 def _read_raw(fast5_file_name):

@@ -29,3 +29,12 @@ extern "C" int sloika_b200_device_info(int *sm_count, int *cc_major, int *cc_min
     if (cc_minor) *cc_minor = prop.minor;
     return SLOIKA_OK;
 }
+
+namespace sloika { namespace gemm_tc { extern int sm_budget; } }
+
+extern "C" int sloika_b200_set_gemm_sm_budget(int sms)
+{
+    if (sms < 0) return SLOIKA_ERR_ARG;
+    sloika::gemm_tc::sm_budget = sms;
+    return SLOIKA_OK;
+}

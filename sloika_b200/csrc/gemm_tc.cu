@@ -34,6 +34,8 @@ namespace sloika {
 
 namespace gemm_tc {
 
+int sm_budget = 0;                 // 0 = all SMs; set through sloika_b200_set_gemm_sm_budget()
+
 constexpr int BM = 128;            // rows per tile (UMMA M)
 constexpr int KB = 32;             // k elements per K block (one 128-byte swizzle row)
 constexpr int MAX_STAGES = 12;     // smem stages of x-tiles (as many as fit)
@@ -540,6 +542,10 @@ int launch(const float *x, long ldx, const float *W, const float *bias, float *y
     const char *dbg = getenv("SLOIKA_B200_GEMM_DBG");
     p.dbg = dbg ? atoi(dbg) : 0;
     const long m_tiles = (M + BM - 1) / BM;
+    // SM budget: a caller that pipelines several batches on different streams keeps part of the SMs busy with the
+    // long recurrence kernels (their CTAs own the tensor memory of their SM, so a GEMM CTA cannot share it);
+    // a grid no larger than the SMs that are free starts at once instead of queueing behind them.
+    if (sm_budget > 0 && sm_budget < sms) sms = sm_budget < n_slices ? n_slices : sm_budget;
     long per = sms / n_slices;
     if (per > m_tiles) per = m_tiles;
     p.ctas_per_slice = (int)per;

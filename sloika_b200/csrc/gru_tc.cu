@@ -49,19 +49,41 @@ __device__ __forceinline__ void wait_bar(uint64_t *bar, uint32_t parity) {
     }
 }
 
-template <int N>
-__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&r)[N]) {
-    if constexpr (N == 8) tmem_ld_32x32b_x8(taddr, r);
-    else tmem_ld_32x32b_x16(taddr, r);
+template <int NS>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&r)[NS]) {
+    if constexpr (NS == 8) tmem_ld_32x32b_x8(taddr, r);
+    else if constexpr (NS == 4) tmem_ld_32x32b_x4(taddr, r);
+    else tmem_ld_32x32b_x2(taddr, r);
 }
 
-// x -> fp16 hi (low half) | fp16 lo (high half): hi = x with the low 13 mantissa bits cleared (exactly representable
-// in fp16 for |x| in [2^-14, 65504]), lo = x - hi (exact), both converted by one packed cvt.  Below 2^-14 the fp16
+// Activations for the epilogue: MUFU ex2 / rcp in their flush-to-zero forms with no range fix-up code (4 and 5
+// instructions).  Saturation is by construction: ex2(+big) = inf -> rcp = 0, ex2(-big) = 0.  Absolute error ~1e-7;
+// Theano's hard 0 / 1 outside [-88, 15] (sigm.py) differs from the smooth value by < 3.1e-7.
+__device__ __forceinline__ float rcp_ftz(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float sigmoid_lean(float x) { return rcp_ftz(1.0f + ex2_ftz(x * -SLOIKA_LOG2E)); }
+__device__ __forceinline__ float tanh_lean(float x) { return fmaf(-2.0f, rcp_ftz(1.0f + ex2_ftz(x * (2.0f * SLOIKA_LOG2E))), 1.0f); }
+
+// (x0, x1) -> packed fp16 pairs hi = (hi0, hi1), lo = (lo0, lo1): hi_i = x_i with the low 13 mantissa bits cleared
+// (exactly representable in fp16 for |x| in [2^-14, 65504]), lo_i = x_i - hi_i (exact).  Below 2^-14 the fp16
 // subnormal rounding of hi is not compensated: an absolute error <= 2^-25, far under the fp32 noise of the sums.
-__device__ __forceinline__ uint32_t split_pack(float x) {
-    const float hi = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
-    const __half2 p = __floats2half2_rn(hi, x - hi);
-    return *reinterpret_cast<const uint32_t *>(&p);
+__device__ __forceinline__ void split_pair(float x0, float x1, uint32_t &hi, uint32_t &lo) {
+    const float h0 = __uint_as_float(__float_as_uint(x0) & 0xffffe000u);
+    const float h1 = __uint_as_float(__float_as_uint(x1) & 0xffffe000u);
+    const __half2 ph = __floats2half2_rn(h0, h1);
+    const __half2 pl = __floats2half2_rn(x0 - h0, x1 - h1);
+    hi = *reinterpret_cast<const uint32_t *>(&ph);
+    lo = *reinterpret_cast<const uint32_t *>(&pl);
+}
+
+template <int NS>
+__device__ __forceinline__ void store_halves(uint8_t *dst, const uint32_t (&w)[NS / 2]) {
+    if constexpr (NS == 8) *reinterpret_cast<uint4 *>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+    else if constexpr (NS == 4) *reinterpret_cast<uint2 *>(dst) = make_uint2(w[0], w[1]);
+    else *reinterpret_cast<uint32_t *>(dst) = w[0];
 }
 
 struct Bars {                 // per group
@@ -69,37 +91,40 @@ struct Bars {                 // per group
     uint64_t pad;
 };
 
-template <int HP, int N, int G>
-__global__ void __launch_bounds__(G * 160, 1)
+constexpr int N = 8;          // sequences per group = N of every MMA (one core matrix wide)
+
+// G groups of 8 sequences per CTA; CW compute warps per group (4: a thread owns unit j for all 8 sequences,
+// 8: for 4 of them, 16: for 2), one issuing warp per group.
+template <int HP, int G, int CW>
+__global__ void __launch_bounds__(G *(CW + 1) * 32, 1)
 gru_tc_kernel(const float *__restrict__ vI, long ldv, const float *__restrict__ sW, const float *__restrict__ sW2,
               float *__restrict__ y, long ldy, const int32_t *__restrict__ lengths, int T, int B, int H, int reverse)
 {
     constexpr int KC = HP / 16;                   // K = 16 chunks
-    constexpr int NKB = (HP + 31) / 32;           // K blocks of 32 halves (one 64-byte swizzle row each)
     constexpr int ACOLS = HP / 2;                 // TMEM columns of one A tile
     constexpr int D_BASE = 6 * ACOLS;             // accumulators behind the 6 weight tiles
-    constexpr int OPB = NKB * N * 64;             // bytes of one operand array (N sequences x K halves, swizzled)
-    constexpr int NCW = 4 * G;                    // compute warps
+    constexpr int OPB = HP * 16;                  // bytes of one operand array: [k][8 sequences] fp16, MN-major
+    constexpr int NCW = G * CW;                   // compute warps
+    constexpr int NS = N / (CW / 4);              // sequences per compute thread
+    constexpr int VLD = 3 * HP;                   // floats per staged vI row
+    constexpr int NTHREADS = G * (CW + 1) * 32;
     static_assert(D_BASE + G * 3 * N <= 512, "tensor memory: 512 columns");
-    static_assert(N == 8 || N == 16, "sequences per group");
+    static_assert(CW == 4 || CW == 8 || CW == 16, "compute warps per group");
 
     extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    const int vld = (3 * H + 3) / 4 * 4;                               // floats per staged vI row (16-byte multiple)
+    uint8_t *smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
     uint8_t *ops = smem;                                               // [G][4][OPB]: h hi, h lo, r*h hi, r*h lo
-    float *vring = reinterpret_cast<float *>(ops + (size_t)G * 4 * OPB);   // [G][3][N][vld]
-    Bars *bars = reinterpret_cast<Bars *>(vring + (size_t)G * 3 * N * vld);
-    int *lens_s = reinterpret_cast<int *>(bars + G);                   // [G][N]
-    uint32_t *tmem_base_s = reinterpret_cast<uint32_t *>(lens_s + G * N);
+    float *vring = reinterpret_cast<float *>(ops + (size_t)G * 4 * OPB);   // [G][3][N][VLD]
+    Bars *bars = reinterpret_cast<Bars *>(vring + (size_t)G * 3 * N * VLD);
+    uint32_t *tmem_base_s = reinterpret_cast<uint32_t *>(bars + G);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int nthreads = G * 160;
     const int b_cta = blockIdx.x * (G * N);
 
     // ---------------- prologue ----------------
     if (tid == 0) {
         for (int g = 0; g < G; g++) {
-            mbar_init(&bars[g].h, 128); mbar_init(&bars[g].rh, 128);
+            mbar_init(&bars[g].h, CW * 32); mbar_init(&bars[g].rh, CW * 32);
             mbar_init(&bars[g].d1, 1); mbar_init(&bars[g].d2, 1);
             for (int i = 0; i < 3; i++) mbar_init(&bars[g].v[i], 1);
         }
@@ -109,11 +134,7 @@ gru_tc_kernel(const float *__restrict__ vI, long ldv, const float *__restrict__ 
     {
         uint32_t *z = reinterpret_cast<uint32_t *>(smem);
         const int nz = (int)(((uint8_t *)bars - smem) / 4);
-        for (int e = tid; e < nz; e += nthreads) z[e] = 0u;
-    }
-    for (int e = tid; e < G * N; e += nthreads) {
-        const int bg = b_cta + e;
-        lens_s[e] = bg < B ? (lengths ? min(lengths[bg], T) : T) : 0;
+        for (int e = tid; e < nz; e += NTHREADS) z[e] = 0u;
     }
     fence_proxy_async();
     tc_fence_before();
@@ -123,10 +144,11 @@ gru_tc_kernel(const float *__restrict__ vI, long ldv, const float *__restrict__ 
 
     if (warp < NCW) {
         // weights -> TMEM (split once): lane = gate row j, tile 2m + p (m: z, r, candidate; p: hi, lo), chunk kc at
-        // columns kc*8 .. kc*8+7, column i = k pair (16kc + 2i, 16kc + 2i + 1).  Chunks are dealt over the groups.
-        const int q = warp & 3, j = 32 * q + lane, g = warp >> 2;
+        // columns kc*8 .. kc*8+7, column i = k pair (16kc + 2i, 16kc + 2i + 1).  Chunks are dealt over the warps
+        // that share a lane quarter.
+        const int q = warp & 3, j = 32 * q + lane;
         const uint32_t lane_addr = (uint32_t)(32 * q) << 16;
-        for (int c = g; c < 3 * KC; c += G) {
+        for (int c = warp >> 2; c < 3 * KC; c += NCW / 4) {
             const int m = c / KC, kc = c - m * KC;
             const float *row = m < 2 ? sW + (long)(m * H + j) * H : sW2 + (long)j * H;
             uint32_t hi[8], lo[8];
@@ -151,96 +173,92 @@ gru_tc_kernel(const float *__restrict__ vI, long ldv, const float *__restrict__ 
     tc_fence_after();
 
     if (warp < NCW) {
-        // ================= compute warps: thread = hidden unit j, N sequences =================
-        const int g = warp >> 2, q = warp & 3, j = 32 * q + lane;
+        // ================= compute warps: thread = hidden unit j, NS sequences =================
+        const int g = warp / CW, wg = warp - g * CW, q = wg & 3, j = 32 * q + lane;
+        const int n0 = (wg >> 2) * NS;                                     // first sequence of this thread
         const uint32_t lane_addr = (uint32_t)(32 * q) << 16;
-        const uint32_t dcol = tmem_base + lane_addr + (uint32_t)(D_BASE + g * 3 * N);
+        const uint32_t dcol = tmem_base + lane_addr + (uint32_t)(D_BASE + g * 3 * N + n0);
         Bars &bar = bars[g];
         const int b0 = b_cta + g * N;
-        uint8_t *op = ops + (size_t)g * 4 * OPB;
-        const float *vr0 = vring + (size_t)g * 3 * N * vld;
-        const int *lens = lens_s + g * N;
-        const bool jop = j < HP;                       // this unit has a k column in the operands
+        const bool jop = j < HP;                       // this unit has a k row in the operands
         const bool jv = j < H;
         const int jc = jv ? j : H - 1;                 // clamped column for vI reads of padding rows
-        // operand byte offsets of element (sequence n, k = j): sw64 layout, K block j >> 5
-        const int kk = j & 31;
-        const uint32_t obase = (uint32_t)((j >> 5) * (N * 64) + ((kk & 7) << 1));
-        uint32_t oswz[4];
+        uint8_t *op = ops + (size_t)g * 4 * OPB + (size_t)(jop ? j : 0) * 16 + n0 * 2;      // row k = j, sequences n0..
+        const float *vbase = vring + (size_t)g * 3 * N * VLD + n0 * VLD + jc;
+        int len[NS];
 #pragma unroll
-        for (int mth = 0; mth < 4; mth++) oswz[mth] = (uint32_t)((((kk >> 3) ^ mth) & 3) << 4);
-        float h[N];
+        for (int n = 0; n < NS; n++) {
+            const int bg = b0 + n0 + n;
+            len[n] = (jv && bg < B) ? (lengths ? min(lengths[bg], T) : T) : 0;
+        }
+        float h[NS];
 #pragma unroll
-        for (int n = 0; n < N; n++) h[n] = 0.0f;
-        float *yp = y + ((long)(reverse ? T - 1 : 0) * B + b0) * ldy + j;
+        for (int n = 0; n < NS; n++) h[n] = 0.0f;
+        float *yp = y + ((long)(reverse ? T - 1 : 0) * B + b0 + n0) * ldy + j;
         const long ystep = (long)(reverse ? -1 : 1) * B * ldy;
+        const bool live = b0 < B;                      // a group wholly past the batch end has no issuer either
 
-        if (b0 < B) mbar_arrive(&bar.h);               // completion 0: h_{-1} = 0 is in place
-        for (int s = 0; s < (b0 < B ? T : 0); s++) {      // a group wholly past the batch end has no issuer either
+        if (live) mbar_arrive(&bar.h);                 // completion 0: h_{-1} = 0 is in place
+        for (int s = 0; s < (live ? T : 0); s++) {
             const int t = reverse ? T - 1 - s : s;
-            const float *vrow = vr0 + (size_t)(s % 3) * N * vld;
+            const float *vrow = vbase + (size_t)(s % 3) * N * VLD;
             const uint32_t par = (uint32_t)(s & 1);
             // ---- phase 1: r (needed at once) and z pre-activations ----
+            wait_bar(&bar.v[s % 3], (uint32_t)((s / 3) & 1));
+            float vr[NS];
+#pragma unroll
+            for (int n = 0; n < NS; n++) vr[n] = vrow[n * VLD + H];
             wait_bar(&bar.d1, par);
             tc_fence_after();
-            uint32_t dr[N], dz[N];
-            tmem_ld_cols<N>(dcol + N, dr);
-            tmem_ld_cols<N>(dcol, dz);
+            uint32_t dr[NS], dz[NS];
+            tmem_ld_cols<NS>(dcol + N, dr);
+            tmem_ld_cols<NS>(dcol, dz);
             tmem_ld_wait();
-            wait_bar(&bar.v[s % 3], (uint32_t)((s / 3) & 1));
             if (jop) {
-                float vr[N];
+                float rh[NS];
 #pragma unroll
-                for (int n = 0; n < N; n++) vr[n] = vrow[n * vld + H + jc];
-                uint32_t pk[N];
+                for (int n = 0; n < NS; n++) rh[n] = sigmoid_lean(__uint_as_float(dr[n]) + vr[n]) * h[n];
+                uint32_t whi[NS / 2], wlo[NS / 2];
 #pragma unroll
-                for (int n = 0; n < N; n++) pk[n] = split_pack(sigmoid_fast(__uint_as_float(dr[n]) + vr[n]) * h[n]);
-#pragma unroll
-                for (int n = 0; n < N; n++) {
-                    const uint32_t o = obase + (uint32_t)((n >> 3) * 512 + (n & 7) * 64) + oswz[(n >> 1) & 3];
-                    *reinterpret_cast<uint16_t *>(op + 2 * OPB + o) = (uint16_t)(pk[n] & 0xffffu);
-                    *reinterpret_cast<uint16_t *>(op + 3 * OPB + o) = (uint16_t)(pk[n] >> 16);
-                }
+                for (int n = 0; n < NS; n += 2) split_pair(rh[n], rh[n + 1], whi[n / 2], wlo[n / 2]);
+                store_halves<NS>(op + 2 * OPB, whi);
+                store_halves<NS>(op + 3 * OPB, wlo);
             }
             fence_proxy_async();
             tc_fence_before();
             mbar_arrive(&bar.rh);
-            float z[N];
-            if (jop) {
+            float z[NS], vc[NS];
 #pragma unroll
-                for (int n = 0; n < N; n++) z[n] = sigmoid_fast(__uint_as_float(dz[n]) + vrow[n * vld + jc]);
+            for (int n = 0; n < NS; n++) {
+                z[n] = sigmoid_lean(__uint_as_float(dz[n]) + vrow[n * VLD]);
+                vc[n] = vrow[n * VLD + 2 * H];
             }
             // ---- phase 2: candidate, blend, publish h_t ----
             wait_bar(&bar.d2, par);
             tc_fence_after();
-            uint32_t dc[N];
-            tmem_ld_cols<N>(dcol + 2 * N, dc);
+            uint32_t dc[NS];
+            tmem_ld_cols<NS>(dcol + 2 * N, dc);
             tmem_ld_wait();
+#pragma unroll
+            for (int n = 0; n < NS; n++) {
+                const float hbar = tanh_lean(__uint_as_float(dc[n]) + vc[n]);
+                const float hn = z[n] * h[n] + (1.0f - z[n]) * hbar;
+                h[n] = t < len[n] ? hn : 0.0f;                   // ragged batch: state stays 0 outside the read
+            }
             if (jop) {
-                float vc[N];
+                uint32_t whi[NS / 2], wlo[NS / 2];
 #pragma unroll
-                for (int n = 0; n < N; n++) vc[n] = vrow[n * vld + 2 * H + jc];
-#pragma unroll
-                for (int n = 0; n < N; n++) {
-                    const float hbar = tanh_fast(__uint_as_float(dc[n]) + vc[n]);
-                    const float hn = z[n] * h[n] + (1.0f - z[n]) * hbar;
-                    h[n] = (jv && t < lens[n]) ? hn : 0.0f;          // ragged batch: state stays 0 outside the read
-                }
-#pragma unroll
-                for (int n = 0; n < N; n++) {
-                    const uint32_t pk = split_pack(h[n]);
-                    const uint32_t o = obase + (uint32_t)((n >> 3) * 512 + (n & 7) * 64) + oswz[(n >> 1) & 3];
-                    *reinterpret_cast<uint16_t *>(op + o) = (uint16_t)(pk & 0xffffu);
-                    *reinterpret_cast<uint16_t *>(op + OPB + o) = (uint16_t)(pk >> 16);
-                }
+                for (int n = 0; n < NS; n += 2) split_pair(h[n], h[n + 1], whi[n / 2], wlo[n / 2]);
+                store_halves<NS>(op, whi);
+                store_halves<NS>(op + OPB, wlo);
             }
             fence_proxy_async();
             tc_fence_before();
             mbar_arrive(&bar.h);
             if (jv) {
 #pragma unroll
-                for (int n = 0; n < N; n++)
-                    if (b0 + n < B) yp[(long)n * ldy] = h[n];
+                for (int n = 0; n < NS; n++)
+                    if (b0 + n0 + n < B) yp[(long)n * ldy] = h[n];
             }
             yp += ystep;
         }
@@ -251,20 +269,20 @@ gru_tc_kernel(const float *__restrict__ vI, long ldv, const float *__restrict__ 
         const int b0 = b_cta + g * N;
         const int nrows = min(N, B - b0);                                  // sequences of this group that exist
         const uint32_t op = smem_u32(ops + (size_t)g * 4 * OPB);
-        float *vr0 = vring + (size_t)g * 3 * N * vld;
-        const uint32_t idesc = umma_idesc_f16_m128(N);
+        float *vr0 = vring + (size_t)g * 3 * N * VLD;
+        const uint32_t idesc = umma_idesc_f16_m128_bmn(N);
         const uint32_t dz = tmem_base + (uint32_t)(D_BASE + g * 3 * N), dr = dz + N, dc = dz + 2 * N;
-        const uint64_t b_hh = umma_desc_sw64_kmajor(op), b_hl = umma_desc_sw64_kmajor(op + OPB);
-        const uint64_t b_rh = umma_desc_sw64_kmajor(op + 2 * OPB), b_rl = umma_desc_sw64_kmajor(op + 3 * OPB);
-        const uint32_t rowbytes = (uint32_t)vld * 4u;
+        const uint64_t b_hh = umma_desc_mn8_noswizzle(op), b_hl = umma_desc_mn8_noswizzle(op + OPB);
+        const uint64_t b_rh = umma_desc_mn8_noswizzle(op + 2 * OPB), b_rl = umma_desc_mn8_noswizzle(op + 3 * OPB);
+        const uint32_t rowbytes = (uint32_t)((3 * H + 3) / 4 * 4) * 4u;     // <= ldv * 4: vI rows are 16-byte multiples
         auto load_vi = [&](int st) {                                       // elected lane: vI rows of scan step st
-            if (st >= T || nrows <= 0) return;
+            if (st >= T) return;
             const int t = reverse ? T - 1 - st : st;
             uint64_t *vb = &bar.v[st % 3];
             mbar_arrive_expect_tx(vb, rowbytes * (uint32_t)nrows);
             const float *src = vI + ((long)t * B + b0) * ldv;
-            float *dst = vr0 + (size_t)(st % 3) * N * vld;
-            for (int n = 0; n < nrows; n++) bulk_load_1d(dst + (size_t)n * vld, src + (long)n * ldv, rowbytes, vb);
+            float *dst = vr0 + (size_t)(st % 3) * N * VLD;
+            for (int n = 0; n < nrows; n++) bulk_load_1d(dst + (size_t)n * VLD, src + (long)n * ldv, rowbytes, vb);
         };
         if (nrows > 0) {
             if (elect_one()) { load_vi(0); load_vi(1); load_vi(2); }
@@ -276,14 +294,14 @@ gru_tc_kernel(const float *__restrict__ vI, long ldv, const float *__restrict__ 
                 if (elect_one()) {
 #pragma unroll
                     for (int kc = 0; kc < KC; kc++) {
-                        const uint64_t koff = (uint64_t)(((kc >> 1) * (N * 64) + (kc & 1) * 32) >> 4);
+                        const uint64_t koff = (uint64_t)(kc * 16);         // 256 bytes per K = 16 step
                         const uint32_t acol = tmem_base + (uint32_t)(kc * 8);
-                        umma_f16_ts(dz, acol + 0 * ACOLS, b_hh + koff, idesc, kc != 0);
                         umma_f16_ts(dr, acol + 2 * ACOLS, b_hh + koff, idesc, kc != 0);
-                        umma_f16_ts(dz, acol + 1 * ACOLS, b_hh + koff, idesc, true);
+                        umma_f16_ts(dz, acol + 0 * ACOLS, b_hh + koff, idesc, kc != 0);
                         umma_f16_ts(dr, acol + 3 * ACOLS, b_hh + koff, idesc, true);
-                        umma_f16_ts(dz, acol + 0 * ACOLS, b_hl + koff, idesc, true);
+                        umma_f16_ts(dz, acol + 1 * ACOLS, b_hh + koff, idesc, true);
                         umma_f16_ts(dr, acol + 2 * ACOLS, b_hl + koff, idesc, true);
+                        umma_f16_ts(dz, acol + 0 * ACOLS, b_hl + koff, idesc, true);
                     }
                     umma_commit(&bar.d1);
                     if (s >= 1) load_vi(s + 2);                            // slot (s-1) % 3 was released by step s-1
@@ -294,7 +312,7 @@ gru_tc_kernel(const float *__restrict__ vI, long ldv, const float *__restrict__ 
                 if (elect_one()) {
 #pragma unroll
                     for (int kc = 0; kc < KC; kc++) {
-                        const uint64_t koff = (uint64_t)(((kc >> 1) * (N * 64) + (kc & 1) * 32) >> 4);
+                        const uint64_t koff = (uint64_t)(kc * 16);
                         const uint32_t acol = tmem_base + (uint32_t)(kc * 8);
                         umma_f16_ts(dc, acol + 4 * ACOLS, b_rh + koff, idesc, kc != 0);
                         umma_f16_ts(dc, acol + 5 * ACOLS, b_rh + koff, idesc, true);
@@ -311,53 +329,54 @@ gru_tc_kernel(const float *__restrict__ vI, long ldv, const float *__restrict__ 
     if (warp == NCW) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
-template <int HP, int N, int G>
+template <int HP, int G, int CW>
 static int launch(const float *vI, long ldv, const float *sW, const float *sW2, float *y, long ldy, const int32_t *lengths,
                   int T, int B, int H, int reverse, cudaStream_t st)
 {
-    constexpr int NKB = (HP + 31) / 32, OPB = NKB * N * 64;
-    const int vld = (3 * H + 3) / 4 * 4;
-    size_t smem = 1024 + (size_t)G * 4 * OPB + (size_t)G * 3 * N * vld * 4 + (size_t)G * sizeof(Bars) + (size_t)G * N * 4 + 64;
+    size_t smem = 128 + (size_t)G * 4 * HP * 16 + (size_t)G * 3 * N * 3 * HP * 4 + (size_t)G * sizeof(Bars) + 64;
     // every CTA of this kernel owns the whole tensor memory of its SM: ask for more than half of the shared memory
     // so that a second one (another stream's batch) is placed on a free SM instead of stalling in tcgen05.alloc
     if (smem < 116 * 1024) smem = 116 * 1024;
-    auto kern = gru_tc_kernel<HP, N, G>;
+    auto kern = gru_tc_kernel<HP, G, CW>;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return (int)err;
     const unsigned grid = (unsigned)ceil_div(B, G * N);
-    kern<<<grid, G * 160, smem, st>>>(vI, ldv, sW, sW2, y, ldy, lengths, T, B, H, reverse);
+    kern<<<grid, G *(CW + 1) * 32, smem, st>>>(vI, ldv, sW, sW2, y, ldy, lengths, T, B, H, reverse);
     SLOIKA_RETURN_LAUNCH_STATUS();
 }
 
 template <int HP>
-static int launch_hp(int n, int g, const float *vI, long ldv, const float *sW, const float *sW2, float *y, long ldy,
+static int launch_hp(int g, int cw, const float *vI, long ldv, const float *sW, const float *sW2, float *y, long ldy,
                      const int32_t *lengths, int T, int B, int H, int reverse, cudaStream_t st)
 {
-    if (n == 8 && g == 1) return launch<HP, 8, 1>(vI, ldv, sW, sW2, y, ldy, lengths, T, B, H, reverse, st);
-    if (n == 8 && g == 2) return launch<HP, 8, 2>(vI, ldv, sW, sW2, y, ldy, lengths, T, B, H, reverse, st);
-    if (n == 16 && g == 1) return launch<HP, 16, 1>(vI, ldv, sW, sW2, y, ldy, lengths, T, B, H, reverse, st);
-    if (n == 16 && g == 2) return launch<HP, 16, 2>(vI, ldv, sW, sW2, y, ldy, lengths, T, B, H, reverse, st);
+#define TC_SHAPE(G_, CW_) \
+    if (g == G_ && cw == CW_) return launch<HP, G_, CW_>(vI, ldv, sW, sW2, y, ldy, lengths, T, B, H, reverse, st)
+    TC_SHAPE(1, 4); TC_SHAPE(1, 8); TC_SHAPE(1, 16);
+    TC_SHAPE(2, 4); TC_SHAPE(2, 8);
+    if constexpr (3 * HP + 4 * 24 <= 512) { TC_SHAPE(4, 4); }
+#undef TC_SHAPE
     return SLOIKA_ERR_UNSUPPORTED;
 }
 
 // tanh / sigmoid GRUs with H <= 128 whose vI rows are 16-byte aligned; SLOIKA_ERR_UNSUPPORTED otherwise (the caller
 // falls back to gru_h16.cu).  `seqs_in_flight` is the number of sequences the caller keeps on the device at once
-// (this batch times the batches it pipelines on other streams): it picks how many sequences share a CTA, i.e.
-// whether the SMs are spread over one batch (latency) or packed (throughput).  SLOIKA_B200_GRU_TC="N,G" overrides.
+// (this batch times the batches it pipelines on other streams): it picks how many groups of 8 sequences share a
+// CTA, i.e. whether the SMs are spread over one batch (latency) or packed (throughput).
+// SLOIKA_B200_GRU_TC="G,CW" overrides (groups per CTA, compute warps per group).
 int dispatch(const float *vI, long ldv, const float *sW, const float *sW2, float *y, long ldy, const int32_t *lengths, int T,
              int B, int H, int reverse, int act, int gate_act, long seqs_in_flight, cudaStream_t st)
 {
     if (act != SLOIKA_ACT_TANH || gate_act != SLOIKA_ACT_SIGMOID) return SLOIKA_ERR_UNSUPPORTED;
     if (H > 128 || (ldv & 3) != 0 || ((uintptr_t)vI & 15) != 0) return SLOIKA_ERR_UNSUPPORTED;
-    int n = 8, g = 1;
     const long load = seqs_in_flight > B ? seqs_in_flight : B;
-    if (load > 8L * 148) g = 2;
-    if (load > 16L * 148) n = 16;
+    int g = 1, cw = 8;
+    if (load > 8L * 148) { g = 2; cw = 8; }
+    if (load > 16L * 148 && H <= 96) { g = 4; cw = 4; }
     if (const char *ov = getenv("SLOIKA_B200_GRU_TC")) {
-        int on = 0, og = 0;
-        if (sscanf(ov, "%d,%d", &on, &og) == 2 && (on == 8 || on == 16) && (og == 1 || og == 2)) { n = on; g = og; }
+        int og = 0, ocw = 0;
+        if (sscanf(ov, "%d,%d", &og, &ocw) == 2) { g = og; cw = ocw; }
     }
-#define TC_CASE(HP_) return launch_hp<HP_>(n, g, vI, ldv, sW, sW2, y, ldy, lengths, T, B, H, reverse, st)
+#define TC_CASE(HP_) return launch_hp<HP_>(g, cw, vI, ldv, sW, sW2, y, ldy, lengths, T, B, H, reverse, st)
     if (H <= 32) TC_CASE(32);
     if (H <= 64) TC_CASE(64);
     if (H <= 96) TC_CASE(96);

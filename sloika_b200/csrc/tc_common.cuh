@@ -102,6 +102,15 @@ __device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)
         : "memory");
 }
 
+__device__ __forceinline__ void tmem_ld_32x32b_x2(uint32_t taddr, uint32_t (&r)[2]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x32b_x4(uint32_t taddr, uint32_t (&r)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(taddr)
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_ld_32x32b_x8(uint32_t taddr, uint32_t (&r)[8]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
@@ -157,6 +166,17 @@ __device__ __forceinline__ uint64_t umma_desc_sw64_kmajor(uint32_t addr) {
     d |= (uint64_t)4 << 61;                         // layout type SWIZZLE_64B
     return d;
 }
+// No-swizzle descriptor for an MN-major 16-bit operand that is ONE core matrix wide in the MN direction (8 elements
+// = 16 bytes per k row): core matrices of 8 k rows (128 bytes) follow each other along K.  With a single core
+// matrix across MN only the K-direction stride is ever used, so both stride fields carry it.
+__device__ __forceinline__ uint64_t umma_desc_mn8_noswizzle(uint32_t addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr >> 4) & 0x3fff);
+    d |= (uint64_t)(128 >> 4) << 16;
+    d |= (uint64_t)(128 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
 // Instruction descriptor for kind::tf32, fp32 accumulate, both operands K-major, M = 128.
 __host__ __device__ __forceinline__ uint32_t umma_idesc_tf32_m128(int n) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
@@ -164,6 +184,10 @@ __host__ __device__ __forceinline__ uint32_t umma_idesc_tf32_m128(int n) {
 // kind::f16 with fp16 operands (format code 0), fp32 accumulate, both operands K-major, M = 128.
 __host__ __device__ __forceinline__ uint32_t umma_idesc_f16_m128(int n) {
     return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+}
+// same with the B operand MN-major (bit 16): B[k][n] with n contiguous
+__host__ __device__ __forceinline__ uint32_t umma_idesc_f16_m128_bmn(int n) {
+    return umma_idesc_f16_m128(n) | (1u << 16);
 }
 __device__ __forceinline__ void umma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {
     asm volatile(

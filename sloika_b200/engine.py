@@ -95,6 +95,27 @@ class KernelTimer(object):
 
 TIMER = KernelTimer()
 
+# Number of batches the caller keeps in flight on separate CUDA streams (`basecall.basecall_chunk_stream`, bench.py).
+# Only a scheduling hint for the recurrence kernel (how many sequences share a CTA); results do not depend on it.
+BATCHES_IN_FLIGHT = 1
+
+
+def set_batches_in_flight(k, gemm_sms=None):
+    """Tell the kernels how many batches the caller pipelines on separate streams (1 = none).
+
+    Two scheduling knobs follow from it, neither changes results: the recurrence kernel packs more sequences per
+    CTA (fewer, busier SMs per batch), and the tensor-core GEMMs are held to the SMs the other batches' recurrence
+    kernels leave free (`gemm_sms`, default 148 - 32 per further batch, never under a quarter of the device;
+    SLOIKA_B200_GEMM_SMS overrides), so that their CTAs start at once instead of queueing behind 1 ms kernels."""
+    global BATCHES_IN_FLIGHT
+    k = max(1, int(k))
+    BATCHES_IN_FLIGHT = k
+    if gemm_sms is None:
+        env = os.environ.get('SLOIKA_B200_GEMM_SMS')
+        gemm_sms = int(env) if env else (0 if k == 1 else max(37, 148 - 32 * (k - 1)))
+    cabi.check(cabi.load().sloika_b200_set_gemm_sm_budget(int(gemm_sms)), 'set_gemm_sm_budget')
+    return k
+
 
 def launch(name, nkernels, fn, *args):
     """Enqueue one C-ABI call, bracketed by events when profiling is on."""
@@ -283,10 +304,10 @@ def run_gru(layer, act, out=None):
     vI = _padded_rows(act.T, act.B, 3 * H, dev)          # 16-byte row pitch also for odd H
     st = cabi.stream_ptr(dev)
     _linear('gru_projection', lib, act, layer.iW, layer.b, vI, _row_stride(vI), 3 * H, 0, dev)
-    launch('gru_recurrence', 1, lib.sloika_gru_recurrence_fwd,
+    launch('gru_recurrence', 1, lib.sloika_gru_recurrence_fwd_ex,
            cabi.ptr(vI), _row_stride(vI), cabi.ptr(layer.sW.device(dev)), cabi.ptr(layer.sW2.device(dev)), cabi.ptr(y),
            _row_stride(y), cabi.ptr(act.lengths), act.T, act.B, H, 1 if act.reverse else 0,
-           code_of(layer.fun), code_of(layer.gatefun), st)
+           code_of(layer.fun), code_of(layer.gatefun), act.B * max(1, BATCHES_IN_FLIGHT), st)
     # h is a convex combination of act(.) values when the gates are sigmoids
     return act.like(y, bounded=_bounded_fun(layer.fun) and code_of(layer.gatefun) == 2)
 
@@ -350,6 +371,25 @@ class CompiledNetwork(object):
     def to(self, device):
         import torch
         self._device = torch.device(device)
+        return self
+
+    def prepare(self):
+        """Upload every parameter to the device and wait for it: callers that enqueue batches on several CUDA
+        streams call this once first, so that no stream reads a weight buffer another stream is still filling."""
+        import torch
+        from sloika_b200 import layers as L
+
+        def visit(layer):
+            if isinstance(layer, L._Container):
+                for child in layer._children():
+                    visit(child)
+            else:
+                for p in layer.params():
+                    p.device(self.device)
+                for key in getattr(layer, '_ordered', lambda: [])():
+                    getattr(layer, key).device(self.device)
+        visit(self.network)
+        torch.cuda.synchronize(self.device)
         return self
 
     def forward_device(self, x, lengths=None, fused_decode=False):

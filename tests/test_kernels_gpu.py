@@ -125,13 +125,14 @@ def test_gru(I, H, T, B, reverse):
 
 
 @pytest.mark.parametrize('env', [{'SLOIKA_B200_GRU': 'v1'}, {'SLOIKA_B200_GRU': 'v3'}, {'SLOIKA_B200_GRU': 'v4'},
-                                 {'SLOIKA_B200_GRU_TC': '8,1'}, {'SLOIKA_B200_GRU_TC': '8,2'},
-                                 {'SLOIKA_B200_GRU_TC': '16,1'}, {'SLOIKA_B200_GRU_TC': '16,2'}])
+                                 {'SLOIKA_B200_GRU_TC': '1,4'}, {'SLOIKA_B200_GRU_TC': '1,8'},
+                                 {'SLOIKA_B200_GRU_TC': '1,16'}, {'SLOIKA_B200_GRU_TC': '2,4'},
+                                 {'SLOIKA_B200_GRU_TC': '2,8'}, {'SLOIKA_B200_GRU_TC': '4,4'}])
 @pytest.mark.parametrize('I,H,T,B,reverse', [(96, 96, 90, 37, False), (40, 110, 50, 21, True), (20, 128, 40, 9, False),
                                              (24, 48, 30, 50, True)])
 def test_gru_every_kernel_generation(env, I, H, T, B, reverse, monkeypatch):
     """Each selectable recurrence kernel -- FFMA2 (v1), 3xTF32 mma.sync (v3), fp16x3 mma.sync (v4) and every
-    (sequences per group, groups per CTA) shape of the tcgen05 / tensor-memory kernel -- against the oracle, with a
+    (groups per CTA, compute warps per group) shape of the tcgen05 / tensor-memory kernel -- against the oracle, with a
     ragged batch whose size is not a multiple of any CTA tile."""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
