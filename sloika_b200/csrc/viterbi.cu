@@ -169,17 +169,20 @@ viterbi_kernel(const float *__restrict__ post, long ld_t, long ld_b, const int32
 
 
 // ---------------------------------------------------------------------------------------------------
-// Specialisation for the basecaller's shape: 4 bases, k = 5 -> K = 1024 states, 256 threads, thread r
-// owns states 4r..4r+3.  Compile-time strides (immediate shared-memory offsets), 128-bit accesses to
-// the own-state quads of v (the generic kernel's stride-4 scalar accesses cost 46 % of its
-// shared-memory wavefronts in bank conflicts), log-posterior row of the NEXT event fetched while the
-// current one is processed.
+// Specialisation for the basecaller's shape: 4 bases, k = 5 -> K = 1024 states, 128 threads, thread r owns the
+// eight states 8r..8r+7, i.e. the two quads 2r and 2r+1 (a quad = the four states that share a step predecessor
+// set) which also share their skip predecessor set (index r >> 1).  Per event and thread: eight log-posteriors,
+// two step maxima, ONE skip search -- the per-thread fixed work (row staging, barriers, addresses, the stay term)
+// is paid once per eight states; round 1's 256-thread form (four states per thread, 32 registers, spilling) issued
+// 1520 warp instructions per event, this one about 700.  Compile-time strides, 128-bit accesses to the own-state
+// octet of v, the row of the NEXT event staged with cp.async while the current one is processed.
 //   IN_POST / IN_LOG : rows laid out [stay, kmer 0..1023] (the network's posterior layout), any stride
 //   IN_LOGITS        : rows laid out [kmer 0..1023, stay] (16-byte aligned), un-normalised logits plus
 //                      the per-slice (max, sum exp) pairs of the softmax GEMM epilogue; the softmax
 //                      division, the min_prob floor and the log are all applied here, so the
 //                      posterior matrix is never written to HBM on the fused basecall path.
 constexpr int IN_POST = 0, IN_LOG = 1, IN_LOGITS = 2;
+constexpr int VIT_THREADS = 128;
 
 __device__ __forceinline__ void cp_async16_v(void *smem_dst, const void *gsrc) {
     const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
@@ -194,23 +197,21 @@ __device__ __forceinline__ void cp_async_commit_v() { asm volatile("cp.async.com
 __device__ __forceinline__ void cp_async_wait1_v() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 
 template <int MODE>
-__global__ void __launch_bounds__(256, 7)      // 7 CTAs/SM: all 1024 reads of a batch resident in one wave on 148 SMs
+__global__ void __launch_bounds__(VIT_THREADS, 7)      // 7 CTAs/SM: all 1024 reads of a batch resident in one wave on 148 SMs
 viterbi_k1024_kernel(const float *__restrict__ post, long ld_t, long ld_b, const float2 *__restrict__ stats, int n_slices,
                      const int32_t *__restrict__ lengths, int T, int B, float skip_pen, float c0, float c1,
                      uint8_t *__restrict__ tb, int32_t *__restrict__ path_out,
                      int32_t *__restrict__ path_len, float *__restrict__ score_out)
 {
-    constexpr int K = 1024, RS = 256, RK = 64;
+    constexpr int K = 1024, RS = 256, RK = 64, NT = VIT_THREADS;
     __shared__ __align__(16) float vbuf[2][K];
-    __shared__ float2 ms_s[2];                       // (row max, 1 / row sum) of the softmax, double buffered
-    __shared__ float2 m4_s[256];                     // per row r: (max_a p[a*256 + r], 4 * argmax) of the current event
-    __shared__ float red_v[8];
-    __shared__ int red_i[8];
+    __shared__ float2 ms_s[2];                       // (-(m log2e + log2 rowsum), unused) of the softmax, double buffered
+    __shared__ __align__(16) float2 m4_s[256];       // per quad q4: (max_a p[a*256 + q4], 4 * argmax) of the current event
+    __shared__ float red_v[NT / 32];
+    __shared__ int red_i[NT / 32];
     __shared__ int s_best, s_state;
-    // the next event's row, staged with cp.async: no registers are held across the event (at 32 registers per
-    // thread they used to spill, which made every event wait on its own prefetch) and the HBM latency is fully
-    // asynchronous.  [0, K) k-mer columns, [K] stay column.  The storage doubles as the second traceback chunk
-    // buffer of the backtrace.
+    // the next event's row, staged with cp.async.  [0, K) k-mer columns, [K] stay column.  The storage doubles as
+    // the second traceback chunk buffer of the backtrace.
     constexpr int XROW = K + 4;
     __shared__ __align__(16) float xrow_s[2][XROW];
     uint8_t *tb_s2 = reinterpret_cast<uint8_t *>(&xrow_s[0][0]);
@@ -242,12 +243,12 @@ viterbi_k1024_kernel(const float *__restrict__ post, long ld_t, long ld_b, const
         float mx = m;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        float tot = r < n_slices ? s * expf(m - mx) : 0.0f;
+        float tot = r < n_slices ? s * ex2_ftz((m - mx) * SLOIKA_LOG2E) : 0.0f;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
         if (r == 0) ms_s[i & 1] = make_float2(-(mx * SLOIKA_LOG2E + lg2_ftz(tot)), 0.0f);
     };
-    // stage the row of the next event (this thread: its own 4 k-mer columns; thread 0 also the stay column)
+    // stage the row of the next event (this thread: its own 8 k-mer columns; thread 0 also the stay column)
     const float *rowp = pb;                                           // advanced by ld_t per event
     const bool vec_rows = MODE == IN_LOGITS && (ld_t & 3) == 0 && (ld_b & 3) == 0 && (((uintptr_t)post & 15) == 0);
     auto stage_row = [&](int buf) {
@@ -255,15 +256,17 @@ viterbi_k1024_kernel(const float *__restrict__ post, long ld_t, long ld_b, const
         const float *row = rowp;
         rowp += ld_t;
         if (MODE == IN_LOGITS) {
-            if (vec_rows) cp_async16_v(dst + 4 * r, row + 4 * r);
-            else {
+            if (vec_rows) {
+                cp_async16_v(dst + 8 * r, row + 8 * r);
+                cp_async16_v(dst + 8 * r + 4, row + 8 * r + 4);
+            } else {
 #pragma unroll
-                for (int c = 0; c < 4; c++) cp_async4_v(dst + 4 * r + c, row + 4 * r + c);
+                for (int c = 0; c < 8; c++) cp_async4_v(dst + 8 * r + c, row + 8 * r + c);
             }
             if (r == 0) cp_async4_v(dst + K, row + K);
         } else {
 #pragma unroll
-            for (int c = 0; c < 4; c++) cp_async4_v(dst + 4 * r + c, row + 1 + 4 * r + c);
+            for (int c = 0; c < 8; c++) cp_async4_v(dst + 8 * r + c, row + 1 + 8 * r + c);
             if (r == 0) cp_async4_v(dst + K, row);
         }
         cp_async_commit_v();
@@ -273,7 +276,6 @@ viterbi_k1024_kernel(const float *__restrict__ post, long ld_t, long ld_b, const
         if (MODE == IN_LOGITS) {
             // fused path: softmax (exp(t - m) * 1/rowsum), min_prob floor and log with the MUFU ex2 / lg2
             // approximations (|error| ~1e-6 on a log-posterior, inside what libm-vs-device logf already allows);
-            // branch free, ~10 instructions per value instead of ~60
             // ms = (-(m * log2e + log2 rowsum), unused): posterior = 2^(v*log2e + ms.x), 5 instructions per value
             const float pr = ex2_ftz(fmaf(v, SLOIKA_LOG2E, ms.x));
             return lg2_ftz(fmaf(c1, pr, c0)) * SLOIKA_LN2;             // c0 carries min_prob + 1e-10 on this path
@@ -287,42 +289,46 @@ viterbi_k1024_kernel(const float *__restrict__ post, long ld_t, long ld_b, const
     __syncthreads();
     {
         const float2 ms = ms_s[0];
-        const float4 q = reinterpret_cast<const float4 *>(xrow_s[0])[r];
-        float4 v0;
-        v0.x = lpost_of(q.x, ms); v0.y = lpost_of(q.y, ms); v0.z = lpost_of(q.z, ms); v0.w = lpost_of(q.w, ms);
-        reinterpret_cast<float4 *>(vbuf[0])[r] = v0;             // v_0 = lpost[0][1:]   (decode.py:57)
+        const float4 qa = reinterpret_cast<const float4 *>(xrow_s[0])[2 * r], qb = reinterpret_cast<const float4 *>(xrow_s[0])[2 * r + 1];
+        float4 va, vb;
+        va.x = lpost_of(qa.x, ms); va.y = lpost_of(qa.y, ms); va.z = lpost_of(qa.z, ms); va.w = lpost_of(qa.w, ms);
+        vb.x = lpost_of(qb.x, ms); vb.y = lpost_of(qb.y, ms); vb.z = lpost_of(qb.z, ms); vb.w = lpost_of(qb.w, ms);
+        reinterpret_cast<float4 *>(vbuf[0])[2 * r] = va;             // v_0 = lpost[0][1:]   (decode.py:57)
+        reinterpret_cast<float4 *>(vbuf[0])[2 * r + 1] = vb;
     }
     if (nev > 1) { row_stats(1); stage_row(1); }
     cp_async_wait0_v();
     __syncthreads();
 
     int cur = 0;
-    uint16_t *tbp = tbb + r;                                          // traceback entry of this thread, advanced per event
+    uint32_t *tbp = reinterpret_cast<uint32_t *>(tbb) + r;            // this thread's two traceback entries, advanced per event
     for (int i = 1; i < nev; i++) {
-        const float4 xq = reinterpret_cast<const float4 *>(xrow_s[i & 1])[r];
-        const float x[4] = {xq.x, xq.y, xq.z, xq.w};
-        const float x0 = xrow_s[i & 1][K];
+        const float *xr = xrow_s[i & 1];
+        const float4 xa = reinterpret_cast<const float4 *>(xr)[2 * r], xb = reinterpret_cast<const float4 *>(xr)[2 * r + 1];
+        const float x[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+        const float x0 = xr[K];
         const float2 ms = ms_s[i & 1];
         if (i + 1 < nev) { row_stats(i + 1); stage_row((i + 1) & 1); }  // next event, asynchronous
         const float *p = vbuf[cur];
-        // step: first maximum over a of p[a*256 + r]; published as (value, 4*a) for the skip search
-        float ss = p[r];
-        int as = 0;
+        // step: first maximum over a of p[a*256 + q4] for the two quads q4 = 2r, 2r+1; published as (value, 4*a)
+        float2 ss = reinterpret_cast<const float2 *>(p)[r];
+        int as0 = 0, as1 = 0;
 #pragma unroll
         for (int a = 1; a < 4; a++) {
-            const float c = p[a * RS + r];
-            if (c > ss) { ss = c; as = a; }
+            const float2 c = reinterpret_cast<const float2 *>(p + a * RS)[r];
+            if (c.x > ss.x) { ss.x = c.x; as0 = a; }
+            if (c.y > ss.y) { ss.y = c.y; as1 = a; }
         }
-        m4_s[r] = make_float2(ss, __int_as_float(4 * as));
-        const float4 pv = reinterpret_cast<const float4 *>(p)[r];
+        reinterpret_cast<float4 *>(m4_s)[r] = make_float4(ss.x, __int_as_float(4 * as0), ss.y, __int_as_float(4 * as1));
+        const float4 pa = reinterpret_cast<const float4 *>(p)[2 * r], pb4 = reinterpret_cast<const float4 *>(p)[2 * r + 1];
         const float lp0 = lpost_of(x0, ms);
-        float lp[4];
+        float lp[8];
 #pragma unroll
-        for (int c = 0; c < 4; c++) lp[c] = lpost_of(x[c], ms);
+        for (int c = 0; c < 8; c++) lp[c] = lpost_of(x[c], ms);
         __syncthreads();
         // skip: predecessor a*64 + q with a = 4*a_hi + a_lo is p[a_hi*256 + (a_lo*64 + q)], so its maximum is
-        // the maximum over a_lo of the published step maxima of rows a_lo*64 + q; "first maximum" = smallest a
-        const int q = r >> 2;
+        // the maximum over a_lo of the published step maxima of quads a_lo*64 + q; "first maximum" = smallest a
+        const int q = r >> 1;
         float sk;
         int ak;
         {
@@ -337,23 +343,29 @@ viterbi_k1024_kernel(const float *__restrict__ post, long ld_t, long ld_b, const
             }
         }
         sk = __fsub_rn(sk, skip_pen);
-        const bool use_step = ss > sk;                               // tie -> skip (decode.py:76)
-        const float best = use_step ? ss : sk;
-        const unsigned code = use_step ? (1u + as) : (5u + ak);
-        const float pj[4] = {pv.x, pv.y, pv.z, pv.w};
-        float vo[4];
-        unsigned packed = code << 4;
+        const float pj[8] = {pa.x, pa.y, pa.z, pa.w, pb4.x, pb4.y, pb4.z, pb4.w};
+        float vo[8];
+        unsigned packed = 0;
 #pragma unroll
-        for (int c = 0; c < 4; c++) {
-            const float move = __fadd_rn(lp[c], best);
-            const float stay = __fadd_rn(pj[c], lp0);
-            const bool mv = move > stay;                             // tie -> stay (decode.py:81)
-            vo[c] = mv ? move : stay;
-            packed |= (mv ? 1u : 0u) << c;
+        for (int h = 0; h < 2; h++) {
+            const float ssh = h == 0 ? ss.x : ss.y;
+            const bool use_step = ssh > sk;                              // tie -> skip (decode.py:76)
+            const float best = use_step ? ssh : sk;
+            unsigned e = (use_step ? (1u + (unsigned)(h == 0 ? as0 : as1)) : (5u + (unsigned)ak)) << 4;
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const float move = __fadd_rn(lp[4 * h + c], best);
+                const float stay = __fadd_rn(pj[4 * h + c], lp0);
+                const bool mv = move > stay;                             // tie -> stay (decode.py:81)
+                vo[4 * h + c] = mv ? move : stay;
+                e |= (mv ? 1u : 0u) << c;
+            }
+            packed |= e << (16 * h);
         }
-        reinterpret_cast<float4 *>(vbuf[cur ^ 1])[r] = make_float4(vo[0], vo[1], vo[2], vo[3]);
-        tbp += TBROW;
-        *tbp = (uint16_t)packed;
+        reinterpret_cast<float4 *>(vbuf[cur ^ 1])[2 * r] = make_float4(vo[0], vo[1], vo[2], vo[3]);
+        reinterpret_cast<float4 *>(vbuf[cur ^ 1])[2 * r + 1] = make_float4(vo[4], vo[5], vo[6], vo[7]);
+        tbp += TBROW / 2;
+        *tbp = packed;
         cur ^= 1;
         cp_async_wait0_v();                                          // the next row has landed (issued an event ago)
         __syncthreads();
@@ -364,9 +376,9 @@ viterbi_k1024_kernel(const float *__restrict__ post, long ld_t, long ld_b, const
     float bv = -INFINITY;
     int bi = 0x7fffffff;
 #pragma unroll
-    for (int c = 0; c < 4; c++) {
-        const float val = v[4 * r + c];
-        if (val > bv) { bv = val; bi = 4 * r + c; }
+    for (int c = 0; c < 8; c++) {
+        const float val = v[8 * r + c];
+        if (val > bv) { bv = val; bi = 8 * r + c; }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -377,7 +389,7 @@ viterbi_k1024_kernel(const float *__restrict__ post, long ld_t, long ld_b, const
     if ((r & 31) == 0) { red_v[r >> 5] = bv; red_i[r >> 5] = bi; }
     __syncthreads();
     if (r == 0) {
-        for (int w = 1; w < 8; w++)
+        for (int w = 1; w < NT / 32; w++)
             if (red_v[w] > bv || (red_v[w] == bv && red_i[w] < bi)) { bv = red_v[w]; bi = red_i[w]; }
         score_out[b] = bv;
         s_state = bi;
@@ -394,7 +406,7 @@ viterbi_k1024_kernel(const float *__restrict__ post, long ld_t, long ld_b, const
         uint8_t *bufs[2] = {reinterpret_cast<uint8_t *>(&vbuf[0][0]), tb_s2};
         auto issue = [&](int hi, int which) {                              // rows (hi-CH, hi], clipped at 1
             uint8_t *dst = bufs[which];
-            for (int e = r; e < CH * (ROWB / 16); e += 256) {
+            for (int e = r; e < CH * (ROWB / 16); e += NT) {
                 const int row = hi - e / (ROWB / 16);
                 if (row >= 1)
                     cp_async16_v(dst + (size_t)e * 16,
@@ -436,7 +448,7 @@ viterbi_k1024_kernel(const float *__restrict__ post, long ld_t, long ld_b, const
     const int n = nev - off;
     if (off > 0) {
         int32_t *out = path_out + (size_t)b * T;
-        for (int base = 0; base < n; base += 256) {
+        for (int base = 0; base < n; base += NT) {
             const int idx = base + r;
             int32_t val = 0;
             if (idx < n) val = out[off + idx];
@@ -496,10 +508,10 @@ extern "C" int sloika_viterbi_fwd(const float *post, long ld_t, long ld_b, const
     cudaError_t err;
     if (use_k1024(nbase, K)) {
         if (mode == SLOIKA_VIT_POST)
-            viterbi_k1024_kernel<IN_POST><<<B, 256, 0, st>>>(post, ld_t, ld_b, nullptr, 0, lengths, T, B, sp, c0, c1,
+            viterbi_k1024_kernel<IN_POST><<<B, VIT_THREADS, 0, st>>>(post, ld_t, ld_b, nullptr, 0, lengths, T, B, sp, c0, c1,
                                                               (uint8_t *)tb_ws, path_out, path_len, score_out);
         else
-            viterbi_k1024_kernel<IN_LOG><<<B, 256, 0, st>>>(post, ld_t, ld_b, nullptr, 0, lengths, T, B, sp, c0, c1,
+            viterbi_k1024_kernel<IN_LOG><<<B, VIT_THREADS, 0, st>>>(post, ld_t, ld_b, nullptr, 0, lengths, T, B, sp, c0, c1,
                                                              (uint8_t *)tb_ws, path_out, path_len, score_out);
         SLOIKA_RETURN_LAUNCH_STATUS();
     }
@@ -532,7 +544,7 @@ extern "C" int sloika_viterbi_logits_fwd(const float *logits, long ld_t, long ld
     // on this path the kernel evaluates log(c0 + c1 * p) with one fused multiply-add: c0 carries the + 1e-10 of
     // decode.prepare_post (decode.py:36) as well
     const float c0 = (float)min_prob + 1e-10f, c1 = (float)(1.0 - min_prob), sp = (float)skip_pen;
-    viterbi_k1024_kernel<IN_LOGITS><<<B, 256, 0, (cudaStream_t)stream>>>(
+    viterbi_k1024_kernel<IN_LOGITS><<<B, VIT_THREADS, 0, (cudaStream_t)stream>>>(
         logits, ld_t, ld_b, reinterpret_cast<const float2 *>(stats), n_slices, lengths, T, B, sp, c0, c1,
         (uint8_t *)tb_ws, path_out, path_len, score_out);
     SLOIKA_RETURN_LAUNCH_STATUS();

@@ -30,16 +30,23 @@ def main():
         ref64 = forward_ref.run(net.json(params=True), x, np.float64)
         ref32 = forward_ref.run(net.json(params=True), x, np.float32)
         out = {}
-        for label, env in (('gated fp16/tf32', None), ('tf32 only', '1')):
-            if env:
-                os.environ['SLOIKA_B200_NO_F16'] = env
+        for label, env in (('gated fp16/tf32', {}), ('tf32 only', {'SLOIKA_B200_NO_F16': '1'}),
+                           ('mma.sync recurrence', {'SLOIKA_B200_GRU': 'v4'}),
+                           ('mma.sync + tf32', {'SLOIKA_B200_GRU': 'v4', 'SLOIKA_B200_NO_F16': '1'})):
+            os.environ.update(env)
             out[label] = calc(x)
-            os.environ.pop('SLOIKA_B200_NO_F16', None)
+            for k in env:
+                os.environ.pop(k, None)
         print("%s: %d steps" % (name, ref64.shape[0]))
-        print("   float32 NumPy oracle vs float64 : max abs %.3e" % np.abs(ref32 - ref64).max())
+        lp64 = np.log(ref64.max(2))
+
+        def bias(post):
+            return float(np.mean(np.log(post.astype(np.float64).max(2)) - lp64))
+        print("   float32 NumPy oracle vs float64 : max abs %.3e   mean log-posterior bias of the best state %+.2e" % (
+            np.abs(ref32 - ref64).max(), bias(ref32)))
         for label, post in out.items():
-            print("   device (%-15s) vs float64 : max abs %.3e   vs float32 oracle: %.3e" % (
-                label, np.abs(post - ref64).max(), np.abs(post - ref32).max()))
+            print("   device (%-19s) vs float64 : max abs %.3e   vs float32 oracle: %.3e   bias %+.2e" % (
+                label, np.abs(post - ref64).max(), np.abs(post - ref32).max(), bias(post)))
 
 
 if __name__ == '__main__':
