@@ -154,6 +154,21 @@ int sloika_gru_recurrence_fwd_ex(const float *vI, long ld_vi, const float *sW, c
                                  int gate_act, long seqs_in_flight, void *stream);
 
 /*
+ * Lstm.step scanned by Lstm.run -- sloika/layers.py:677-697 (events route), given the input projection
+ * vW = x iW' + b for all steps: T*B rows of 4H floats (row pitch ld_vw >= 4H).  sW [4H,H] and the projection rows are
+ * in the reference's stored order (row 4*j + g = gate g of unit j: 0 update input, 1 update gate, 2 forget gate,
+ * 3 output gate); peep [3,H] (update, forget, output; zeros when the layer has no peepholes).  y: T*B rows of H.
+ * Outputs at steps >= lengths[b] are zero.  H <= 256.
+ */
+int sloika_lstm_recurrence_fwd(const float *vW, long ld_vw, const float *sW, const float *peep, float *y, long ldy,
+                               const int32_t *lengths, int T, int B, int H, int reverse, int act, int gate_act,
+                               void *stream);
+
+/* Window.run -- sloika/layers.py:346-351: y[t,b,k*F+f] = x[t+k-w/2, b, f], zero outside [0, lengths[b]); w odd. */
+int sloika_window_fwd(const float *x, long ldx, float *y, long ldy, const int32_t *lengths, int T, int B, int F, int w,
+                      void *stream);
+
+/*
  * decode.prepare_post + decode.viterbi -- sloika/decode.py:21-36, :39-93 (called from
  * sloika/basecall.py:44-46), batched: one CTA per read.
  *   post: [T,B,S] with S = nbase^klen + 1, element (t,b,s) at post[t*ld_t + b*ld_b + s]

@@ -144,7 +144,7 @@ def lstm(desc, x, dtype):
 def window(desc, x, dtype):
     """layers.py:346-351: zero-pad w//2 steps either side, concatenate the w shifted copies on the feature
     axis: out[t, b, k*F + f] = xpad[t + k, b, f]."""
-    w = desc['w']
+    w = desc['w'] if 'w' in desc else desc['params']['w']
     T, B, F = x.shape
     pad = np.zeros((w // 2, B, F), dtype)
     xpad = np.concatenate([pad, x, pad], axis=0)

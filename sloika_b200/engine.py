@@ -312,6 +312,37 @@ def run_gru(layer, act, out=None):
     return act.like(y, bounded=_bounded_fun(layer.fun) and code_of(layer.gatefun) == 2)
 
 
+def run_lstm(layer, act, out=None):
+    """Lstm.run (`layers.py:693-697`): input projection for all steps (tensor-core GEMM) + the recurrence kernel."""
+    lib = cabi.load()
+    assert act.F == layer.insize
+    y = _out_buffer(act, act.T, layer.size, out)
+    dev = act.device
+    H = layer.size
+    vW = _padded_rows(act.T, act.B, 4 * H, dev)
+    _linear('lstm_projection', lib, act, layer.iW, layer.b, vW, _row_stride(vW), 4 * H, 0, dev)
+    launch('lstm_recurrence', 1, lib.sloika_lstm_recurrence_fwd,
+           cabi.ptr(vW), _row_stride(vW), cabi.ptr(layer.sW.device(dev)), cabi.ptr(layer.p.device(dev)), cabi.ptr(y),
+           _row_stride(y), cabi.ptr(act.lengths), act.T, act.B, H, 1 if act.reverse else 0,
+           code_of(layer.fun), code_of(layer.gatefun), cabi.stream_ptr(dev))
+    # out = fun(state) * gate(.): bounded when fun is and the gate is a sigmoid
+    return act.like(y, bounded=_bounded_fun(layer.fun) and code_of(layer.gatefun) == 2)
+
+
+def run_window(layer, act, out=None):
+    """Window.run (`layers.py:346-351`)."""
+    lib = cabi.load()
+    assert act.F == layer.insize
+    if act.reverse:
+        # a window is symmetric in time (w odd, equal padding): windowing the reversed input equals reversing the
+        # windowed input with the feature blocks in reverse order -- not supported in place, so say so
+        raise NotImplementedError("Reverse(Window) is not implemented on the device")
+    y = _out_buffer(act, act.T, layer.size, out)
+    launch('window', 1, lib.sloika_window_fwd, cabi.ptr(act.data), act.ld, cabi.ptr(y), _row_stride(y),
+           cabi.ptr(act.lengths), act.T, act.B, act.F, layer.w, cabi.stream_ptr(act.device))
+    return act.like(y, bounded=act.bounded, absmax=act.absmax)
+
+
 _SLICE_WRITERS = {}
 
 
@@ -330,6 +361,8 @@ def run_parallel(layer, act, out=None):
         src = act.flipped() if flips % 2 else act
         if isinstance(inner, L.Gru):
             res = run_gru(inner, src, out=view)
+        elif isinstance(inner, L.Lstm):
+            res = run_lstm(inner, src, out=view)
         elif isinstance(inner, L.FeedForward):
             res = run_feedforward(inner, src, out=view)
         elif isinstance(inner, L.Softmax):

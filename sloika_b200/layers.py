@@ -15,8 +15,8 @@ Parametrised layers are described declaratively (`_SPEC`: parameter name -> stor
 shape used by `json(params=True)` / `set_params`), so the JSON and `set_params` contracts of the
 reference (:139-155, :291-307, :396-415, :985-1008) are produced by one code path.
 
-The 18 other layer classes of the reference (research RNN zoo, `Window`, `MaxPool`, ...) are not on
-the raw basecall path and are deliberately absent.
+`Lstm` and `Window` serve the events route.  The other layer classes of the reference
+(research RNN zoo, `MaxPool`, ...) are used by no shipped model and are deliberately absent.
 """
 import abc
 from collections import OrderedDict
@@ -270,6 +270,96 @@ class Gru(RNN):
     def run(self, inMat):
         from sloika_b200 import engine
         return engine.run_gru(self, inMat)
+
+
+_FORGET_BIAS = 2.0            # layers.py:16
+
+
+class Lstm(RNN):
+    """LSTM with peepholes, "consistent with Currennt" (`layers.py:599-697`).
+
+    Parameters `iW:[4*size,insize]`, `sW:[4*size,size]`, `b:[4*size]`, `p:[3,size]` (scalings and the forget-gate
+    bias of :637-640).  The step (:677-691) views the 4*size pre-activations as `(size, 4)`: stored row `4*j + g`
+    is gate g of unit j (0 update input, 1 update gate, 2 forget gate, 3 output gate):
+        state' = state * gate(s2 + state*p1) + fun(s0) * gate(s1 + state*p0);  out' = fun(state') * gate(s3 + state'*p2)
+    `json` / `set_params` keep the reference's `(4, size, ...)` shapes, including its transposed bias in
+    `set_params` (:666-668).
+    """
+    _TYPE = "LSTM"
+
+    def __init__(self, insize, size, init=zeros, has_bias=False, has_peep=False,
+                 fun=activation.tanh, gatefun=activation.sigmoid, name="LSTM"):
+        self._size, self._insize, self._name = size, insize, name
+        self.has_bias = has_bias
+        self.has_peep = has_peep
+        self.fun = fun
+        self.gatefun = gatefun
+        self.b = Param(has_bias * (init(4 * size) + np.repeat([0, 0, _FORGET_BIAS, 0], size).astype(sloika_dtype)), 'b')
+        self.p = Param(has_peep * init((3, size)) / np.sqrt(size), 'p')
+        self.iW = Param(init((4 * size, insize)) / np.sqrt(insize + size), 'iW')
+        self.sW = Param(init((4 * size, size)) / np.sqrt(size + size), 'sW')
+
+    def params(self):
+        return [self.iW, self.sW] + ([self.b] if self.has_bias else []) + ([self.p] if self.has_peep else [])
+
+    def _head(self):
+        return [('activation', self.fun.__name__), ('gate', self.gatefun.__name__), ('size', self.size),
+                ('insize', self.insize), ('bias', self.has_bias), ('peep', self.has_peep)]
+
+    def _spec(self):
+        n, m = self.size, self.insize
+        return OrderedDict([('iW', ((4 * n, m), (4, n, m))), ('sW', ((4 * n, n), (4, n, n))),
+                            ('b', ((4 * n,), (4, n))), ('p', ((3, n), (3, n)))])
+
+    def set_params(self, values):
+        n, m = self.size, self.insize
+        if self.has_bias:
+            assert values['b'].shape == (4, n)
+            self.b.set_value(np.asarray(values['b']).transpose().reshape(-1))
+        if self.has_peep:
+            assert values['p'].shape == (3, n)
+            self.p.set_value(values['p'])
+        assert values['iW'].shape == (4, n, m)
+        self.iW.set_value(np.asarray(values['iW']).reshape((4 * n, m)))
+        assert values['sW'].shape == (4, n, n)
+        self.sW.set_value(np.asarray(values['sW']).reshape((4 * n, n)))
+
+    def run(self, inMat):
+        from sloika_b200 import engine
+        return engine.run_lstm(self, inMat)
+
+
+class Window(Layer):
+    """Sliding window over the input (`layers.py:317-351`): `w` shifted copies, zero padded by `w // 2` steps either
+    side, concatenated on the feature axis.  (The reference's `json` forgets its `return`; this one returns the
+    description it builds.)"""
+
+    def __init__(self, insize, w, name="Window"):
+        assert w > 0, "Window size must be positive"
+        assert w % 2 == 1, 'Window size should be odd'
+        self.w = w
+        self._insize = insize
+        self._name = name
+
+    @property
+    def size(self):
+        return self.w * self.insize
+
+    def params(self):
+        return []
+
+    def json(self, params=False):
+        res = OrderedDict([('type', "window")])
+        if params:
+            res['params'] = OrderedDict([('w', self.w)])
+        return res
+
+    def set_params(self, values):
+        return
+
+    def run(self, inMat):
+        from sloika_b200 import engine
+        return engine.run_window(self, inMat)
 
 
 class _Container(Layer):

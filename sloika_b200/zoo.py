@@ -11,7 +11,7 @@ Weights are `sd * truncnorm(-2, 2)` draws (`module_tools.py:9-13`); seed NumPy f
 from functools import partial
 
 from sloika_b200 import activation as act
-from sloika_b200.layers import Convolution, FeedForward, Gru, Reverse, Serial, Softmax, birnn
+from sloika_b200.layers import Convolution, FeedForward, Gru, Lstm, Reverse, Serial, Softmax, Window, birnn
 from sloika_b200.module_tools import truncated_normal
 from sloika_b200.variables import DEFAULT_NBASE, nstate
 
@@ -68,7 +68,14 @@ def from_weights(arch, weights):
             return Parallel([build(d, '{}{}.'.format(prefix, i)) for i, d in enumerate(desc['sublayers'])])
         if kind == 'reverse':
             return Reverse(build(desc['sublayer'], prefix + '0.'))
+        if kind == 'window':
+            return Window(desc['insize'], desc['w'])
         fun = getattr(act, desc['activation']) if 'activation' in desc else None
+        if kind == 'LSTM':
+            layer = Lstm(desc['insize'], desc['size'], has_bias=True, has_peep=True, fun=fun, gatefun=getattr(act, desc['gate']))
+            for key in ('iW', 'sW', 'b', 'p'):                  # stored layout, no reshaping (see Lstm.set_params)
+                getattr(layer, key).set_value(weights[prefix + key])
+            return layer
         if kind == 'convolution':
             layer = Convolution(desc['insize'], desc['size'], desc['winlen'], desc['stride'],
                                 has_bias=True, fun=fun, padding_mode=desc['padding_mode'])

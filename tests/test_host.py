@@ -220,7 +220,7 @@ def test_loads_theano_style_pickle(cuda):
 def test_rejects_compiled_function_and_unknown_layers():
     class Fake(object):
         pass
-    for mod_name, cls_name in (('theano.compile.function_module', '_constructor_Function'), ('sloika.layers', 'Lstm')):
+    for mod_name, cls_name in (('theano.compile.function_module', '_constructor_Function'), ('sloika.layers', 'Mut1')):
         data = b'\x80\x03c' + mod_name.encode() + b'\n' + cls_name.encode() + b'\n)\x81.'
         with pytest.raises(model_io.ModelFormatError):
             model_io.loads(data)

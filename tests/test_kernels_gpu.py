@@ -637,3 +637,47 @@ def test_cuda_path_matches_reference_outputs(forward_cases):
         ran += 1
     assert not bad, bad
     assert ran >= 40
+
+
+# ------------------------------------------------------------------ events route operators (row f4)
+@pytest.mark.parametrize('I,H,T,B,reverse,peep', [(12, 64, 60, 7, False, True), (12, 64, 40, 5, True, True),
+                                                  (5, 16, 30, 9, False, False), (20, 100, 25, 3, True, True),
+                                                  (8, 128, 20, 2, False, True)])
+def test_lstm(I, H, T, B, reverse, peep):
+    """Lstm (layers.py:599-697) against the oracle (pinned to the reference's own Lstm.step by forward_cases.npz),
+    ragged batch: every read sees the computation the reference gives it alone."""
+    np.random.seed(I + H)
+    g = layers.Lstm(I, H, init=_init(), has_bias=True, has_peep=peep)
+    g.sW.set_value(g.sW.get_value() * 4)
+    layer = layers.Reverse(g) if reverse else g
+    lengths = [int(v) for v in np.random.randint(1, T + 1, size=B)]
+    lengths[0] = T
+    x = np.random.standard_normal((T, B, I)).astype(np.float32)
+    got, _ = _run(layer, x, lengths)
+    for b, n in enumerate(lengths):
+        ref = _oracle(layer, x[:n, b:b + 1])
+        assert np.abs(got[:n, b] - ref[:, 0]).max() < 5e-5, b
+        assert np.all(got[n:, b] == 0)
+
+
+def test_window_and_events_model():
+    np.random.seed(8)
+    x = np.random.standard_normal((23, 4, 4)).astype(np.float32)
+    for w in (1, 3, 5):
+        layer = layers.Window(4, w)
+        got, _ = _run(layer, x, [23, 1, 7, 22])
+        for b, n in enumerate([23, 1, 7, 22]):
+            ref = forward_ref.window({'w': w}, x[:n, b:b + 1], np.float32)
+            assert np.array_equal(got[:n, b], ref[:, 0]) and np.all(got[n:, b] == 0)
+    # models/baseline_lstm.py architecture: window + birnn(Lstm) + FF + birnn(Lstm) + FF + softmax
+    init = _init()
+    lstm = lambda i, o: layers.Lstm(i, o, init=init, has_bias=True, has_peep=True)
+    net = layers.Serial([layers.Window(4, 3), layers.birnn(lstm(12, 64), lstm(12, 64)),
+                         layers.FeedForward(128, 64, init=init, has_bias=True),
+                         layers.birnn(lstm(64, 64), lstm(64, 64)),
+                         layers.FeedForward(128, 64, init=init, has_bias=True),
+                         layers.Softmax(64, 1025, init=init, has_bias=True)])
+    x = np.random.standard_normal((150, 3, 4)).astype(np.float32)
+    post = net.compile()(x)
+    ref = _oracle(net, x)
+    assert post.shape == ref.shape and np.abs(post - ref).max() < 1e-4
