@@ -1,8 +1,11 @@
 #!/usr/bin/env python3
 """Benchmark of the raw basecall hot path (forward + Viterbi) on B200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload raw_rgrgr|raw_rGr|bigger_raw_gru|pretrained_like]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--in-flight F] [--scaling weak|strong]
+                    [--workload raw_rgrgr|raw_rGr|bigger_raw_gru|bigger_raw_gru_wide|pretrained_like|decode_sweep]
     python bench.py --impl reference ...        # the CPU arm: oracle port on the host cores
+Default = BASELINE.json configs[2] (raw_rgrgr, the config the metric is quoted on); the other workloads are
+configs[1] (raw_rGr), configs[3] (bigger_raw_gru and a widened [64, 256, 256] variant) and configs[4] (decode only).
 
 A step = one pass of the hot path over one batch of synthetic raw-signal chunks
 (x ~ N(0,1) float32 [4000, 1024, 1] per GPU, seeded; weights truncated-normal sd 0.5, seeded):
@@ -43,6 +46,8 @@ def parse_args():
     ap.add_argument('--cpu-sample-chunks', type=int, default=None,
                     help='chunks in the bounded CPU sample (default: 384 once for cpu_baseline, 32 per step for --impl reference)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
+                    help='weak: --batch chunks per GPU; strong: --batch chunks in total, split over the GPUs')
     ap.add_argument('--in-flight', type=int, default=4,
                     help='batches pipelined on separate CUDA streams (1 = one batch after the other)')
     return ap.parse_args()
@@ -51,6 +56,8 @@ def parse_args():
 def build_network(workload):
     from sloika_b200 import zoo
     np.random.seed(WEIGHT_SEED)
+    if workload == 'bigger_raw_gru_wide':
+        return zoo.bigger_raw_gru(size=(64, 256, 256))       # widened variant (H > 144: step-wise scan)
     return getattr(zoo, workload)()
 
 
@@ -95,7 +102,7 @@ def algorithmic_bytes_per_sample(net):
             add('feedforward', 4.0 * layer.insize + 4.0 * layer.size)
         elif isinstance(layer, L.Softmax):
             add('softmax', 4.0 * layer.insize + 4.0 * layer.size)
-            add('viterbi', 4.0 * layer.size + (layer.size - 1))
+            add('viterbi', 4.0 * layer.size + (layer.size - 1) / 2.0)      # posteriors read + uint16-per-quad traceback
         elif isinstance(layer, L.Reverse):
             walk(layer.layer)
         else:
@@ -219,7 +226,113 @@ def run_reference_arm(args):
 
 
 def workload_name(args):
+    if args.scaling == 'strong':
+        return "{}: {} chunks x {} raw samples in total (split over the GPUs), fwd+Viterbi".format(
+            args.workload, args.batch, args.chunk)
     return "{}: {} chunks x {} raw samples per GPU, fwd+Viterbi".format(args.workload, args.batch, args.chunk)
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json configs[4]: decode only, synthetic posteriors (row softmax of 3*N(0,1) logits, 1025 states)
+SWEEP_CASES = [(1000, 1024), (3000, 1024), (10000, 1024), (30000, 444), (100000, 148)]   # (events per read, reads)
+
+
+def run_decode_sweep(args):
+    import torch
+    import torch.distributed as dist
+    from sloika_b200 import cabi, decode
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    cabi.load()
+    S = 1025
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(5 + rank)
+
+    def synth(T, B):
+        post = torch.empty((T, B, S), dtype=torch.float32, device=dev)
+        step = max(1, (1 << 28) // (B * S))
+        for t0 in range(0, T, step):
+            t1 = min(T, t0 + step)
+            p = torch.softmax(torch.randn((t1 - t0, B, S), generator=gen, device=dev) * 3.0, dim=-1)
+            post[t0:t1] = torch.log((1e-5 + (1.0 - 1e-5) * p) + 1e-10)
+        return post
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    rows, total_events, total_ms = [], 0, 0.0
+    cpu = None
+    for T, B in SWEEP_CASES:
+        post = synth(T, B)
+        for _ in range(max(args.warmup, 3)):
+            decode.viterbi_batch(post, None, log=True, return_device=True)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        reps = max(1, min(args.steps, 5))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            score, paths, plen = decode.viterbi_batch(post, None, log=True, return_device=True)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        rows.append({"events_per_read": T, "reads_per_gpu": B, "ms": ms, "events_per_s": T * B * world / (ms * 1e-3),
+                     "GBps_per_gpu": T * B * (S * 4.0 + 512.0) / (ms * 1e-3) / 1e9})
+        total_events += T * B * world
+        total_ms += ms
+        if rank == 0 and world == 1 and not args.no_cpu_baseline and T == 10000:
+            # bounded CPU sample: the C restatement of decode.py:39-93 on the host cores, same log-posteriors
+            from oracle import cbind
+            ncpu = os.cpu_count() or 1
+            n_cpu = min(B, 2 * ncpu)
+            sample = post[:, :n_cpu].cpu().numpy()
+            t0 = time.perf_counter()
+            s_ref, p_ref = cbind.viterbi_batch(sample, None, 5, 4, 0.0)
+            dt = time.perf_counter() - t0
+            plen_h, paths_h = plen[:n_cpu].cpu().numpy(), paths[:n_cpu].cpu().numpy()
+            same = all(paths_h[b, :plen_h[b]].tolist() == list(p_ref[b]) for b in range(n_cpu))
+            cpu = {"value": T * n_cpu / dt, "unit": "events/s", "cores": ncpu, "kind": "port",
+                   "sample": "{} reads x {} events, oracle/viterbi_ref.c over {} threads, {:.1f} s; paths identical to the device's: {}".format(
+                       n_cpu, T, ncpu, dt, same)}
+        del post, score, paths, plen
+        torch.cuda.empty_cache()
+    clocks = sampler.stop() if sampler else None
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as fh:
+            peaks = json.load(fh)
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
+    value = total_events / (total_ms * 1e-3)
+    big = rows[2]
+    line = {"metric": "events_per_s_viterbi_decoded", "value": value, "unit": "events/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "decode_sweep: Viterbi over synthetic posteriors, reads of 1k/3k/10k/30k/100k events x 1025 states per GPU",
+                       "cases": rows, "l2": "posteriors per case exceed L2; no flush needed"},
+            "e2e": None, "gpu_launches": len(SWEEP_CASES) * max(1, min(args.steps, 5)) * world,
+            "roofline": {"kernel": "viterbi_k1024 (10k x 1024 case)", "bound": "hbm", "achieved": big["GBps_per_gpu"],
+                         "peak": hbm_peak, "unit": "GB/s", "frac": big["GBps_per_gpu"] / hbm_peak, "traffic": None,
+                         "algorithmic_bytes_per_event": S * 4.0 + 512.0},
+            "cpu_baseline": cpu, "clocks": clocks}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def run_b200_arm(args):
@@ -241,6 +354,8 @@ def run_b200_arm(args):
     net = build_network(args.workload)
     calc_post = net.compile().to(dev)
     T, B = args.chunk, args.batch
+    if args.scaling == 'strong':
+        B = max(1, B // world)                              # the batch is split over the ranks
     gen = torch.Generator().manual_seed(INPUT_SEED + rank)
     x_host = torch.randn((T, B, 1), generator=gen, dtype=torch.float32).pin_memory()
     x_dev = x_host.to(dev)
@@ -407,7 +522,7 @@ def run_b200_arm(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_dev / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args), "chunks_per_gpu": B, "chunk_len": T, "stride": stride_of(net),
                    "batches_in_flight": K, "value_excludes_h2d": True,
                    "sharding": "reads x{} (no collective)".format(world),
@@ -434,6 +549,8 @@ def main():
     args = parse_args()
     if args.impl == 'reference':
         run_reference_arm(args)
+    elif args.workload == 'decode_sweep':
+        run_decode_sweep(args)
     else:
         run_b200_arm(args)
 

@@ -188,6 +188,11 @@ __device__ __forceinline__ void cp_async16_v(void *smem_dst, const void *gsrc) {
     const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
 }
+// 16-byte copy of which only the first `nbytes` are read from global memory (the rest is zero filled)
+__device__ __forceinline__ void cp_async16_zfill_v(void *smem_dst, const void *gsrc, int nbytes) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(nbytes) : "memory");
+}
 __device__ __forceinline__ void cp_async4_v(void *smem_dst, const void *gsrc) {
     const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
@@ -212,7 +217,7 @@ viterbi_k1024_kernel(const float *__restrict__ post, long ld_t, long ld_b, const
     __shared__ int s_best, s_state;
     // the next event's row, staged with cp.async.  [0, K) k-mer columns, [K] stay column.  The storage doubles as
     // the second traceback chunk buffer of the backtrace.
-    constexpr int XROW = K + 4;
+    constexpr int XROW = K + 12;                     // K k-mer columns (+ up to 3 floats of alignment phase + 1 chunk), stay at [XROW - 1]
     __shared__ __align__(16) float xrow_s[2][XROW];
     uint8_t *tb_s2 = reinterpret_cast<uint8_t *>(&xrow_s[0][0]);
     static_assert(sizeof(float) * 2 * XROW >= 8 * 1024, "xrow_s doubles as a traceback chunk buffer");
@@ -248,28 +253,55 @@ viterbi_k1024_kernel(const float *__restrict__ post, long ld_t, long ld_b, const
         for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
         if (r == 0) ms_s[i & 1] = make_float2(-(mx * SLOIKA_LOG2E + lg2_ftz(tot)), 0.0f);
     };
-    // stage the row of the next event (this thread: its own 8 k-mer columns; thread 0 also the stay column)
+    // stage the row of the next event.  The k-mer columns of a row start at `a` = row (logits layout) or row + 1
+    // (posterior layout), which is 16-byte aligned only in the first case; in general the row is copied as the
+    // 16-byte ALIGNED chunks that cover it (257 128-bit cp.async per row instead of 1024 32-bit ones), keeping its
+    // alignment phase ph = (a / 4 bytes) mod 4 in shared memory: column j lands at xrow[ph + j].  The last chunk is
+    // copied with its valid byte count only (zero filled), so nothing is read past the row's end; the first chunk
+    // starts at most 3 floats before `a`, inside the tensor because its base is 16-byte aligned (checked: otherwise
+    // 32-bit copies).  Thread 0 also stages the stay column at xrow[XROW - 1].
     const float *rowp = pb;                                           // advanced by ld_t per event
-    const bool vec_rows = MODE == IN_LOGITS && (ld_t & 3) == 0 && (ld_b & 3) == 0 && (((uintptr_t)post & 15) == 0);
+    constexpr int KOFF = MODE == IN_LOGITS ? 0 : 1;                    // first k-mer column of a row
+    const bool span_rows = (((uintptr_t)post & 15) == 0);
+    auto phase_of = [&](const float *row) -> int { return span_rows ? (int)(((uintptr_t)(row + KOFF) >> 2) & 3) : 0; };
     auto stage_row = [&](int buf) {
         float *dst = xrow_s[buf];
         const float *row = rowp;
         rowp += ld_t;
-        if (MODE == IN_LOGITS) {
-            if (vec_rows) {
-                cp_async16_v(dst + 8 * r, row + 8 * r);
-                cp_async16_v(dst + 8 * r + 4, row + 8 * r + 4);
-            } else {
-#pragma unroll
-                for (int c = 0; c < 8; c++) cp_async4_v(dst + 8 * r + c, row + 8 * r + c);
-            }
-            if (r == 0) cp_async4_v(dst + K, row + K);
+        const float *a = row + KOFF;
+        if (span_rows) {
+            const int ph = (int)(((uintptr_t)a >> 2) & 3);
+            const float *a0 = a - ph;                                  // 16-byte aligned
+            cp_async16_v(dst + 8 * r, a0 + 8 * r);
+            cp_async16_v(dst + 8 * r + 4, a0 + 8 * r + 4);
+            if (r == 0 && ph != 0) cp_async16_zfill_v(dst + K, a0 + K, 4 * ph);
         } else {
 #pragma unroll
-            for (int c = 0; c < 8; c++) cp_async4_v(dst + 8 * r + c, row + 1 + 8 * r + c);
-            if (r == 0) cp_async4_v(dst + K, row);
+            for (int c = 0; c < 8; c++) cp_async4_v(dst + 8 * r + c, a + 8 * r + c);
         }
+        if (r == 0) cp_async4_v(dst + XROW - 1, MODE == IN_LOGITS ? row + K : row);
         cp_async_commit_v();
+    };
+    // this thread's 8 k-mer columns of a staged row: three aligned 128-bit loads (conflict free; 32-bit loads at a
+    // stride of 8 floats would hit 4 banks), then a shift by the row's phase (uniform over the CTA)
+    auto load_cols = [&](const float *xr, int ph, float (&x)[8]) {
+        const float4 xa = reinterpret_cast<const float4 *>(xr)[2 * r], xb = reinterpret_cast<const float4 *>(xr)[2 * r + 1];
+        if (ph == 0) {
+            x[0] = xa.x; x[1] = xa.y; x[2] = xa.z; x[3] = xa.w; x[4] = xb.x; x[5] = xb.y; x[6] = xb.z; x[7] = xb.w;
+            return;
+        }
+        const float4 xc = reinterpret_cast<const float4 *>(xr)[2 * r + 2];
+        const float w[12] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w, xc.x, xc.y, xc.z, xc.w};
+        if (ph == 1) {
+#pragma unroll
+            for (int c = 0; c < 8; c++) x[c] = w[c + 1];
+        } else if (ph == 2) {
+#pragma unroll
+            for (int c = 0; c < 8; c++) x[c] = w[c + 2];
+        } else {
+#pragma unroll
+            for (int c = 0; c < 8; c++) x[c] = w[c + 3];
+        }
     };
     auto lpost_of = [&](float v, float2 ms) -> float {
         if (MODE == IN_LOG) return v;
@@ -283,16 +315,19 @@ viterbi_k1024_kernel(const float *__restrict__ post, long ld_t, long ld_b, const
         return logf(__fadd_rn(__fadd_rn(c0, __fmul_rn(c1, v)), VIT_ETA));
     };
 
+    const float *rowq = pb;                                           // row of the event being consumed (phase only)
     row_stats(0);
     stage_row(0);
     cp_async_wait0_v();
     __syncthreads();
     {
         const float2 ms = ms_s[0];
-        const float4 qa = reinterpret_cast<const float4 *>(xrow_s[0])[2 * r], qb = reinterpret_cast<const float4 *>(xrow_s[0])[2 * r + 1];
+        float q[8];
+        load_cols(xrow_s[0], phase_of(rowq), q);
+        rowq += ld_t;
         float4 va, vb;
-        va.x = lpost_of(qa.x, ms); va.y = lpost_of(qa.y, ms); va.z = lpost_of(qa.z, ms); va.w = lpost_of(qa.w, ms);
-        vb.x = lpost_of(qb.x, ms); vb.y = lpost_of(qb.y, ms); vb.z = lpost_of(qb.z, ms); vb.w = lpost_of(qb.w, ms);
+        va.x = lpost_of(q[0], ms); va.y = lpost_of(q[1], ms); va.z = lpost_of(q[2], ms); va.w = lpost_of(q[3], ms);
+        vb.x = lpost_of(q[4], ms); vb.y = lpost_of(q[5], ms); vb.z = lpost_of(q[6], ms); vb.w = lpost_of(q[7], ms);
         reinterpret_cast<float4 *>(vbuf[0])[2 * r] = va;             // v_0 = lpost[0][1:]   (decode.py:57)
         reinterpret_cast<float4 *>(vbuf[0])[2 * r + 1] = vb;
     }
@@ -304,9 +339,10 @@ viterbi_k1024_kernel(const float *__restrict__ post, long ld_t, long ld_b, const
     uint32_t *tbp = reinterpret_cast<uint32_t *>(tbb) + r;            // this thread's two traceback entries, advanced per event
     for (int i = 1; i < nev; i++) {
         const float *xr = xrow_s[i & 1];
-        const float4 xa = reinterpret_cast<const float4 *>(xr)[2 * r], xb = reinterpret_cast<const float4 *>(xr)[2 * r + 1];
-        const float x[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
-        const float x0 = xr[K];
+        float x[8];
+        load_cols(xr, phase_of(rowq), x);
+        rowq += ld_t;
+        const float x0 = xr[XROW - 1];
         const float2 ms = ms_s[i & 1];
         if (i + 1 < nev) { row_stats(i + 1); stage_row((i + 1) & 1); }  // next event, asynchronous
         const float *p = vbuf[cur];

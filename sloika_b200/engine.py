@@ -98,6 +98,7 @@ TIMER = KernelTimer()
 # Number of batches the caller keeps in flight on separate CUDA streams (`basecall.basecall_chunk_stream`, bench.py).
 # Only a scheduling hint for the recurrence kernel (how many sequences share a CTA); results do not depend on it.
 BATCHES_IN_FLIGHT = 1
+_CONCURRENT_BRANCHES = 1      # > 1 while the branches of a Parallel layer are being enqueued on side streams
 
 
 def set_batches_in_flight(k, gemm_sms=None):
@@ -307,7 +308,7 @@ def run_gru(layer, act, out=None):
     launch('gru_recurrence', 1, lib.sloika_gru_recurrence_fwd_ex,
            cabi.ptr(vI), _row_stride(vI), cabi.ptr(layer.sW.device(dev)), cabi.ptr(layer.sW2.device(dev)), cabi.ptr(y),
            _row_stride(y), cabi.ptr(act.lengths), act.T, act.B, H, 1 if act.reverse else 0,
-           code_of(layer.fun), code_of(layer.gatefun), act.B * max(1, BATCHES_IN_FLIGHT), st)
+           code_of(layer.fun), code_of(layer.gatefun), act.B * max(1, BATCHES_IN_FLIGHT) * _CONCURRENT_BRANCHES, st)
     # h is a convex combination of act(.) values when the gates are sigmoids
     return act.like(y, bounded=_bounded_fun(layer.fun) and code_of(layer.gatefun) == 2)
 
@@ -346,36 +347,72 @@ def run_window(layer, act, out=None):
 _SLICE_WRITERS = {}
 
 
+_SIDE_STREAMS = {}            # (device, launching stream) -> side streams for the branches of a Parallel layer
+
+
+def _side_streams(dev, n):
+    import torch
+    key = (str(dev), torch.cuda.current_stream(dev).cuda_stream)
+    have = _SIDE_STREAMS.setdefault(key, [])
+    while len(have) < n:
+        have.append(torch.cuda.Stream(dev))
+    return have[:n]
+
+
 def run_parallel(layer, act, out=None):
-    """Parallel.run (`layers.py:1486-1487`): sub-layers write their column slice of one buffer."""
+    """Parallel.run (`layers.py:1486-1487`): sub-layers write their column slice of one buffer.
+
+    The branches are independent, so every branch after the first is enqueued on a side stream that forks from and
+    joins the launching stream: the two directions of a birnn (`layers.py:1622-1629`) scan at the same time instead
+    of paying the recurrence latency twice per layer (each occupies at most 128 SMs at one CTA per SM)."""
+    import torch
     from sloika_b200 import layers as L
     y = _out_buffer(act, act.T, layer.size, out)
+    dev = act.device
+    nsub = len(layer.layers)
+    concurrent = nsub > 1 and not os.environ.get('SLOIKA_B200_SERIAL_BRANCHES')
+    main = torch.cuda.current_stream(dev)
+    sides = _side_streams(dev, nsub - 1) if concurrent else []
+    if concurrent:
+        fork = torch.cuda.Event()
+        fork.record(main)
+    global _CONCURRENT_BRANCHES
+    saved_branches = _CONCURRENT_BRANCHES
+    if concurrent:
+        _CONCURRENT_BRANCHES = saved_branches * nsub       # the recurrence kernels of the branches share the SMs
     col = 0
     result = None
     bounded = True
-    for sub in layer.layers:
+    for idx, sub in enumerate(layer.layers):
         view = y[:, :, col:col + sub.size]
         inner, flips = sub, 0
         while isinstance(inner, L.Reverse):
             inner, flips = inner.layer, flips + 1
         src = act.flipped() if flips % 2 else act
-        if isinstance(inner, L.Gru):
-            res = run_gru(inner, src, out=view)
-        elif isinstance(inner, L.Lstm):
-            res = run_lstm(inner, src, out=view)
-        elif isinstance(inner, L.FeedForward):
-            res = run_feedforward(inner, src, out=view)
-        elif isinstance(inner, L.Softmax):
-            res = run_softmax(inner, src, out=view)
-        else:
-            res = sub.run(act)                  # nested containers: run, then place
-            view.copy_(res.data)
-            res = act.like(view, res.lengths, bounded=res.bounded)
-            flips = 0
+        stream = sides[idx - 1] if (concurrent and idx > 0) else main
+        if stream is not main:
+            stream.wait_event(fork)
+        with torch.cuda.stream(stream):
+            if isinstance(inner, L.Gru):
+                res = run_gru(inner, src, out=view)
+            elif isinstance(inner, L.Lstm):
+                res = run_lstm(inner, src, out=view)
+            elif isinstance(inner, L.FeedForward):
+                res = run_feedforward(inner, src, out=view)
+            elif isinstance(inner, L.Softmax):
+                res = run_softmax(inner, src, out=view)
+            else:
+                res = sub.run(act)                  # nested containers: run, then place
+                view.copy_(res.data)
+                res = act.like(view, res.lengths, bounded=res.bounded)
+                flips = 0
+        if stream is not main:
+            main.wait_stream(stream)
         if result is None:
             result = res.flipped() if flips % 2 else res
         bounded = bounded and res.bounded
         col += sub.size
+    _CONCURRENT_BRANCHES = saved_branches
     return Act(y, result.lengths, act.reverse, bounded)
 
 
