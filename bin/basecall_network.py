@@ -122,7 +122,9 @@ def main(argv=None):
         torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', '0')))
         dist.init_process_group('nccl')
 
-    compiled_file = helpers.compile_model(args.model, args.compile)
+    # under torchrun every rank would check and write the same --compile file: rank 0 writes it, the others compile
+    # into a private temporary file
+    compiled_file = helpers.compile_model(args.model, args.compile if rank == 0 else None)
     basecall.init_worker(compiled_file)
     seq_printer = basecall.SeqPrinter(args.kmer_len, datatype=args.datatype, transducer=args.transducer,
                                       alphabet=args.alphabet)

@@ -357,18 +357,70 @@ def raw_batch(fast5_file_names, trim=(200, 10), open_pore_fraction=0, kmer_len=5
         for k, sig, (score, path) in zip(keep, signals, calls):
             results[slots[k]] = (names[k], np.float32(score), path, len(sig))
         return results
-    # trimming and normalisation on the device, for the whole batch at once
-    x, lens_d, lens_h = prepare_signals_device(raws, trim, open_pore_fraction)
-    if (lens_h < 0).any():
-        raise ValueError("zero-size array to reduction operation minimum which has no identity")   # trim_open_pore
-    calls = basecall_prepared(x, lens_d, kmer_len=kmer_len, min_prob=min_prob, skip=skip, nbase=len(alphabet),
-                              assemble=(alphabet, transducer))
-    for k, (score, path) in enumerate(calls):
-        if lens_h[k] == 0:
+    # trimming and normalisation on the device.  Every read of a device batch is padded to the longest one, and the
+    # logits alone take ~4 KB per event and slot: reads are therefore taken longest first and cut into sub-batches
+    # under a padded-sample budget (many short reads together, an ultra-long read on its own), and a sub-batch that
+    # still runs out of device memory is split and retried instead of aborting the run.
+    order = sorted(range(len(raws)), key=lambda k: -len(raws[k]))
+    for group in plan_sub_batches([len(raws[k]) for k in order], padded_sample_budget()):
+        _raw_sub_batch([order[g] for g in group], raws, names, slots, fast5_file_names, results, trim, open_pore_fraction,
+                       kmer_len, min_prob, skip, alphabet, transducer)
+    return results
+
+
+def padded_sample_budget():
+    """Padded raw samples (batch size x longest read) one device batch may hold: SLOIKA_B200_BATCH_SAMPLES, else a third
+    of the free device memory at ~1.5 KB per sample (logits + traceback + activations of a stride-5 network)."""
+    import os
+    env = os.environ.get('SLOIKA_B200_BATCH_SAMPLES')
+    if env:
+        return max(1, int(env))
+    import torch
+    free, _total = torch.cuda.mem_get_info(calc_post.device if calc_post is not None else None)
+    return max(1 << 20, int(free / 3 / 1500))
+
+
+def plan_sub_batches(lengths, budget):
+    """Greedy grouping of reads sorted longest first: a group is closed when adding the next read would push
+    (group size x longest read of the group) over `budget`.  Returns lists of positions; a read longer than the
+    budget gets a group of its own."""
+    groups, cur, longest = [], [], 0
+    for pos, n in enumerate(lengths):
+        if cur and (len(cur) + 1) * max(longest, n) > budget:
+            groups.append(cur)
+            cur, longest = [], 0
+        cur.append(pos)
+        longest = max(longest, n)
+    if cur:
+        groups.append(cur)
+    return groups
+
+
+def _raw_sub_batch(ks, raws, names, slots, fast5_file_names, results, trim, open_pore_fraction, kmer_len, min_prob, skip,
+                   alphabet, transducer):
+    import torch
+    try:
+        x, lens_d, lens_h = prepare_signals_device([raws[k] for k in ks], trim, open_pore_fraction)
+        if (lens_h < 0).any():
+            raise ValueError("zero-size array to reduction operation minimum which has no identity")   # trim_open_pore
+        calls = basecall_prepared(x, lens_d, kmer_len=kmer_len, min_prob=min_prob, skip=skip, nbase=len(alphabet),
+                                  assemble=(alphabet, transducer))
+    except torch.cuda.OutOfMemoryError:
+        x = lens_d = calls = None
+        torch.cuda.empty_cache()
+        if len(ks) == 1:
+            sys.stderr.write("Read does not fit in device memory, file {}\n".format(fast5_file_names[slots[ks[0]]]))
+            return
+        half = len(ks) // 2
+        for part in (ks[:half], ks[half:]):
+            _raw_sub_batch(part, raws, names, slots, fast5_file_names, results, trim, open_pore_fraction, kmer_len, min_prob,
+                           skip, alphabet, transducer)
+        return
+    for j, (k, (score, path)) in enumerate(zip(ks, calls)):
+        if lens_h[j] == 0:
             sys.stderr.write("Read too short in file {}\n".format(fast5_file_names[slots[k]]))
             continue
-        results[slots[k]] = (names[k], np.float32(score), path, int(lens_h[k]))
-    return results
+        results[slots[k]] = (names[k], np.float32(score), path, int(lens_h[j]))
 
 
 def _to_device(inMat):

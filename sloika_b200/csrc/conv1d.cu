@@ -23,8 +23,8 @@ conv1d_raw_kernel(const float *__restrict__ x, const float *__restrict__ W, cons
                   int stride, int pad_l, int Tout, int TT, int BT, int act, unsigned *__restrict__ absmax_bits)
 {
     extern __shared__ float xs[];                    // [rows][BT]
-    const int b0 = blockIdx.x * BT;
-    const int t0 = blockIdx.y * TT;
+    const int b0 = blockIdx.y * BT;           // time tiles on grid.x (2^31 - 1 of them), batch tiles on grid.y
+    const int t0 = blockIdx.x * TT;
     const int rows = (TT - 1) * stride + WIN;
     const int nc4 = Cout >> 2;
     const int bq = blockDim.x / nc4;                 // sequences handled per pass
@@ -87,8 +87,11 @@ conv1d_raw_kernel(const float *__restrict__ x, const float *__restrict__ W, cons
     if (absmax_bits) {
         // non-negative floats order like their bit patterns; a NaN has the largest pattern, so it also reads as "huge"
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(__activemask(), amax, o));
-        if ((threadIdx.x & 31) == 0) atomicMax(absmax_bits, __float_as_uint(amax));
+        // the block size (a multiple of Cout / 4) need not be a multiple of 32 and threads leave the loops above at
+        // different times: reduce over whoever is here with the hardware reduction under the real mask
+        const unsigned mask = __activemask();
+        const unsigned wmax = __reduce_max_sync(mask, __float_as_uint(amax));
+        if ((threadIdx.x & 31) == (unsigned)(__ffs(mask) - 1)) atomicMax(absmax_bits, wmax);
     }
 }
 
@@ -158,9 +161,9 @@ extern "C" int sloika_conv1d_fwd_ex(const float *x, const float *W, const float 
         const int BT = 32, TT = 16;
         const int nc4 = Cout / 4;
         const int threads = (256 / nc4) * nc4;
-        dim3 grid((unsigned)ceil_div(B, BT), (unsigned)ceil_div(Tout, TT));
+        dim3 grid((unsigned)ceil_div(Tout, TT), (unsigned)ceil_div(B, BT));
         const size_t smem = sizeof(float) * ((size_t)(TT - 1) * stride + winlen) * BT;
-        if (smem <= 48 * 1024) {
+        if (smem <= 48 * 1024 && ceil_div(B, BT) <= 65535) {
             conv1d_raw_kernel<11><<<grid, threads, smem, st>>>(x, W, bias, y, ldy, lengths, T, B, Cout, stride,
                                                                pad_l, Tout, TT, BT, act, absmax_bits);
             SLOIKA_RETURN_LAUNCH_STATUS();

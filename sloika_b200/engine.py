@@ -198,6 +198,10 @@ def run_convolution(layer, act, out=None):
     assert act.F == layer.insize, "Convolution input has {} features, expected {}".format(act.F, layer.insize)
     if act.ld != act.F:
         raise ValueError("Convolution needs a dense input")
+    if act.reverse:
+        # Reverse only flips a direction flag that the recurrent kernels honour; conv(x[::-1])[::-1] differs from
+        # conv(x) for even windows, asymmetric padding or stride > 1, and no shipped model reverses a convolution
+        raise NotImplementedError("Reverse(Convolution) is not implemented on the device")
     Tout = output_length(act.T, layer.winlen, layer.stride, layer.padding)
     y = _out_buffer(act, Tout, layer.size, out)
     dev = act.device

@@ -53,6 +53,16 @@ _SHARED_NAMES = ('TensorSharedVariable', 'CudaNdarraySharedVariable', 'ScalarSha
                  'SharedVariable', 'GpuArraySharedVariable')
 
 
+_ALLOWED_GLOBALS = {
+    ('numpy._core.multiarray', '_reconstruct'), ('numpy._core.multiarray', 'scalar'),
+    ('numpy', 'ndarray'), ('numpy', 'dtype'), ('copyreg', '_reconstructor'), ('copy_reg', '_reconstructor'),
+    ('collections', 'OrderedDict'), ('builtins', 'object'), ('builtins', 'tuple'), ('builtins', 'list'),
+    ('builtins', 'dict'), ('builtins', 'set'), ('builtins', 'frozenset'), ('builtins', 'bytearray'),
+    ('__builtin__', 'object'), ('_codecs', 'encode'),
+    ('sloika_b200.layers', 'Param'),
+}
+
+
 class _SloikaUnpickler(pickle.Unpickler):
     def find_class(self, module, name):
         if module == 'sloika.layers' or module == 'sloika_b200.layers':
@@ -79,7 +89,11 @@ class _SloikaUnpickler(pickle.Unpickler):
         if module.startswith('numpy.core'):
             # numpy >= 2 moved numpy.core -> numpy._core; keep old pickles quiet
             module = 'numpy._core' + module[len('numpy.core'):]
-        return super().find_class(module, name)
+        # everything else a Sloika model pickle legitimately names; any other global (os.system, builtins.eval, ...)
+        # is refused, so unpickling cannot be made to call arbitrary code
+        if (module, name) in _ALLOWED_GLOBALS:
+            return super().find_class(module, name)
+        raise ModelFormatError("model pickle names {}.{}, which a Sloika model does not need".format(module, name))
 
 
 def _is_shared(obj):

@@ -241,6 +241,28 @@ def test_raw_batch_with_device_preprocessing_equals_host_preprocessing(tmp_path,
         assert a[0] == b[0] and a[3] == b[3] and list(a[2]) == list(b[2]) and a[1] == b[1]
 
 
+def test_raw_batch_splits_under_sample_budget(tmp_path, pretrained, reads_daq, read_basecalls, monkeypatch):
+    """With a small padded-sample budget the CLI's batch is cut into length-sorted sub-batches (down to single
+    reads); the calls are the same as with one big batch."""
+    from h5write import write_fast5
+    files = []
+    for i, name in enumerate(('read7', 'read5', 'read3')):
+        offset, rng_, digi = reads_daq[name + '_scaling']
+        fn = str(tmp_path / (name + '.fast5'))
+        write_fast5(fn, reads_daq[name], float(offset), float(rng_), float(digi), read_number=i)
+        files.append(fn)
+    basecall.calc_post = pretrained.compile()
+    try:
+        whole = basecall.raw_batch(files)
+        monkeypatch.setenv('SLOIKA_B200_BATCH_SAMPLES', '70000')     # read3 (51 k) alone, read5 + read7 together
+        split = basecall.raw_batch(files)
+    finally:
+        basecall.calc_post = None
+    for a, b in zip(whole, split):
+        assert a[0] == b[0] and a[3] == b[3] and list(a[2]) == list(b[2]) and abs(a[1] - b[1]) < 1e-3
+    assert list(whole[0][2]) == read_basecalls['read7']['path']
+
+
 # ------------------------------------------------------------------ full benchmark size (BASELINE.json configs[2])
 def test_full_size_batch_properties():
     """rgrgr at the benchmark's size (1024 chunks x 4000 samples): properties that do not need an oracle run of that

@@ -369,3 +369,28 @@ def test_seqprinter_uses_device_assembled_sequence_only_when_conventions_match(c
     assert host_seq != 'NNNNNNN'
     from sloika_b200 import transducer
     assert transducer.argmax(3.0, 9.0, 1.0) == (1, 9.0)                      # transducer.py:9-11
+
+
+def test_unpickler_refuses_globals_a_model_does_not_need():
+    """A model pickle cannot name arbitrary callables (find_class used to fall through to pickle's own)."""
+    import pickle
+
+    class Evil(object):
+        def __reduce__(self):
+            import os
+            return (os.system, ('true',))
+    with pytest.raises(model_io.ModelFormatError):
+        model_io.loads(pickle.dumps(Evil(), protocol=3))
+
+
+def test_sub_batches_under_a_padded_sample_budget():
+    """Reads sorted longest first are grouped so that (reads x longest read) stays under the budget; an outlier
+    longer than the budget is called on its own (one ultra-long read used to inflate a 64-read batch)."""
+    from sloika_b200.basecall import plan_sub_batches
+    lengths = [1000000, 60000, 59000, 58000, 100, 90]
+    groups = plan_sub_batches(lengths, 200000)
+    assert groups[0] == [0]
+    assert sorted(p for g in groups for p in g) == list(range(6))
+    for g in groups[1:]:
+        assert len(g) * max(lengths[p] for p in g) <= 200000
+    assert plan_sub_batches([], 10) == [] and plan_sub_batches([5], 1) == [[0]]
