@@ -74,33 +74,47 @@ def existing(path):
     return path
 
 
+def _common(p):
+    """Options shared by both sub-commands (reference `bin/basecall_network.py:22-48`)."""
+    p.add_argument('--alphabet', default='ACGT', help='Alphabet of the sequences')
+    p.add_argument('--compile', default=None, help='File output compiled model')
+    p.add_argument('--input_strand_list', default=None, type=existing, help='Strand summary file containing subset')
+    p.add_argument('--jobs', default=1, metavar='n', type=positive_int,
+                   help='Processes parsing fast5 files (the network itself runs on the GPU of this process)')
+    p.add_argument('--kmer_len', default=5, metavar='length', type=positive_int, help='Length of kmer')
+    p.add_argument('--limit', default=None, metavar='reads', type=positive_int, help='Limit number of reads to process')
+    p.add_argument('--min_prob', metavar='proportion', default=1e-5, type=proportion,
+                   help='Minimum allowed probabiility for basecalls')
+    p.add_argument('--skip', default=0.0, type=non_negative(float), help='Skip penalty')
+    p.add_argument('--trans', default=None, type=proportion, nargs=3, metavar=('stay', 'step', 'skip'),
+                   help='Base transition probabilities (non-transducer models)')
+    p.add_argument('--transducer', default=True, action=AutoBool, help='Model is transducer')
+    p.add_argument('model', type=existing, help='Pickled model file')
+    p.add_argument('input_folder', type=existing, help='Directory containing single-read fast5 files')
+
+
 def build_parser():
     parser = argparse.ArgumentParser(description='1D basecaller for RNNs (B200)',
                                      formatter_class=argparse.ArgumentDefaultsHelpFormatter)
     sub = parser.add_subparsers(help='command', dest='command')
     sub.required = True
+    ev = sub.add_parser('events', help='basecall from events', formatter_class=argparse.ArgumentDefaultsHelpFormatter)
+    _common(ev)
+    ev.add_argument('--bad', default=True, action=AutoBool, help='Model emits bad events as a separate state')
+    ev.add_argument('--section', default='template', choices=['template', 'complement'], help='Section to call')
+    ev.add_argument('--segmentation', default='Segmentation', metavar='location',
+                    help='Location of segmentation information')
+    ev.add_argument('--trim', default=(50, 1), nargs=2, type=non_negative(int), metavar=('beginning', 'end'),
+                    help='Number of events to trim off start and end')
+    ev.set_defaults(datatype='events')
     raw = sub.add_parser('raw', help='basecall from raw signal', formatter_class=argparse.ArgumentDefaultsHelpFormatter)
-    raw.add_argument('--alphabet', default='ACGT', help='Alphabet of the sequences')
-    raw.add_argument('--compile', default=None, help='File output compiled model')
-    raw.add_argument('--input_strand_list', default=None, type=existing, help='Strand summary file containing subset')
-    raw.add_argument('--jobs', default=1, metavar='n', type=positive_int,
-                     help='Processes parsing fast5 files (the network itself runs on the GPU of this process)')
-    raw.add_argument('--kmer_len', default=5, metavar='length', type=positive_int, help='Length of kmer')
-    raw.add_argument('--limit', default=None, metavar='reads', type=positive_int, help='Limit number of reads to process')
-    raw.add_argument('--min_prob', metavar='proportion', default=1e-5, type=proportion,
-                     help='Minimum allowed probabiility for basecalls')
-    raw.add_argument('--skip', default=0.0, type=non_negative(float), help='Skip penalty')
-    raw.add_argument('--trans', default=None, type=proportion, nargs=3, metavar=('stay', 'step', 'skip'),
-                     help='Base transition probabilities (non-transducer models only; unused)')
-    raw.add_argument('--transducer', default=True, action=AutoBool, help='Model is transducer')
+    _common(raw)
     raw.add_argument('--bad', default=True, action=AutoBool, help='Model emits bad signal blocks as a separate state')
     raw.add_argument('--open_pore_fraction', metavar='proportion', default=0, type=proportion,
                      help='Max fraction of signal to trim due to open pore')
     raw.add_argument('--trim', default=(200, 10), nargs=2, type=non_negative(int), metavar=('beginning', 'end'),
                      help='Number of samples to trim off start and end')
     raw.add_argument('--batch', default=64, type=positive_int, help='Reads per device batch')
-    raw.add_argument('model', type=existing, help='Pickled model file')
-    raw.add_argument('input_folder', type=existing, help='Directory containing single-read fast5 files')
     raw.set_defaults(datatype='samples')
     return parser
 
@@ -135,7 +149,15 @@ def main(argv=None):
     nbases = nevents = 0
     t0 = time.time()
     results = []
-    chunks = [[files[i] for i in mine[lo:lo + args.batch]] for lo in range(0, len(mine), args.batch)]
+    if args.command == 'events':
+        # the events route (reference `basecall.events_worker`): one read per call, as the reference does
+        for i in mine:
+            results.append(basecall.events_worker(files[i], section=args.section, segmentation=args.segmentation,
+                                                  trim=tuple(args.trim), kmer_len=args.kmer_len,
+                                                  transducer=args.transducer, bad=args.bad, min_prob=args.min_prob,
+                                                  alphabet=args.alphabet, skip=args.skip, trans=args.trans))
+    chunks = [] if args.command == 'events' else \
+        [[files[i] for i in mine[lo:lo + args.batch]] for lo in range(0, len(mine), args.batch)]
     # with --jobs the files of the next batch are parsed by the pool while this batch is on the device
     ahead = basecall.read_files(chunks[0], reader_pool, wait=False) if (reader_pool is not None and chunks) else None
     for k, chunk in enumerate(chunks):

@@ -169,6 +169,33 @@ int sloika_window_fwd(const float *x, long ldx, float *y, long ldy, const int32_
                       void *stream);
 
 /*
+ * olddecode.decode_profile -- sloika/olddecode.py:13-73 (non-transducer models; reached from basecall.decode_post,
+ * sloika/basecall.py:47-50), one CTA per read.
+ *   post   [T,B,K] posteriors over the K = 4^k k-mer states (K a multiple of 16, <= 4096), element (t,b,j) at
+ *          post[t*ld_t + b*ld_b + j]; log_mode != 0: log-probabilities already (`log=True`)
+ *   ltrans per-event log weights (stay, step, skip) as float64 [B][T][3] (read b at ltrans + b*ldw_b) with log 4 and
+ *          log 16 ALREADY SUBTRACTED from the step and skip columns (olddecode.py:31-32), or NULL for no weights
+ *   slip   probability of a slip from the best state (0 -> log(1e-10))
+ *   tb_ws  sloika_olddecode_workspace_bytes(T,B,K) bytes (int32 predecessor per state and event)
+ *   seq_out int32 [B,T]: ONE state per event (stays included); score_out float64 [B].
+ * The recursion is float64 on float32 log-posteriors (the reference's arithmetic under NumPy >= 2).
+ */
+size_t sloika_olddecode_workspace_bytes(int T, int B, int K);
+int sloika_olddecode_fwd(const float *post, long ld_t, long ld_b, const double *ltrans, long ldw_b, const int32_t *lengths,
+                         int T, int B, int K, double slip, int log_mode, void *tb_ws, size_t ws_bytes, int32_t *seq_out,
+                         double *score_out, void *stream);
+
+/* The per-event sums of olddecode.estimate_transitions -- sloika/olddecode.py:101-109: res[ev-1] = (stay, step, skip)
+ * for ev = 1..T-1 (row T-1 is left to the caller), float64 [T,3]; post [T,K] float32 with row pitch ld_t. */
+int sloika_transitions_fwd(const float *post, long ld_t, int T, int K, double *res, void *stream);
+
+/* Forward-only scoring -- bin/validate_network.py:46-54: over M rows of S posteriors (row pitch ld) with one int32
+ * label each, ADDS sum_m -log post[m][label[m]] to *loss_sum (float64) and the number of rows whose first maximum is the
+ * label to *ncorrect (both device words, zeroed by the caller). */
+int sloika_score_fwd(const float *post, long ld, const int32_t *labels, long M, int S, double *loss_sum,
+                     unsigned long long *ncorrect, void *stream);
+
+/*
  * decode.prepare_post + decode.viterbi -- sloika/decode.py:21-36, :39-93 (called from
  * sloika/basecall.py:44-46), batched: one CTA per read.
  *   post: [T,B,S] with S = nbase^klen + 1, element (t,b,s) at post[t*ld_t + b*ld_b + s]

@@ -34,8 +34,13 @@ def decode_post(post, kmer_len, transducer, bad, min_prob, skip=5.0, trans=None,
     """
     assert post.shape[2] == nstate(kmer_len, transducer=transducer, bad_state=bad, nbase=nbase)
     if not transducer:
-        raise NotImplementedError("the non-transducer decoder (sloika/olddecode.py) is not on the "
-                                  "B200 raw basecall path; all raw models are transducers")
+        # legacy models (`basecall.py:47-50`): drop bad events, estimate per-event transition weights, old decoder
+        from sloika_b200 import olddecode
+        assert nbase == 4, "Modified bases not supported by old decoder"
+        post = decode._as_device(post)
+        post = decode.prepare_post(post, min_prob=min_prob, drop_bad=bad and not transducer)
+        est = olddecode.estimate_transitions(post, trans=trans, return_device=True)
+        return olddecode.decode_profile(post, trans=(eta + est).log(), log=False)
     assert post.shape[1] == 1, "decode_post decodes one read; use decode.viterbi_batch for batches"
     score, paths = decode.viterbi_batch(post, None, klen=kmer_len, skip_pen=skip, min_prob=min_prob,
                                         nbase=nbase)
@@ -326,8 +331,11 @@ def raw_batch(fast5_file_names, trim=(200, 10), open_pore_fraction=0, kmer_len=5
     :param loaded: optional result of `read_files(fast5_file_names, ...)` obtained earlier (prefetched by the caller
         while the previous batch was on the device)
     """
-    assert transducer, "only transducer models are supported"
     import os
+    if not transducer:
+        # legacy (non-transducer) raw models: the old decoder works on one read at a time
+        return [raw_worker(fn, trim, open_pore_fraction, kmer_len, transducer, bad, min_prob, alphabet=alphabet,
+                           skip=skip, trans=trans) for fn in fast5_file_names]
     names, raws, slots = [], [], []
     results = [None] * len(fast5_file_names)
     if loaded is None:
@@ -421,6 +429,34 @@ def _raw_sub_batch(ks, raws, names, slots, fast5_file_names, results, trim, open
             sys.stderr.write("Read too short in file {}\n".format(fast5_file_names[slots[k]]))
             continue
         results[slots[k]] = (names[k], np.float32(score), path, int(lens_h[j]))
+
+
+def events_worker(fast5_file_name, section, segmentation, trim, kmer_len, transducer,
+                  bad, min_prob, alphabet=DEFAULT_ALPHABET, skip=5.0, trans=None):
+    """ Worker function for basecalling one fast5 file from events (`basecall.py:54-85`)
+
+    :param section: part of read to basecall, 'template' or 'complement'
+    :param segmentation: location of segmentation analysis for extracting target read section
+    :param trim: (int, int) events to remove from read beginning and end
+    :returns: (read name, score, state path, number of events) or None (message on stderr, as the reference)
+    """
+    from sloika_b200 import features
+    from sloika_b200.fast5 import Fast5
+    try:
+        with Fast5(fast5_file_name) as f5:
+            ev = f5.get_section_events(section, analysis=segmentation)
+            sn = f5.filename_short
+    except Exception as e:
+        sys.stderr.write("Error getting events for section {!r} in file {}\n{!r}\n".format(section, fast5_file_name, e))
+        return None
+    ev = util.trim_array(ev, *trim)
+    if ev.size == 0:
+        sys.stderr.write("Read too short in file {}\n".format(fast5_file_name))
+        return None
+    inMat = features.from_events(ev, tag='')[:, None, :]
+    post = calc_post.forward_device(_to_device(inMat))
+    score, call = decode_post(post.data, kmer_len, transducer, bad, min_prob, skip, trans, nbase=len(alphabet))
+    return sn, score, call, inMat.shape[0]
 
 
 def _to_device(inMat):

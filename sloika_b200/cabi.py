@@ -36,6 +36,10 @@ EXPORTS = {
     'sloika_gru_recurrence_fwd': (_i, [_p, _l, _p, _p, _p, _l, _p, _i, _i, _i, _i, _i, _i, _p]),
     'sloika_b200_set_gemm_sm_budget': (_i, [_i]),
     'sloika_lstm_recurrence_fwd': (_i, [_p, _l, _p, _p, _p, _l, _p, _i, _i, _i, _i, _i, _i, _p]),
+    'sloika_olddecode_workspace_bytes': (_z, [_i, _i, _i]),
+    'sloika_olddecode_fwd': (_i, [_p, _l, _l, _p, _l, _p, _i, _i, _i, ctypes.c_double, _i, _p, _z, _p, _p, _p]),
+    'sloika_transitions_fwd': (_i, [_p, _l, _i, _i, _p, _p]),
+    'sloika_score_fwd': (_i, [_p, _l, _p, _l, _i, _p, _p, _p]),
     'sloika_window_fwd': (_i, [_p, _l, _p, _l, _p, _i, _i, _i, _i, _p]),
     'sloika_gru_recurrence_fwd_ex': (_i, [_p, _l, _p, _p, _p, _l, _p, _i, _i, _i, _i, _i, _i, _l, _p]),
     'sloika_viterbi_workspace_bytes': (_z, [_i, _i, _i, _i]),

@@ -153,6 +153,38 @@ class H5File(object):
             return np.dtype('{}f{}'.format(order, size)), 8 + 12
         if cls == 3:        # fixed-length string
             return np.dtype('S{}'.format(size)), 8
+        if cls == 8:        # enumeration (h5py stores bool arrays as an int8 enum): the base type is what is stored
+            nmemb = bits0 | (b[pos + 2] << 8)
+            base, used = self._datatype(pos + 8)
+            cur = pos + 8 + used
+            version = b[pos] >> 4
+            for _ in range(nmemb):
+                end = b.index(b'\x00', cur)
+                cur = cur + ((end - cur) // 8 + 1) * 8 if version < 3 else end + 1
+            return base, cur + nmemb * base.itemsize - pos
+        if cls == 6:        # compound (event tables): versions 1-3 of the datatype message
+            version = b[pos] >> 4
+            nmemb = bits0 | (b[pos + 2] << 8)
+            cur = pos + 8
+            names, formats, offsets = [], [], []
+            for _ in range(nmemb):
+                end = b.index(b'\x00', cur)
+                names.append(bytes(b[cur:end]).decode('ascii'))
+                if version < 3:
+                    cur += ((end - cur) // 8 + 1) * 8                    # name null padded to a multiple of 8
+                    offsets.append(self._u(cur, 4))
+                    cur += 4
+                    if version == 1:
+                        cur += 1 + 3 + 4 + 4 + 16                         # dimensionality, reserved, permutation, reserved, sizes
+                else:
+                    cur = end + 1
+                    nb = max(1, (int(size).bit_length() + 7) // 8)
+                    offsets.append(self._u(cur, nb))
+                    cur += nb
+                sub, used = self._datatype(cur)
+                formats.append(sub)
+                cur += used
+            return np.dtype({'names': names, 'formats': formats, 'offsets': offsets, 'itemsize': size}), cur - pos
         raise Fast5Error("datatype class {} not supported".format(cls))
 
     def _layout(self, pos):
@@ -402,6 +434,49 @@ class Fast5(object):
         meta = self.channel_meta
         raw_unit = float(meta['range']) / float(meta['digitisation'])
         return (signal + float(meta['offset'])) * raw_unit
+
+
+    def _event_detection_group(self):
+        groups = sorted(g for g in self._h5.children('/Analyses') if g.startswith('EventDetection'))
+        if not groups:
+            raise Fast5Error("{}: no EventDetection analysis".format(self.filename))
+        base = '/Analyses/' + groups[-1] + '/Reads'
+        reads = sorted(self._h5.children(base))
+        if not reads:
+            raise Fast5Error("{}: no event-detection reads".format(self.filename))
+        return base + '/' + reads[0]
+
+    def get_section_events(self, section, analysis='Segmentation'):
+        """Events of the 'template' or 'complement' section of the read, as `fast5_research.Fast5.get_section_events`
+        gives them to `basecall.events_worker` (`sloika/basecall.py:75-77`): the event-detection table
+        (`/Analyses/EventDetection_*/Reads/Read_*/Events`, fields start / length / mean / stdv) cut to the section
+        named by the segmentation summary (`/Analyses/<analysis>_*/Summary/<...>`), which gives either event indices
+        (`start_index_temp`, `end_index_temp`, ...) or sample positions (`first_sample_template`,
+        `duration_template`, ...).  fast5_research (>= 1.2.2, `requirements.txt:5`) is not vendored with the
+        reference and the bundled reads carry no event-detection group: restated from that package's documented
+        behaviour, exercised with synthetic files only."""
+        if section not in ('template', 'complement'):
+            raise ValueError("section must be 'template' or 'complement'")
+        grp = self._event_detection_group()
+        events = self._h5.dataset(grp + '/Events')
+        segs = sorted(g for g in self._h5.children('/Analyses') if g.startswith(analysis))
+        if not segs:
+            raise Fast5Error("{}: no {} analysis".format(self.filename, analysis))
+        summary = '/Analyses/' + segs[-1] + '/Summary'
+        attrs = {}
+        for child in self._h5.children(summary):
+            attrs.update(self._h5.attrs(summary + '/' + child))
+        short = 'temp' if section == 'template' else 'comp'
+        if 'start_index_' + short in attrs:
+            lo, hi = int(attrs['start_index_' + short]), int(attrs['end_index_' + short])
+            return events[lo:hi + 1]
+        if 'first_sample_' + section in attrs:
+            first, dur = int(attrs['first_sample_' + section]), int(attrs['duration_' + section])
+            start = events['start'].astype(np.int64)
+            start = start - (int(self._h5.attrs(grp).get('start_time', 0)) if start.size and start[0] > first + dur else 0)
+            keep = (start >= first) & (start < first + dur)
+            return events[keep]
+        raise Fast5Error("{}: segmentation summary names no {} section".format(self.filename, section))
 
 
 def iterate_fast5(path, strand_list=None, paths=False, mode='r', limit=None, files_group_pattern=None,

@@ -55,6 +55,7 @@ _SHARED_NAMES = ('TensorSharedVariable', 'CudaNdarraySharedVariable', 'ScalarSha
 
 _ALLOWED_GLOBALS = {
     ('numpy._core.multiarray', '_reconstruct'), ('numpy._core.multiarray', 'scalar'),
+    ('numpy._core.numeric', '_frombuffer'),                    # how NumPy 2 pickles arrays (files we wrote ourselves)
     ('numpy', 'ndarray'), ('numpy', 'dtype'), ('copyreg', '_reconstructor'), ('copy_reg', '_reconstructor'),
     ('collections', 'OrderedDict'), ('builtins', 'object'), ('builtins', 'tuple'), ('builtins', 'list'),
     ('builtins', 'dict'), ('builtins', 'set'), ('builtins', 'frozenset'), ('builtins', 'bytearray'),

@@ -222,3 +222,23 @@ def test_forward_oracle_whole_read_matches_reference(pretrained, reads_daq):
         post = forward_ref.run(desc, x)[:, 0]
         assert np.abs(post[fwd[name + '_rows']] - fwd[name + '_post']).max() < 2e-5
         assert np.abs(post.max(1) - fwd[name + '_rowmax']).max() < 2e-5
+
+
+# ---- non-transducer decoder: pinned to outputs of the reference's own olddecode.py (tools/make_golden_olddecode.py) ----
+def test_olddecode_oracle_matches_reference_outputs():
+    from oracle import olddecode_ref
+    data = np.load(os.path.join(GOLDEN, 'olddecode_cases.npz'))
+    with open(os.path.join(GOLDEN, 'olddecode_cases.json')) as fh:
+        meta = json.load(fh)
+    assert len(meta) >= 12
+    for case in meta:
+        name = case['name']
+        post = data[name + '/post']
+        if case['mode'] == 'profile':
+            prior = None if case['prior'] is None else np.array(case['prior'])
+            est = olddecode_ref.estimate_transitions(np.exp(post) if case['log'] else post, trans=prior)
+            assert np.array_equal(est, data[name + '/est']), name
+            score, seq = olddecode_ref.decode_profile(post, trans=data[name + '/ltrans'], log=case['log'], slip=case['slip'])
+        else:
+            score, seq = olddecode_ref.decode_profile(post, trans=None, log=case['log'], slip=case['slip'])
+        assert score == data[name + '/score'] and np.array_equal(seq, data[name + '/seq']), name
