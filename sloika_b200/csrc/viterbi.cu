@@ -232,6 +232,12 @@ viterbi_k1024_kernel(const float *__restrict__ post, long ld_t, long ld_b, const
     }
     const float *pb = post + (long)b * ld_b;
     uint16_t *tbb = reinterpret_cast<uint16_t *>(tb) + (size_t)b * (size_t)T * (size_t)TBROW;
+    // The thread's two quads 2r and 2r+1 are 32 bytes apart, so a warp's 128-bit accesses "quad 2r of every lane"
+    // would touch only every other 16-byte chunk: a 2-way bank conflict on each.  Lanes with bit 2 set therefore take
+    // their odd quad first (slot A) and the even one second (slot B): any 8 consecutive lanes then cover 8 different
+    // chunks modulo 128 bytes in both accesses.
+    const int swp = (r >> 2) & 1;
+    const int qa = 2 * r + swp, qb = 2 * r + 1 - swp;                 // quad index (16-byte chunk) of slot A / B
 
     // softmax row statistics of event i -> ms_s[i & 1] (warp 0; visible after the next barrier)
     const float2 *stp = stats + (long)b * n_slices + r;               // advanced by B*n_slices per event
@@ -272,8 +278,8 @@ viterbi_k1024_kernel(const float *__restrict__ post, long ld_t, long ld_b, const
         if (span_rows) {
             const int ph = (int)(((uintptr_t)a >> 2) & 3);
             const float *a0 = a - ph;                                  // 16-byte aligned
-            cp_async16_v(dst + 8 * r, a0 + 8 * r);
-            cp_async16_v(dst + 8 * r + 4, a0 + 8 * r + 4);
+            cp_async16_v(dst + 4 * qa, a0 + 4 * qa);
+            cp_async16_v(dst + 4 * qb, a0 + 4 * qb);
             if (r == 0 && ph != 0) cp_async16_zfill_v(dst + K, a0 + K, 4 * ph);
         } else {
 #pragma unroll
@@ -285,22 +291,29 @@ viterbi_k1024_kernel(const float *__restrict__ post, long ld_t, long ld_b, const
     // this thread's 8 k-mer columns of a staged row: three aligned 128-bit loads (conflict free; 32-bit loads at a
     // stride of 8 floats would hit 4 banks), then a shift by the row's phase (uniform over the CTA)
     auto load_cols = [&](const float *xr, int ph, float (&x)[8]) {
-        const float4 xa = reinterpret_cast<const float4 *>(xr)[2 * r], xb = reinterpret_cast<const float4 *>(xr)[2 * r + 1];
-        if (ph == 0) {
+        if (ph == 0) {          // slot order (A then B), see qa / qb
+            const float4 xa = reinterpret_cast<const float4 *>(xr)[qa], xb = reinterpret_cast<const float4 *>(xr)[qb];
             x[0] = xa.x; x[1] = xa.y; x[2] = xa.z; x[3] = xa.w; x[4] = xb.x; x[5] = xb.y; x[6] = xb.z; x[7] = xb.w;
             return;
         }
+        const float4 xa = reinterpret_cast<const float4 *>(xr)[2 * r], xb = reinterpret_cast<const float4 *>(xr)[2 * r + 1];
         const float4 xc = reinterpret_cast<const float4 *>(xr)[2 * r + 2];
         const float w[12] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w, xc.x, xc.y, xc.z, xc.w};
+        float y[8];
         if (ph == 1) {
 #pragma unroll
-            for (int c = 0; c < 8; c++) x[c] = w[c + 1];
+            for (int c = 0; c < 8; c++) y[c] = w[c + 1];
         } else if (ph == 2) {
 #pragma unroll
-            for (int c = 0; c < 8; c++) x[c] = w[c + 2];
+            for (int c = 0; c < 8; c++) y[c] = w[c + 2];
         } else {
 #pragma unroll
-            for (int c = 0; c < 8; c++) x[c] = w[c + 3];
+            for (int c = 0; c < 8; c++) y[c] = w[c + 3];
+        }
+#pragma unroll
+        for (int c = 0; c < 4; c++) {           // state order -> slot order
+            x[c] = swp ? y[4 + c] : y[c];
+            x[4 + c] = swp ? y[c] : y[4 + c];
         }
     };
     auto lpost_of = [&](float v, float2 ms) -> float {
@@ -328,8 +341,8 @@ viterbi_k1024_kernel(const float *__restrict__ post, long ld_t, long ld_b, const
         float4 va, vb;
         va.x = lpost_of(q[0], ms); va.y = lpost_of(q[1], ms); va.z = lpost_of(q[2], ms); va.w = lpost_of(q[3], ms);
         vb.x = lpost_of(q[4], ms); vb.y = lpost_of(q[5], ms); vb.z = lpost_of(q[6], ms); vb.w = lpost_of(q[7], ms);
-        reinterpret_cast<float4 *>(vbuf[0])[2 * r] = va;             // v_0 = lpost[0][1:]   (decode.py:57)
-        reinterpret_cast<float4 *>(vbuf[0])[2 * r + 1] = vb;
+        reinterpret_cast<float4 *>(vbuf[0])[qa] = va;                // v_0 = lpost[0][1:]   (decode.py:57); q[] is in slot order
+        reinterpret_cast<float4 *>(vbuf[0])[qb] = vb;
     }
     if (nev > 1) { row_stats(1); stage_row(1); }
     cp_async_wait0_v();
@@ -356,7 +369,10 @@ viterbi_k1024_kernel(const float *__restrict__ post, long ld_t, long ld_b, const
             if (c.y > ss.y) { ss.y = c.y; as1 = a; }
         }
         reinterpret_cast<float4 *>(m4_s)[r] = make_float4(ss.x, __int_as_float(4 * as0), ss.y, __int_as_float(4 * as1));
-        const float4 pa = reinterpret_cast<const float4 *>(p)[2 * r], pb4 = reinterpret_cast<const float4 *>(p)[2 * r + 1];
+        const float4 pa = reinterpret_cast<const float4 *>(p)[qa], pb4 = reinterpret_cast<const float4 *>(p)[qb];
+        // step maximum / argument of slot A and slot B
+        const float ssA = swp ? ss.y : ss.x, ssB = swp ? ss.x : ss.y;
+        const int asA = swp ? as1 : as0, asB = swp ? as0 : as1;
         const float lp0 = lpost_of(x0, ms);
         float lp[8];
 #pragma unroll
@@ -383,11 +399,12 @@ viterbi_k1024_kernel(const float *__restrict__ post, long ld_t, long ld_b, const
         float vo[8];
         unsigned packed = 0;
 #pragma unroll
-        for (int h = 0; h < 2; h++) {
-            const float ssh = h == 0 ? ss.x : ss.y;
+        unsigned ent[2];
+        for (int h = 0; h < 2; h++) {                                    // h = slot (A, B)
+            const float ssh = h == 0 ? ssA : ssB;
             const bool use_step = ssh > sk;                              // tie -> skip (decode.py:76)
             const float best = use_step ? ssh : sk;
-            unsigned e = (use_step ? (1u + (unsigned)(h == 0 ? as0 : as1)) : (5u + (unsigned)ak)) << 4;
+            unsigned e = (use_step ? (1u + (unsigned)(h == 0 ? asA : asB)) : (5u + (unsigned)ak)) << 4;
 #pragma unroll
             for (int c = 0; c < 4; c++) {
                 const float move = __fadd_rn(lp[4 * h + c], best);
@@ -396,10 +413,11 @@ viterbi_k1024_kernel(const float *__restrict__ post, long ld_t, long ld_b, const
                 vo[4 * h + c] = mv ? move : stay;
                 e |= (mv ? 1u : 0u) << c;
             }
-            packed |= e << (16 * h);
+            ent[h] = e;
         }
-        reinterpret_cast<float4 *>(vbuf[cur ^ 1])[2 * r] = make_float4(vo[0], vo[1], vo[2], vo[3]);
-        reinterpret_cast<float4 *>(vbuf[cur ^ 1])[2 * r + 1] = make_float4(vo[4], vo[5], vo[6], vo[7]);
+        packed = swp ? (ent[1] | (ent[0] << 16)) : (ent[0] | (ent[1] << 16));      // even quad in the low half
+        reinterpret_cast<float4 *>(vbuf[cur ^ 1])[qa] = make_float4(vo[0], vo[1], vo[2], vo[3]);
+        reinterpret_cast<float4 *>(vbuf[cur ^ 1])[qb] = make_float4(vo[4], vo[5], vo[6], vo[7]);
         tbp += TBROW / 2;
         *tbp = packed;
         cur ^= 1;
