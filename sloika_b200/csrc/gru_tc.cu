@@ -105,11 +105,10 @@ struct Bars {                 // per group
     uint64_t d1z;             // z pre-activations (committed after r's, which the dependent chain needs first)
 };
 
-constexpr int N = 8;          // sequences per group = N of every MMA (one core matrix wide)
-
-// G groups of 8 sequences per CTA; CW compute warps per group (4: a thread owns unit j for all 8 sequences,
-// 8: for 4 of them, 16: for 2), one issuing warp per group.
-template <int HP, int G, int CW>
+// G groups of N sequences per CTA (N = 8 or 16 = the N of every MMA: at N = 16 an instruction costs 9 cycles instead
+// of 8, so the tensor pipe -- the limiter once several groups share an SM -- serves twice the sequences); CW compute
+// warps per group (CW / 4 of them share a lane quarter and split the group's sequences), one issuing warp per group.
+template <int HP, int G, int CW, int N>
 __global__ void __launch_bounds__(G *(CW + 1) * 32, 1)
 gru_tc_kernel(const float *__restrict__ vI, long ldv, const float *__restrict__ sW, const float *__restrict__ sW2,
               float *__restrict__ y, long ldy, const int32_t *__restrict__ lengths, int T, int B, int H, int reverse)
@@ -117,13 +116,15 @@ gru_tc_kernel(const float *__restrict__ vI, long ldv, const float *__restrict__ 
     constexpr int KC = HP / 16;                   // K = 16 chunks
     constexpr int ACOLS = HP / 2;                 // TMEM columns of one A tile
     constexpr int D_BASE = 6 * ACOLS;             // accumulators behind the 6 weight tiles
-    constexpr int OPB = HP * 16;                  // bytes of one operand array: [k][8 sequences] fp16, MN-major
+    constexpr int OPB = HP * 2 * N;               // bytes of one operand array: [k][N sequences] fp16, MN-major core matrices
     constexpr int NCW = G * CW;                   // compute warps
     constexpr int NS = N / (CW / 4);              // sequences per compute thread
     constexpr int VLD = 3 * HP;                   // floats per staged vI row
     constexpr int NTHREADS = G * (CW + 1) * 32;
     static_assert(D_BASE + G * 3 * N <= 512, "tensor memory: 512 columns");
     static_assert(CW == 4 || CW == 8 || CW == 16, "compute warps per group");
+    static_assert(N == 8 || N == 16, "sequences per group");
+    static_assert(N / (CW / 4) >= 2 && N / (CW / 4) <= 8, "sequences per compute thread");
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
@@ -196,7 +197,10 @@ gru_tc_kernel(const float *__restrict__ vI, long ldv, const float *__restrict__ 
         const bool jop = j < HP;                       // this unit has a k row in the operands
         const bool jv = j < H;
         const int jc = jv ? j : H - 1;                 // clamped column for vI reads of padding rows
-        uint8_t *op = ops + (size_t)g * 4 * OPB + (size_t)(jop ? j : 0) * 16 + n0 * 2;      // row k = j, sequences n0..
+        // operand element (k, n): core matrices of 8 k rows x 8 sequences (128 bytes, a k row = 16 bytes); the N / 8 core
+        // matrices of a k block follow each other, k blocks after that
+        const int jk = jop ? j : 0;
+        uint8_t *op = ops + (size_t)g * 4 * OPB + (size_t)(jk >> 3) * (16 * N) + (size_t)(n0 >> 3) * 128 + (jk & 7) * 16 + (n0 & 7) * 2;
         const float *vbase = vring + (size_t)g * 3 * N * VLD + n0 * VLD + jc;
         int len[NS];
 #pragma unroll
@@ -296,8 +300,8 @@ gru_tc_kernel(const float *__restrict__ vI, long ldv, const float *__restrict__ 
         float *vr0 = vring + (size_t)g * 3 * N * VLD;
         const uint32_t idesc = umma_idesc_f16_m128_bmn(N);
         const uint32_t dz = tmem_base + (uint32_t)(D_BASE + g * 3 * N), dr = dz + N, dc = dz + 2 * N;
-        const uint64_t b_hh = umma_desc_mn8_noswizzle(op), b_hl = umma_desc_mn8_noswizzle(op + OPB);
-        const uint64_t b_rh = umma_desc_mn8_noswizzle(op + 2 * OPB), b_rl = umma_desc_mn8_noswizzle(op + 3 * OPB);
+        const uint64_t b_hh = umma_desc_mn_noswizzle(op, N), b_hl = umma_desc_mn_noswizzle(op + OPB, N);
+        const uint64_t b_rh = umma_desc_mn_noswizzle(op + 2 * OPB, N), b_rl = umma_desc_mn_noswizzle(op + 3 * OPB, N);
         const uint32_t rowbytes = (uint32_t)((3 * H + 3) / 4 * 4) * 4u;     // <= ldv * 4: vI rows are 16-byte multiples
         auto load_vi = [&](int st) {                                       // elected lane: vI rows of scan step st
             if (st >= T) return;
@@ -320,7 +324,7 @@ gru_tc_kernel(const float *__restrict__ vI, long ldv, const float *__restrict__ 
                     // r first: the dependent chain (r -> r*h -> candidate) waits for it; z is needed only at the blend
 #pragma unroll
                     for (int kc = 0; kc < KC; kc++) {
-                        const uint64_t koff = (uint64_t)(kc * 16);         // 256 bytes per K = 16 step
+                        const uint64_t koff = (uint64_t)(kc * 2 * N);      // 32 N bytes per K = 16 step
                         const uint32_t acol = tmem_base + (uint32_t)(kc * 8);
                         umma_f16_ts(dr, acol + 2 * ACOLS, b_hh + koff, idesc, kc != 0);
                         umma_f16_ts(dr, acol + 3 * ACOLS, b_hh + koff, idesc, true);
@@ -329,7 +333,7 @@ gru_tc_kernel(const float *__restrict__ vI, long ldv, const float *__restrict__ 
                     umma_commit(&bar.d1);
 #pragma unroll
                     for (int kc = 0; kc < KC; kc++) {
-                        const uint64_t koff = (uint64_t)(kc * 16);
+                        const uint64_t koff = (uint64_t)(kc * 2 * N);
                         const uint32_t acol = tmem_base + (uint32_t)(kc * 8);
                         umma_f16_ts(dz, acol + 0 * ACOLS, b_hh + koff, idesc, kc != 0);
                         umma_f16_ts(dz, acol + 1 * ACOLS, b_hh + koff, idesc, true);
@@ -346,7 +350,7 @@ gru_tc_kernel(const float *__restrict__ vI, long ldv, const float *__restrict__ 
                 if (elect_one()) {
 #pragma unroll
                     for (int kc = 0; kc < KC; kc++) {
-                        const uint64_t koff = (uint64_t)(kc * 16);
+                        const uint64_t koff = (uint64_t)(kc * 2 * N);
                         const uint32_t acol = tmem_base + (uint32_t)(kc * 8);
                         umma_f16_ts(dc, acol + 4 * ACOLS, b_rh + koff, idesc, kc != 0);
                         umma_f16_ts(dc, acol + 5 * ACOLS, b_rh + koff, idesc, true);
@@ -364,15 +368,15 @@ gru_tc_kernel(const float *__restrict__ vI, long ldv, const float *__restrict__ 
     if (warp == NCW) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
-template <int HP, int G, int CW>
+template <int HP, int G, int CW, int N>
 static int launch(const float *vI, long ldv, const float *sW, const float *sW2, float *y, long ldy, const int32_t *lengths,
                   int T, int B, int H, int reverse, cudaStream_t st)
 {
-    size_t smem = 128 + (size_t)G * 4 * HP * 16 + (size_t)G * 3 * N * 3 * HP * 4 + (size_t)G * sizeof(Bars) + 64;
+    size_t smem = 128 + (size_t)G * 4 * HP * 2 * N + (size_t)G * 3 * N * 3 * HP * 4 + (size_t)G * sizeof(Bars) + 64;
     // every CTA of this kernel owns the whole tensor memory of its SM: ask for more than half of the shared memory
     // so that a second one (another stream's batch) is placed on a free SM instead of stalling in tcgen05.alloc
     if (smem < 116 * 1024) smem = 116 * 1024;
-    auto kern = gru_tc_kernel<HP, G, CW>;
+    auto kern = gru_tc_kernel<HP, G, CW, N>;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return (int)err;
     const unsigned grid = (unsigned)ceil_div(B, G * N);
@@ -381,14 +385,15 @@ static int launch(const float *vI, long ldv, const float *sW, const float *sW2, 
 }
 
 template <int HP>
-static int launch_hp(int g, int cw, const float *vI, long ldv, const float *sW, const float *sW2, float *y, long ldy,
+static int launch_hp(int g, int cw, int n, const float *vI, long ldv, const float *sW, const float *sW2, float *y, long ldy,
                      const int32_t *lengths, int T, int B, int H, int reverse, cudaStream_t st)
 {
-#define TC_SHAPE(G_, CW_) \
-    if (g == G_ && cw == CW_) return launch<HP, G_, CW_>(vI, ldv, sW, sW2, y, ldy, lengths, T, B, H, reverse, st)
-    TC_SHAPE(1, 4); TC_SHAPE(1, 8); TC_SHAPE(1, 16);
-    TC_SHAPE(2, 4); TC_SHAPE(2, 8);
-    if constexpr (3 * HP + 4 * 24 <= 512) { TC_SHAPE(4, 4); }
+#define TC_SHAPE(G_, CW_, N_) \
+    if (g == G_ && cw == CW_ && n == N_) return launch<HP, G_, CW_, N_>(vI, ldv, sW, sW2, y, ldy, lengths, T, B, H, reverse, st)
+    TC_SHAPE(1, 4, 8); TC_SHAPE(1, 8, 8); TC_SHAPE(1, 16, 8);
+    TC_SHAPE(2, 4, 8); TC_SHAPE(2, 8, 8);
+    TC_SHAPE(4, 4, 8);
+    TC_SHAPE(1, 8, 16); TC_SHAPE(2, 8, 16);
 #undef TC_SHAPE
     return SLOIKA_ERR_UNSUPPORTED;
 }
@@ -397,21 +402,22 @@ static int launch_hp(int g, int cw, const float *vI, long ldv, const float *sW, 
 // falls back to gru_h16.cu).  `seqs_in_flight` is the number of sequences the caller keeps on the device at once
 // (this batch times the batches it pipelines on other streams): it picks how many groups of 8 sequences share a
 // CTA, i.e. whether the SMs are spread over one batch (latency) or packed (throughput).
-// SLOIKA_B200_GRU_TC="G,CW" overrides (groups per CTA, compute warps per group).
+// SLOIKA_B200_GRU_TC="G,CW[,N]" overrides (groups per CTA, compute warps per group, sequences per group).
 int dispatch(const float *vI, long ldv, const float *sW, const float *sW2, float *y, long ldy, const int32_t *lengths, int T,
              int B, int H, int reverse, int act, int gate_act, long seqs_in_flight, cudaStream_t st)
 {
     if (act != SLOIKA_ACT_TANH || gate_act != SLOIKA_ACT_SIGMOID) return SLOIKA_ERR_UNSUPPORTED;
     if (H > 128 || (ldv & 3) != 0 || ((uintptr_t)vI & 15) != 0) return SLOIKA_ERR_UNSUPPORTED;
     const long load = seqs_in_flight > B ? seqs_in_flight : B;
-    int g = 1, cw = 8;
+    int g = 1, cw = 8, n = 8;
     if (load > 8L * 148) { g = 2; cw = 8; }
-    if (load > 16L * 148 && H <= 96) { g = 4; cw = 4; }
+    if (load > 16L * 148) { g = 2; cw = 8; n = 16; }       // 32 sequences per CTA, half the MMAs of 4 groups of 8
     if (const char *ov = getenv("SLOIKA_B200_GRU_TC")) {
-        int og = 0, ocw = 0;
-        if (sscanf(ov, "%d,%d", &og, &ocw) == 2) { g = og; cw = ocw; }
+        int og = 0, ocw = 0, on = 8;
+        const int got = sscanf(ov, "%d,%d,%d", &og, &ocw, &on);
+        if (got >= 2) { g = og; cw = ocw; n = got == 3 ? on : 8; }
     }
-#define TC_CASE(HP_) return launch_hp<HP_>(g, cw, vI, ldv, sW, sW2, y, ldy, lengths, T, B, H, reverse, st)
+#define TC_CASE(HP_) return launch_hp<HP_>(g, cw, n, vI, ldv, sW, sW2, y, ldy, lengths, T, B, H, reverse, st)
     if (H <= 32) TC_CASE(32);
     if (H <= 64) TC_CASE(64);
     if (H <= 96) TC_CASE(96);

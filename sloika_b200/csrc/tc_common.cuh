@@ -177,6 +177,18 @@ __device__ __forceinline__ uint64_t umma_desc_mn8_noswizzle(uint32_t addr) {
     d |= (uint64_t)1 << 46;
     return d;
 }
+// The same for n sequences (a multiple of 8): the n / 8 core matrices of a k block are contiguous (128 bytes apart),
+// k blocks follow each other (16 n bytes apart).  For an MN-major no-swizzle operand the "leading dimension byte
+// offset" field is the distance between core matrices along K and the "stride dimension byte offset" the distance
+// along MN (settled numerically: the other assignment fails the N = 16 parity tests).
+__device__ __forceinline__ uint64_t umma_desc_mn_noswizzle(uint32_t addr, int n) {
+    uint64_t d = 0;
+    d |= (uint64_t)((addr >> 4) & 0x3fff);
+    d |= (uint64_t)((16 * n) >> 4) << 16;     // next core matrix along K
+    d |= (uint64_t)(128 >> 4) << 32;          // next core matrix along MN
+    d |= (uint64_t)1 << 46;
+    return d;
+}
 // Instruction descriptor for kind::tf32, fp32 accumulate, both operands K-major, M = 128.
 __host__ __device__ __forceinline__ uint32_t umma_idesc_tf32_m128(int n) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);

@@ -127,7 +127,8 @@ def test_gru(I, H, T, B, reverse):
 @pytest.mark.parametrize('env', [{'SLOIKA_B200_GRU': 'v1'}, {'SLOIKA_B200_GRU': 'v3'}, {'SLOIKA_B200_GRU': 'v4'},
                                  {'SLOIKA_B200_GRU_TC': '1,4'}, {'SLOIKA_B200_GRU_TC': '1,8'},
                                  {'SLOIKA_B200_GRU_TC': '1,16'}, {'SLOIKA_B200_GRU_TC': '2,4'},
-                                 {'SLOIKA_B200_GRU_TC': '2,8'}, {'SLOIKA_B200_GRU_TC': '4,4'}])
+                                 {'SLOIKA_B200_GRU_TC': '2,8'}, {'SLOIKA_B200_GRU_TC': '4,4'},
+                                 {'SLOIKA_B200_GRU_TC': '1,8,16'}, {'SLOIKA_B200_GRU_TC': '2,8,16'}])
 @pytest.mark.parametrize('I,H,T,B,reverse', [(96, 96, 90, 37, False), (40, 110, 50, 21, True), (20, 128, 40, 9, False),
                                              (24, 48, 30, 50, True)])
 def test_gru_every_kernel_generation(env, I, H, T, B, reverse, monkeypatch):

@@ -10,7 +10,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
 
-from sloika_b200 import basecall, decode, transducer, zoo
+from sloika_b200 import basecall, decode, engine, layers, olddecode, transducer, validate, zoo
+from sloika_b200 import module_tools as smt
 
 DEV = torch.device('cuda:0')
 
@@ -33,6 +34,25 @@ def main():
         net = build().compile()
         out = net.forward_device(torch.randn((400, 5, 1), device=DEV), None, fused_decode=True)
         decode.viterbi_batch(out, None, min_prob=1e-5)
+    # every shape of the tensor-memory recurrence (groups per CTA, compute warps per group, sequences per group)
+    g = layers.Gru(40, 96, init=smt.partial(smt.truncated_normal, sd=0.5), has_bias=True)
+    xg = torch.tanh(torch.randn((50, 37, 40), device=DEV))
+    for shape in ('1,4', '1,8', '1,16', '2,4', '2,8', '4,4', '1,8,16', '2,8,16'):
+        os.environ['SLOIKA_B200_GRU_TC'] = shape
+        engine.run_gru(g, engine.Act(xg, None))
+        engine.run_gru(g, engine.Act(xg, torch.randint(1, 51, (37,), dtype=torch.int32, device=DEV), reverse=True))
+    os.environ.pop('SLOIKA_B200_GRU_TC')
+    # events route: Window + birnn(Lstm), old decoder, transition estimates, scoring
+    init = smt.partial(smt.truncated_normal, sd=0.5)
+    lstm = lambda i, o: layers.Lstm(i, o, init=init, has_bias=True, has_peep=True)
+    ev_net = layers.Serial([layers.Window(4, 3), layers.birnn(lstm(12, 64), lstm(12, 64)),
+                            layers.FeedForward(128, 64, init=init, has_bias=True),
+                            layers.Softmax(64, 1024, init=init, has_bias=True)])
+    post = ev_net.compile().forward_device(torch.randn((70, 1, 4), device=DEV)).data
+    est = olddecode.estimate_transitions(post[:, 0], return_device=True)
+    olddecode.decode_profile(post[:, 0], trans=(1e-10 + est).log())
+    validate.wrap_network(ev_net.compile())(np.random.standard_normal((30, 3, 4)).astype(np.float32),
+                                             np.random.randint(0, 1024, (30, 3)).astype(np.int32))
     # remap decode, both launch geometries
     rng = np.random.default_rng(2)
     for T, B, S, P in ((60, 5, 65, 40), (40, 3, 65, 1100)):
