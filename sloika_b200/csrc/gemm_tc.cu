@@ -69,7 +69,9 @@ __host__ __device__ inline size_t smem_bytes(int BN, int nkb, int stages, bool f
 {
     size_t w = (size_t)2 * nkb * BN * (f16 ? 64 : 128);    // W_hi + W_lo
     size_t a = (size_t)stages * (f16 ? 1 : 2) * A_TILE_BYTES;   // tf32: (hi, lo) per stage; f16: hi16 | lo16 in place of the raw tile
-    size_t stg = (size_t)8 * 32 * STG_LD * 4;              // epilogue transpose buffers (one per epilogue warp)
+    // epilogue staging per epilogue warp: 32 x STG_LD floats (transposing fallback) or 32 x 32 swizzled boxes for the TMA
+    // stores -- two of them in the f16 form, whose weights leave the room (the tf32 form would lose slice width)
+    size_t stg = f16 ? (size_t)8 * 2 * 4096 : (size_t)8 * 32 * STG_LD * 4;
     size_t misc = (size_t)BN * 4 + 512;                    // bias slice + barriers
     return w + a + stg + misc + 1024;                      // + alignment slack
 }
@@ -96,7 +98,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
     uint8_t *Abase = Wlo + (size_t)nkb * BN * WROW;                       // stage s: raw tile, converted in place to hi; lo behind it
                                                                           // (F16: raw tile replaced by hi16 | lo16, 8 KB each)
     float *stg_all = reinterpret_cast<float *>(Abase + (size_t)STAGES * STAGE_BYTES);
-    float *bias_s = stg_all + 8 * 32 * STG_LD;
+    float *bias_s = stg_all + (F16 ? 8 * 2 * 1024 : 8 * 32 * STG_LD);
     uint64_t *bars = reinterpret_cast<uint64_t *>(bias_s + BN);
     uint64_t *full_raw = bars;                     // [STAGES] TMA -> transform
     uint64_t *full_split = bars + MAX_STAGES;      // [STAGES] transform -> MMA
@@ -106,8 +108,9 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
     uint32_t *tmem_base_s = reinterpret_cast<uint32_t *>(tmem_empty + NACC);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int slice = blockIdx.x % p.n_slices;
+    const int slice = blockIdx.x % p.n_slices;             // slices interleaved: the CTAs that share an x tile run together
     const int cta_in_slice = blockIdx.x / p.n_slices;
+    const int mt_stride = p.ctas_per_slice;
     const int n0 = slice * BN;
     const long m_tiles = (p.M + BM - 1) / BM;
 
@@ -147,7 +150,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
         // ================= TMA producer =================
         if (lane == 0) {
             uint32_t it = 0;
-            for (long mt = cta_in_slice; mt < m_tiles; mt += p.ctas_per_slice) {
+            for (long mt = cta_in_slice; mt < m_tiles; mt += mt_stride) {
                 for (int kb = 0; kb < nkb; kb++, it++) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
@@ -162,7 +165,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
         if (lane == 0) {
             const uint32_t idesc = F16 ? tc::umma_idesc_f16_m128(BN) : tc::umma_idesc_tf32_m128(BN);
             uint32_t it = 0, tile = 0;
-            for (long mt = cta_in_slice; mt < m_tiles; mt += p.ctas_per_slice, tile++) {
+            for (long mt = cta_in_slice; mt < m_tiles; mt += mt_stride, tile++) {
                 const int a = tile % NACC;
                 const uint32_t aph = (tile / NACC) & 1;
                 tc::mbar_wait(&tmem_empty[a], aph ^ 1);
@@ -219,7 +222,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
         // ================= transform: fp32 -> (hi, lo) =================
         const int tt = tid - 6 * 32;                            // 0..127
         uint32_t it = 0;
-        for (long mt = cta_in_slice; mt < m_tiles; mt += p.ctas_per_slice) {
+        for (long mt = cta_in_slice; mt < m_tiles; mt += mt_stride) {
             for (int kb = 0; kb < nkb; kb++, it++) {
                 const int s = it % STAGES;
                 const uint32_t ph = (it / STAGES) & 1;
@@ -292,10 +295,12 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
         const int lq = warp & 3;
         float *stg = stg_all + (eg * 4 + lq) * 32 * STG_LD;
         // TMA-store path: a dense 32 x 32 fp32 box per warp in the SWIZZLE_128B layout (1024-byte aligned)
-        uint8_t *stg_t = reinterpret_cast<uint8_t *>(stg_all) + (eg * 4 + lq) * 4096;
+        // two staging boxes per warp: the TMA engine may still be reading one while the next is filled
+        uint8_t *stg_t2 = reinterpret_cast<uint8_t *>(stg_all) + (eg * 4 + lq) * (F16 ? 8192 : 4096);
+        uint32_t box = 0;
         const int nchunks = (BN + 31) / 32;
         uint32_t tile = 0;
-        for (long mt = cta_in_slice; mt < m_tiles; mt += p.ctas_per_slice, tile++) {
+        for (long mt = cta_in_slice; mt < m_tiles; mt += mt_stride, tile++) {
             const int a = tile % NACC;
             const uint32_t aph = (tile / NACC) & 1;
             tc::mbar_wait(&tmem_full[a], aph);
@@ -316,8 +321,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
                     tc::mbar_arrive(&tmem_empty[a]);
                     released = true;
                 }
-                if (p.tma_out) {                                 // the previous box of this warp has left shared memory
-                    if (lane == 0) tc::bulk_wait_read();
+                uint8_t *stg_t = stg_t2 + ((!F16 || (p.dbg & 8)) ? 0u : (box & 1u)) * 4096;
+                box++;
+                if (p.tma_out) {                                 // the store that last used THIS box has left shared memory
+                    if (lane == 0) { if (!F16 || (p.dbg & 8)) tc::bulk_wait_read(); else tc::bulk_wait_read1(); }   // (at most the other box's store is still in flight)
                     __syncwarp();
                 }
                 // thread = row: bias + activation
@@ -549,6 +556,9 @@ int launch(const float *x, long ldx, const float *W, const float *bias, float *y
     long per = sms / n_slices;
     if (per > m_tiles) per = m_tiles;
     p.ctas_per_slice = (int)per;
+    // (Tried: giving a narrower last slice -- 1025 logits = 4 x 224 + 129 -- CTAs in proportion to its width so that
+    // it does not finish early.  The slices then walk the m-tiles at different paces, their x tiles stop meeting in L2,
+    // and both GEMM shapes get 20-30 % slower: every slice keeps the same number of CTAs.)
     // Pipeline depth (measured sweep, tools/gemm_bench.py SHAPES=sweep): with few slices a deeper ring of x tiles
     // hides more HBM latency (best at ~5); with many slices (softmax logits: write dominated, every x tile is
     // re-read by each slice's CTA out of L2) a deep ring lets the slices drift apart and costs up to 25 %.
