@@ -16,7 +16,18 @@ namespace sloika {
 //   thread = (c4, bq): fixed group of 4 output channels (weights + bias live in registers for the
 //   whole CTA), loops over (t, b) pairs; a warp writes consecutive float4 of the dense [B, Cout]
 //   slab of one time step -> fully coalesced 128-bit stores.
-template <int WIN>
+// Epilogue activations with the MUFU-based forms (absolute error ~1e-7, as in the recurrence epilogues): the
+// accurate expm1f / tanhf of libdevice cost 25-40 instructions per value and made this kernel issue-bound at 24 % of
+// the HBM rate (271 warp instructions per float4 of output, profiles/r2_step_kernels_ncu.txt).
+template <int ACT>
+__device__ __forceinline__ float conv_act(float v) {
+    if constexpr (ACT == SLOIKA_ACT_ELU) return v > 0.0f ? v : ex2_ftz(v * SLOIKA_LOG2E) - 1.0f;
+    else if constexpr (ACT == SLOIKA_ACT_TANH) return tanh_fast(v);
+    else if constexpr (ACT == SLOIKA_ACT_SIGMOID) return sigmoid_fast(v);
+    else return v;
+}
+
+template <int WIN, int ACT>
 __global__ void __launch_bounds__(256, 2)
 conv1d_raw_kernel(const float *__restrict__ x, const float *__restrict__ W, const float *__restrict__ bias,
                   float *__restrict__ y, long ldy, const int32_t *__restrict__ lengths, int T, int B, int Cout,
@@ -43,15 +54,15 @@ conv1d_raw_kernel(const float *__restrict__ x, const float *__restrict__ W, cons
         xs[e] = v;
     }
 
-    float4 w[WIN];
+    float2 wa[WIN], wb[WIN];                         // channels (4c4, 4c4+1) and (4c4+2, 4c4+3): packed fp32x2 FMAs
     float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
     if (bl < bq) {
 #pragma unroll
         for (int k = 0; k < WIN; k++) {
-            w[k].x = __ldg(W + (4 * c4 + 0) * WIN + k);
-            w[k].y = __ldg(W + (4 * c4 + 1) * WIN + k);
-            w[k].z = __ldg(W + (4 * c4 + 2) * WIN + k);
-            w[k].w = __ldg(W + (4 * c4 + 3) * WIN + k);
+            wa[k].x = __ldg(W + (4 * c4 + 0) * WIN + k);
+            wa[k].y = __ldg(W + (4 * c4 + 1) * WIN + k);
+            wb[k].x = __ldg(W + (4 * c4 + 2) * WIN + k);
+            wb[k].y = __ldg(W + (4 * c4 + 3) * WIN + k);
         }
         bv = __ldg(reinterpret_cast<const float4 *>(bias) + c4);
     }
@@ -65,20 +76,20 @@ conv1d_raw_kernel(const float *__restrict__ x, const float *__restrict__ W, cons
         for (int b = bl; b < BT; b += bq) {
             const int bg = b0 + b;
             if (bg >= B) break;
-            float4 acc = bv;
+            float2 a0 = make_float2(bv.x, bv.y), a1 = make_float2(bv.z, bv.w);
             const float *xp = xs + (tl * stride) * BT + b;
 #pragma unroll
             for (int k = 0; k < WIN; k++) {
                 const float xv = xp[k * BT];
-                acc.x = fmaf(w[k].x, xv, acc.x);
-                acc.y = fmaf(w[k].y, xv, acc.y);
-                acc.z = fmaf(w[k].z, xv, acc.z);
-                acc.w = fmaf(w[k].w, xv, acc.w);
+                const float2 x2 = make_float2(xv, xv);
+                a0 = fma2(wa[k], x2, a0);
+                a1 = fma2(wb[k], x2, a1);
             }
-            acc.x = apply_act(acc.x, act);
-            acc.y = apply_act(acc.y, act);
-            acc.z = apply_act(acc.z, act);
-            acc.w = apply_act(acc.w, act);
+            float4 acc;
+            acc.x = conv_act<ACT>(a0.x);
+            acc.y = conv_act<ACT>(a0.y);
+            acc.z = conv_act<ACT>(a1.x);
+            acc.w = conv_act<ACT>(a1.y);
             float *yp = y + ((long)t * B + bg) * ldy + 4 * c4;
             __stcs(reinterpret_cast<float4 *>(yp), acc);     // streamed once, read by the next layer
             amax = fmaxf(amax, fmaxf(fmaxf(fabsf(acc.x), fabsf(acc.y)), fmaxf(fabsf(acc.z), fabsf(acc.w))));
@@ -164,8 +175,15 @@ extern "C" int sloika_conv1d_fwd_ex(const float *x, const float *W, const float 
         dim3 grid((unsigned)ceil_div(Tout, TT), (unsigned)ceil_div(B, BT));
         const size_t smem = sizeof(float) * ((size_t)(TT - 1) * stride + winlen) * BT;
         if (smem <= 48 * 1024 && ceil_div(B, BT) <= 65535) {
-            conv1d_raw_kernel<11><<<grid, threads, smem, st>>>(x, W, bias, y, ldy, lengths, T, B, Cout, stride,
-                                                               pad_l, Tout, TT, BT, act, absmax_bits);
+#define CONV_RAW(A) conv1d_raw_kernel<11, A><<<grid, threads, smem, st>>>(x, W, bias, y, ldy, lengths, T, B, Cout, stride, \
+                                                                       pad_l, Tout, TT, BT, act, absmax_bits)
+            switch (act) {
+                case SLOIKA_ACT_ELU: CONV_RAW(SLOIKA_ACT_ELU); break;
+                case SLOIKA_ACT_TANH: CONV_RAW(SLOIKA_ACT_TANH); break;
+                case SLOIKA_ACT_SIGMOID: CONV_RAW(SLOIKA_ACT_SIGMOID); break;
+                default: CONV_RAW(SLOIKA_ACT_LINEAR); break;
+            }
+#undef CONV_RAW
             SLOIKA_RETURN_LAUNCH_STATUS();
         }
     }
