@@ -239,18 +239,25 @@ viterbi_k1024_kernel(const float *__restrict__ post, long ld_t, long ld_b, const
     const int swp = (r >> 2) & 1;
     const int qa = 2 * r + swp, qb = 2 * r + 1 - swp;                 // quad index (16-byte chunk) of slot A / B
 
-    // softmax row statistics of event i -> ms_s[i & 1] (warp 0; visible after the next barrier)
+    // softmax row statistics of event i -> ms_s[i & 1] (warp 0; visible after the next barrier).  The (max, sum exp)
+    // pairs of an event are LOADED one event before they are reduced (`stats_load` into a register, `stats_reduce` an
+    // iteration later): reduced straight after the load, warp 0 sat out the HBM latency inside every event while the
+    // other warps waited for it at the barrier (34 % of all stall samples, profiles/r2_step_kernels_ncu.txt).
     const float2 *stp = stats + (long)b * n_slices + r;               // advanced by B*n_slices per event
     const long st_step = (long)B * n_slices;
-    auto row_stats = [&](int i) {
-        if (MODE != IN_LOGITS || r >= 32) return;
-        float m = -INFINITY, s = 0.0f;
-        if (r < n_slices) {
-            const float2 st = __ldg(stp);
+    int st_ev = 0;                                                     // next event whose statistics get loaded
+    auto stats_load = [&]() -> float2 {
+        float2 st = make_float2(-INFINITY, 0.0f);
+        if (MODE == IN_LOGITS && r < n_slices && st_ev < T) {
+            st = __ldg(stp);
             stp += st_step;
-            m = st.x;
-            s = st.y;
         }
+        st_ev++;
+        return st;
+    };
+    auto stats_reduce = [&](float2 st, int i) {
+        if (MODE != IN_LOGITS || r >= 32) return;
+        const float m = st.x, s = st.y;
         float mx = m;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
@@ -329,7 +336,9 @@ viterbi_k1024_kernel(const float *__restrict__ post, long ld_t, long ld_b, const
     };
 
     const float *rowq = pb;                                           // row of the event being consumed (phase only)
-    row_stats(0);
+    float2 st_next = stats_load();                                    // event 0
+    stats_reduce(st_next, 0);
+    st_next = stats_load();                                           // event 1 (reduced below; rows past the read are never used)
     stage_row(0);
     cp_async_wait0_v();
     __syncthreads();
@@ -344,7 +353,7 @@ viterbi_k1024_kernel(const float *__restrict__ post, long ld_t, long ld_b, const
         reinterpret_cast<float4 *>(vbuf[0])[qa] = va;                // v_0 = lpost[0][1:]   (decode.py:57); q[] is in slot order
         reinterpret_cast<float4 *>(vbuf[0])[qb] = vb;
     }
-    if (nev > 1) { row_stats(1); stage_row(1); }
+    if (nev > 1) { stats_reduce(st_next, 1); st_next = stats_load(); stage_row(1); }      // st_next: event 2
     cp_async_wait0_v();
     __syncthreads();
 
@@ -357,7 +366,11 @@ viterbi_k1024_kernel(const float *__restrict__ post, long ld_t, long ld_b, const
         rowq += ld_t;
         const float x0 = xr[XROW - 1];
         const float2 ms = ms_s[i & 1];
-        if (i + 1 < nev) { row_stats(i + 1); stage_row((i + 1) & 1); }  // next event, asynchronous
+        if (i + 1 < nev) {                                              // next event, asynchronous
+            stats_reduce(st_next, i + 1);                               // loaded an event ago
+            st_next = stats_load();                                     // event i + 2
+            stage_row((i + 1) & 1);
+        }
         const float *p = vbuf[cur];
         // step: first maximum over a of p[a*256 + q4] for the two quads q4 = 2r, 2r+1; published as (value, 4*a)
         float2 ss = reinterpret_cast<const float2 *>(p)[r];
