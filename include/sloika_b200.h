@@ -223,7 +223,8 @@ int sloika_viterbi_fwd(const float *post, long ld_t, long ld_b, const int32_t *l
  * the softmax division (layers.py:314), the min_prob floor (decode.py:36) and the log (decode.py:56) are
  * applied inside the kernel, so the posterior matrix never exists in HBM.  nbase = 4, klen = 5 only.
  *   logits: element (t, b, j) at logits[t*ld_t + b*ld_b + j], j < 1024 k-mer states, j = 1024 stay;
- *   stats: [T*B][n_slices] float pairs as written by sloika_softmax_logits_fwd.
+ *   stats: [T*B][n_slices] float pairs as written by sloika_softmax_logits_fwd (rows in (t, b) order: ld_t = B*ld_b);
+ *   they are first combined into one float per row in the tail of the workspace (two launches).
  */
 int sloika_viterbi_logits_fwd(const float *logits, long ld_t, long ld_b, const float *stats, int n_slices,
                               const int32_t *lengths, int T, int B, int nbase, int klen, double skip_pen,

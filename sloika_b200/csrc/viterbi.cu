@@ -203,14 +203,13 @@ __device__ __forceinline__ void cp_async_wait1_v() { asm volatile("cp.async.wait
 
 template <int MODE>
 __global__ void __launch_bounds__(VIT_THREADS, 7)      // 7 CTAs/SM: all 1024 reads of a batch resident in one wave on 148 SMs
-viterbi_k1024_kernel(const float *__restrict__ post, long ld_t, long ld_b, const float2 *__restrict__ stats, int n_slices,
+viterbi_k1024_kernel(const float *__restrict__ post, long ld_t, long ld_b, const float *__restrict__ rowms,
                      const int32_t *__restrict__ lengths, int T, int B, float skip_pen, float c0, float c1,
                      uint8_t *__restrict__ tb, int32_t *__restrict__ path_out,
                      int32_t *__restrict__ path_len, float *__restrict__ score_out)
 {
     constexpr int K = 1024, RS = 256, RK = 64, NT = VIT_THREADS;
     __shared__ __align__(16) float vbuf[2][K];
-    __shared__ float2 ms_s[2];                       // (-(m log2e + log2 rowsum), unused) of the softmax, double buffered
     __shared__ __align__(16) float2 m4_s[256];       // per quad q4: (max_a p[a*256 + q4], 4 * argmax) of the current event
     __shared__ float red_v[NT / 32];
     __shared__ int red_i[NT / 32];
@@ -239,33 +238,11 @@ viterbi_k1024_kernel(const float *__restrict__ post, long ld_t, long ld_b, const
     const int swp = (r >> 2) & 1;
     const int qa = 2 * r + swp, qb = 2 * r + 1 - swp;                 // quad index (16-byte chunk) of slot A / B
 
-    // softmax row statistics of event i -> ms_s[i & 1] (warp 0; visible after the next barrier).  The (max, sum exp)
-    // pairs of an event are LOADED one event before they are reduced (`stats_load` into a register, `stats_reduce` an
-    // iteration later): reduced straight after the load, warp 0 sat out the HBM latency inside every event while the
-    // other warps waited for it at the barrier (34 % of all stall samples, profiles/r2_step_kernels_ncu.txt).
-    const float2 *stp = stats + (long)b * n_slices + r;               // advanced by B*n_slices per event
-    const long st_step = (long)B * n_slices;
-    int st_ev = 0;                                                     // next event whose statistics get loaded
-    auto stats_load = [&]() -> float2 {
-        float2 st = make_float2(-INFINITY, 0.0f);
-        if (MODE == IN_LOGITS && r < n_slices && st_ev < T) {
-            st = __ldg(stp);
-            stp += st_step;
-        }
-        st_ev++;
-        return st;
-    };
-    auto stats_reduce = [&](float2 st, int i) {
-        if (MODE != IN_LOGITS || r >= 32) return;
-        const float m = st.x, s = st.y;
-        float mx = m;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        float tot = r < n_slices ? s * ex2_ftz((m - mx) * SLOIKA_LOG2E) : 0.0f;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-        if (r == 0) ms_s[i & 1] = make_float2(-(mx * SLOIKA_LOG2E + lg2_ftz(tot)), 0.0f);
-    };
+    // LOGITS mode: rowms[t*B + b] = -(row max * log2 e + log2 sum exp(logit - max)) of the softmax row, combined from the
+    // GEMM's per-slice statistics by softmax_rowms_kernel; it is staged with the row (xrow[XROW - 2]) like the stay
+    // column.  (It used to be reduced here, by warp 0 with ten shuffles per event, which every other warp then waited
+    // for at the barrier.)
+    const float *msp = MODE == IN_LOGITS ? rowms + b : nullptr;       // advanced by B per event
     // stage the row of the next event.  The k-mer columns of a row start at `a` = row (logits layout) or row + 1
     // (posterior layout), which is 16-byte aligned only in the first case; in general the row is copied as the
     // 16-byte ALIGNED chunks that cover it (257 128-bit cp.async per row instead of 1024 32-bit ones), keeping its
@@ -293,6 +270,10 @@ viterbi_k1024_kernel(const float *__restrict__ post, long ld_t, long ld_b, const
             for (int c = 0; c < 8; c++) cp_async4_v(dst + 8 * r + c, a + 8 * r + c);
         }
         if (r == 0) cp_async4_v(dst + XROW - 1, MODE == IN_LOGITS ? row + K : row);
+        if (MODE == IN_LOGITS && r == 32) {
+            cp_async4_v(dst + XROW - 2, msp);
+            msp += B;
+        }
         cp_async_commit_v();
     };
     // this thread's 8 k-mer columns of a staged row: three aligned 128-bit loads (conflict free; 32-bit loads at a
@@ -336,14 +317,11 @@ viterbi_k1024_kernel(const float *__restrict__ post, long ld_t, long ld_b, const
     };
 
     const float *rowq = pb;                                           // row of the event being consumed (phase only)
-    float2 st_next = stats_load();                                    // event 0
-    stats_reduce(st_next, 0);
-    st_next = stats_load();                                           // event 1 (reduced below; rows past the read are never used)
     stage_row(0);
     cp_async_wait0_v();
     __syncthreads();
     {
-        const float2 ms = ms_s[0];
+        const float2 ms = make_float2(xrow_s[0][XROW - 2], 0.0f);
         float q[8];
         load_cols(xrow_s[0], phase_of(rowq), q);
         rowq += ld_t;
@@ -353,7 +331,7 @@ viterbi_k1024_kernel(const float *__restrict__ post, long ld_t, long ld_b, const
         reinterpret_cast<float4 *>(vbuf[0])[qa] = va;                // v_0 = lpost[0][1:]   (decode.py:57); q[] is in slot order
         reinterpret_cast<float4 *>(vbuf[0])[qb] = vb;
     }
-    if (nev > 1) { stats_reduce(st_next, 1); st_next = stats_load(); stage_row(1); }      // st_next: event 2
+    if (nev > 1) stage_row(1);
     cp_async_wait0_v();
     __syncthreads();
 
@@ -365,12 +343,8 @@ viterbi_k1024_kernel(const float *__restrict__ post, long ld_t, long ld_b, const
         load_cols(xr, phase_of(rowq), x);
         rowq += ld_t;
         const float x0 = xr[XROW - 1];
-        const float2 ms = ms_s[i & 1];
-        if (i + 1 < nev) {                                              // next event, asynchronous
-            stats_reduce(st_next, i + 1);                               // loaded an event ago
-            st_next = stats_load();                                     // event i + 2
-            stage_row((i + 1) & 1);
-        }
+        const float2 ms = make_float2(xr[XROW - 2], 0.0f);
+        if (i + 1 < nev) stage_row((i + 1) & 1);                        // next event, asynchronous
         const float *p = vbuf[cur];
         // step: first maximum over a of p[a*256 + q4] for the two quads q4 = 2r, 2r+1; published as (value, 4*a)
         float2 ss = reinterpret_cast<const float2 *>(p)[r];
@@ -526,6 +500,23 @@ viterbi_k1024_kernel(const float *__restrict__ post, long ld_t, long ld_b, const
     }
 }
 
+// One float per softmax row from the GEMM's per-slice (max, sum exp) pairs: -(M log2 e + log2 S) with M the row maximum
+// and S = sum_j exp(logit_j - M), so that posterior_j = 2^(logit_j * log2 e + rowms).
+__global__ void softmax_rowms_kernel(const float2 *__restrict__ stats, int n_slices, long M, float *__restrict__ rowms)
+{
+    for (long m = blockIdx.x * (long)blockDim.x + threadIdx.x; m < M; m += (long)gridDim.x * blockDim.x) {
+        const float2 *st = stats + m * n_slices;
+        float mx = -INFINITY;
+        for (int s = 0; s < n_slices; s++) mx = fmaxf(mx, __ldg(&st[s]).x);
+        float tot = 0.0f;
+        for (int s = 0; s < n_slices; s++) {
+            const float2 v = __ldg(&st[s]);
+            tot += v.y * ex2_ftz((v.x - mx) * SLOIKA_LOG2E);
+        }
+        rowms[m] = -(mx * SLOIKA_LOG2E + lg2_ftz(tot));
+    }
+}
+
 static bool ipow_ok(int nbase, int klen, long *K)
 {
     long k = 1;
@@ -548,7 +539,8 @@ extern "C" size_t sloika_viterbi_workspace_bytes(int T, int B, int nbase, int kl
     long K;
     if (T < 0 || B < 0 || nbase < 2 || klen < 1 || !ipow_ok(nbase, klen, &K)) return 0;
     // K = 1024 kernel: one uint16 per quad of states; generic kernel: one byte per state
-    if (use_k1024(nbase, K)) return (size_t)T * (size_t)B * (size_t)(K / 2);
+    // (+ one float per event and read for the combined softmax row statistics of the fused-logits path)
+    if (use_k1024(nbase, K)) return (size_t)T * (size_t)B * (size_t)(K / 2) + (size_t)T * (size_t)B * sizeof(float);
     return (size_t)T * (size_t)B * (size_t)K;
 }
 
@@ -575,10 +567,10 @@ extern "C" int sloika_viterbi_fwd(const float *post, long ld_t, long ld_b, const
     cudaError_t err;
     if (use_k1024(nbase, K)) {
         if (mode == SLOIKA_VIT_POST)
-            viterbi_k1024_kernel<IN_POST><<<B, VIT_THREADS, 0, st>>>(post, ld_t, ld_b, nullptr, 0, lengths, T, B, sp, c0, c1,
+            viterbi_k1024_kernel<IN_POST><<<B, VIT_THREADS, 0, st>>>(post, ld_t, ld_b, nullptr, lengths, T, B, sp, c0, c1,
                                                               (uint8_t *)tb_ws, path_out, path_len, score_out);
         else
-            viterbi_k1024_kernel<IN_LOG><<<B, VIT_THREADS, 0, st>>>(post, ld_t, ld_b, nullptr, 0, lengths, T, B, sp, c0, c1,
+            viterbi_k1024_kernel<IN_LOG><<<B, VIT_THREADS, 0, st>>>(post, ld_t, ld_b, nullptr, lengths, T, B, sp, c0, c1,
                                                              (uint8_t *)tb_ws, path_out, path_len, score_out);
         SLOIKA_RETURN_LAUNCH_STATUS();
     }
@@ -611,8 +603,15 @@ extern "C" int sloika_viterbi_logits_fwd(const float *logits, long ld_t, long ld
     // on this path the kernel evaluates log(c0 + c1 * p) with one fused multiply-add: c0 carries the + 1e-10 of
     // decode.prepare_post (decode.py:36) as well
     const float c0 = (float)min_prob + 1e-10f, c1 = (float)(1.0 - min_prob), sp = (float)skip_pen;
+    // the logits rows are (t, b) ordered: ld_t == B * ld_b is what the engine produces and what the statistics index
+    if (ld_t != (long)B * ld_b && B > 1) return SLOIKA_ERR_UNSUPPORTED;
+    float *rowms = reinterpret_cast<float *>(static_cast<uint8_t *>(tb_ws) + (size_t)T * (size_t)B * 512);
+    const long M = (long)T * B;
+    long blocks = ceil_div(M, 256);
+    if (blocks > 148L * 16) blocks = 148L * 16;
+    softmax_rowms_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2 *>(stats), n_slices, M,
+                                                                             rowms);
     viterbi_k1024_kernel<IN_LOGITS><<<B, VIT_THREADS, 0, (cudaStream_t)stream>>>(
-        logits, ld_t, ld_b, reinterpret_cast<const float2 *>(stats), n_slices, lengths, T, B, sp, c0, c1,
-        (uint8_t *)tb_ws, path_out, path_len, score_out);
+        logits, ld_t, ld_b, rowms, lengths, T, B, sp, c0, c1, (uint8_t *)tb_ws, path_out, path_len, score_out);
     SLOIKA_RETURN_LAUNCH_STATUS();
 }

@@ -117,7 +117,7 @@ def _viterbi_logits(la, klen, skip_pen, min_prob, nbase, return_device):
         paths = torch.empty((B, max(T, 1)), dtype=torch.int32, device=dev)
         plen = torch.empty(B, dtype=torch.int32, device=dev)
         score = torch.empty(B, dtype=torch.float32, device=dev)
-        launch('viterbi', 1, lib.sloika_viterbi_logits_fwd,
+        launch('viterbi', 2, lib.sloika_viterbi_logits_fwd,          # row statistics + decode
                cabi.ptr(data), ld_t, ld_b, cabi.ptr(la.stats), la.n_slices, cabi.ptr(la.lengths), T, B, nbase, klen,
                float(skip_pen), float(min_prob), cabi.ptr(tb), nbytes, cabi.ptr(paths), cabi.ptr(plen),
                cabi.ptr(score), cabi.stream_ptr(dev))

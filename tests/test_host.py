@@ -28,7 +28,7 @@ def test_cabi_exports_every_declared_symbol():
     assert lib.sloika_b200_abi_version() == cabi.ABI_VERSION
     assert b'argument' in lib.sloika_b200_strerror(-1)
     assert lib.sloika_gru_workspace_bytes(800, 1024, 96) == 800 * 1024 * 288 * 4
-    assert lib.sloika_viterbi_workspace_bytes(800, 1024, 4, 5) == 800 * 1024 * 512      # uint16 per quad of states
+    assert lib.sloika_viterbi_workspace_bytes(800, 1024, 4, 5) == 800 * 1024 * (512 + 4)   # uint16 per quad of states + a float per event
     assert lib.sloika_viterbi_workspace_bytes(10, 2, 4, 3) == 10 * 2 * 64               # generic kernel: a byte per state
 
 
