@@ -33,9 +33,13 @@ namespace gru5 {
 
 using namespace tc;
 
-// mbarrier wait that turns a protocol bug into a trap after ~2 s instead of a hung device
+// mbarrier wait: try_wait suspends the thread in hardware until the phase completes or the time hint runs out; the retry
+// branch lives inside the asm block (3 instructions per retry; with the loop in C++ the compiler added a spin counter,
+// a compare and a second branch, ~4 % of all instructions issued by a kernel that is issue-bound with several groups per
+// SM).  GRU_TC_TRACE builds keep the bounded loop that traps on a protocol bug.
 __device__ __forceinline__ void wait_bar(uint64_t *bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
+#ifdef GRU_TC_TRACE
     uint32_t done = 0;
     for (uint32_t spins = 0; !done; ++spins) {
         asm volatile(
@@ -47,6 +51,17 @@ __device__ __forceinline__ void wait_bar(uint64_t *bar, uint32_t parity) {
             : "memory");
         if (!done && spins > 100000u) __trap();
     }
+#else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 200000;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}"
+        ::"r"(addr), "r"(parity)
+        : "memory");
+#endif
 }
 
 // Named-barrier hand-off from the compute warps to the issuing warp of a group: the producers `bar.arrive` (they do
@@ -70,8 +85,9 @@ __device__ __forceinline__ float rcp_ftz(float x) {
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-__device__ __forceinline__ float sigmoid_lean(float x) { return rcp_ftz(1.0f + ex2_ftz(x * -SLOIKA_LOG2E)); }
-__device__ __forceinline__ float tanh_lean(float x) { return fmaf(-2.0f, rcp_ftz(1.0f + ex2_ftz(x * (2.0f * SLOIKA_LOG2E))), 1.0f); }
+// arguments already scaled: sigmoid_pre(-x log2 e) = sigmoid(x), tanh_pre(2 x log2 e) = tanh(x)
+__device__ __forceinline__ float sigmoid_pre(float xs) { return rcp_ftz(1.0f + ex2_ftz(xs)); }
+__device__ __forceinline__ float tanh_pre(float xs) { return fmaf(-2.0f, rcp_ftz(1.0f + ex2_ftz(xs)), 1.0f); }
 
 // (x0, x1) -> packed fp16 pairs hi = (hi0, hi1), lo = (lo0, lo1): hi_i = fp16(x_i) ROUNDED TO NEAREST, lo_i =
 // fp16(x_i - hi_i).  (Truncating hi instead would save two conversions, but its error is one-sided: the dropped
@@ -169,8 +185,12 @@ gru_tc_kernel(const float *__restrict__ vI, long ldv, const float *__restrict__ 
 #pragma unroll
             for (int i = 0; i < 8; i++) {
                 const int k = 16 * kc + 2 * i;
-                const float w0 = (j < H && k < H) ? __ldg(row + k) : 0.0f;
-                const float w1 = (j < H && k + 1 < H) ? __ldg(row + k + 1) : 0.0f;
+                // the gate pre-activations feed ex2 directly: z, r rows carry -log2 e, candidate rows 2 log2 e
+                // (sigmoid(x) = 1 / (1 + 2^(-x log2 e)), tanh(x) = 1 - 2 / (1 + 2^(2 x log2 e))); the projection term
+                // is scaled by the same constant when it is added (one FFMA instead of FADD + FMUL per value)
+                const float gs = m < 2 ? -SLOIKA_LOG2E : 2.0f * SLOIKA_LOG2E;
+                const float w0 = (j < H && k < H) ? gs * __ldg(row + k) : 0.0f;
+                const float w1 = (j < H && k + 1 < H) ? gs * __ldg(row + k + 1) : 0.0f;
                 const __half2 h2 = __floats2half2_rn(w0, w1);
                 const float2 hb = __half22float2(h2);
                 const __half2 l2 = __floats2half2_rn(w0 - hb.x, w1 - hb.y);
@@ -237,7 +257,7 @@ gru_tc_kernel(const float *__restrict__ vI, long ldv, const float *__restrict__ 
             if (jop) {
                 float rh[NS];
 #pragma unroll
-                for (int n = 0; n < NS; n++) rh[n] = sigmoid_lean(__uint_as_float(dr[n]) + vr[n]) * h[n];
+                for (int n = 0; n < NS; n++) rh[n] = sigmoid_pre(fmaf(vr[n], -SLOIKA_LOG2E, __uint_as_float(dr[n]))) * h[n];
                 uint32_t whi[NS / 2], wlo[NS / 2];
 #pragma unroll
                 for (int n = 0; n < NS; n += 2) split_pair(rh[n], rh[n + 1], whi[n / 2], wlo[n / 2]);
@@ -255,7 +275,7 @@ gru_tc_kernel(const float *__restrict__ vI, long ldv, const float *__restrict__ 
             float z[NS], vc[NS];
 #pragma unroll
             for (int n = 0; n < NS; n++) {
-                z[n] = sigmoid_lean(__uint_as_float(dz[n]) + vrow[n * VLD]);
+                z[n] = sigmoid_pre(fmaf(vrow[n * VLD], -SLOIKA_LOG2E, __uint_as_float(dz[n])));
                 vc[n] = vrow[n * VLD + 2 * H];
             }
             // ---- phase 2: candidate, blend, publish h_t ----
@@ -268,7 +288,7 @@ gru_tc_kernel(const float *__restrict__ vI, long ldv, const float *__restrict__ 
             if (warp == 0 && lane == 0) TRACE(8);
 #pragma unroll
             for (int n = 0; n < NS; n++) {
-                const float hbar = tanh_lean(__uint_as_float(dc[n]) + vc[n]);
+                const float hbar = tanh_pre(fmaf(vc[n], 2.0f * SLOIKA_LOG2E, __uint_as_float(dc[n])));
                 const float hn = z[n] * h[n] + (1.0f - z[n]) * hbar;
                 h[n] = t < len[n] ? hn : 0.0f;                   // ragged batch: state stays 0 outside the read
             }
