@@ -69,9 +69,10 @@ __host__ __device__ inline size_t smem_bytes(int BN, int nkb, int stages, bool f
 {
     size_t w = (size_t)2 * nkb * BN * (f16 ? 64 : 128);    // W_hi + W_lo
     size_t a = (size_t)stages * (f16 ? 1 : 2) * A_TILE_BYTES;   // tf32: (hi, lo) per stage; f16: hi16 | lo16 in place of the raw tile
-    // epilogue staging per epilogue warp: 32 x STG_LD floats (transposing fallback) or 32 x 32 swizzled boxes for the TMA
-    // stores -- two of them in the f16 form, whose weights leave the room (the tf32 form would lose slice width)
-    size_t stg = f16 ? (size_t)8 * 2 * 4096 : (size_t)8 * 32 * STG_LD * 4;
+    // epilogue staging per epilogue warp: 32 x STG_LD floats (transposing fallback) or one 32 x 32 swizzled box for the TMA
+    // stores.  (Tried: two boxes per warp so that a store drains while the next box is filled.  The plain 1025-column GEMM
+    // gained 7 %, the softmax form with its row statistics -- the one the path uses -- lost 12 %: one box.)
+    size_t stg = (size_t)8 * 32 * STG_LD * 4;
     size_t misc = (size_t)BN * 4 + 512;                    // bias slice + barriers
     return w + a + stg + misc + 1024;                      // + alignment slack
 }
@@ -98,7 +99,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
     uint8_t *Abase = Wlo + (size_t)nkb * BN * WROW;                       // stage s: raw tile, converted in place to hi; lo behind it
                                                                           // (F16: raw tile replaced by hi16 | lo16, 8 KB each)
     float *stg_all = reinterpret_cast<float *>(Abase + (size_t)STAGES * STAGE_BYTES);
-    float *bias_s = stg_all + (F16 ? 8 * 2 * 1024 : 8 * 32 * STG_LD);
+    float *bias_s = stg_all + 8 * 32 * STG_LD;
     uint64_t *bars = reinterpret_cast<uint64_t *>(bias_s + BN);
     uint64_t *full_raw = bars;                     // [STAGES] TMA -> transform
     uint64_t *full_split = bars + MAX_STAGES;      // [STAGES] transform -> MMA
@@ -295,9 +296,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
         const int lq = warp & 3;
         float *stg = stg_all + (eg * 4 + lq) * 32 * STG_LD;
         // TMA-store path: a dense 32 x 32 fp32 box per warp in the SWIZZLE_128B layout (1024-byte aligned)
-        // two staging boxes per warp: the TMA engine may still be reading one while the next is filled
-        uint8_t *stg_t2 = reinterpret_cast<uint8_t *>(stg_all) + (eg * 4 + lq) * (F16 ? 8192 : 4096);
-        uint32_t box = 0;
+        uint8_t *stg_t = reinterpret_cast<uint8_t *>(stg_all) + (eg * 4 + lq) * 4096;
         const int nchunks = (BN + 31) / 32;
         uint32_t tile = 0;
         for (long mt = cta_in_slice; mt < m_tiles; mt += mt_stride, tile++) {
@@ -321,10 +320,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
                     tc::mbar_arrive(&tmem_empty[a]);
                     released = true;
                 }
-                uint8_t *stg_t = stg_t2 + ((!F16 || (p.dbg & 8)) ? 0u : (box & 1u)) * 4096;
-                box++;
-                if (p.tma_out) {                                 // the store that last used THIS box has left shared memory
-                    if (lane == 0) { if (!F16 || (p.dbg & 8)) tc::bulk_wait_read(); else tc::bulk_wait_read1(); }   // (at most the other box's store is still in flight)
+                if (p.tma_out) {                                 // the previous box of this warp has left shared memory
+                    if (lane == 0) tc::bulk_wait_read();
                     __syncwarp();
                 }
                 // thread = row: bias + activation
