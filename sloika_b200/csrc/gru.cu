@@ -312,6 +312,8 @@ static int launch_gru(const float *vI, long ldv, const float *sW, const float *s
 namespace gru4 {
 int dispatch(const float *vI, long ldv, const float *sW, const float *sW2, float *y, long ldy, const int32_t *lengths, int T,
              int B, int H, int reverse, int act, int gate_act, cudaStream_t st);
+int dispatch_cluster(const float *vI, long ldv, const float *sW, const float *sW2, float *y, long ldy, const int32_t *lengths,
+                     int T, int B, int H, int reverse, int act, int gate_act, cudaStream_t st);
 }
 namespace gru5 {
 int dispatch(const float *vI, long ldv, const float *sW, const float *sW2, float *y, long ldy, const int32_t *lengths, int T,
@@ -424,8 +426,12 @@ extern "C" int sloika_gru_recurrence_fwd_ex(const float *vI, long ldv, const flo
             if (rc != SLOIKA_ERR_UNSUPPORTED) return rc;
         }
         if (cap >= 4) {
-            const int rc = gru4::dispatch(vI, ldv, sW, sW2, y, ldy, lengths, T, B, H, reverse, act, gate_act, st);
+            int rc = gru4::dispatch(vI, ldv, sW, sW2, y, ldy, lengths, T, B, H, reverse, act, gate_act, st);
             if (rc != SLOIKA_ERR_UNSUPPORTED) return rc;
+            if (!getenv("SLOIKA_B200_GRU_STEPWISE")) {          // 144 < H <= 256: weights spread over a 4-CTA cluster
+                rc = gru4::dispatch_cluster(vI, ldv, sW, sW2, y, ldy, lengths, T, B, H, reverse, act, gate_act, st);
+                if (rc != SLOIKA_ERR_UNSUPPORTED) return rc;
+            }
         }
         if (cap >= 3) {
             const int rc = gru3::dispatch(vI, ldv, sW, sW2, y, ldy, lengths, T, B, H, reverse, act, gate_act, st);

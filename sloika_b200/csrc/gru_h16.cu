@@ -421,5 +421,214 @@ int dispatch(const float *vI, long ldv, const float *sW, const float *sW2, float
     return SLOIKA_ERR_UNSUPPORTED;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// 144 < H <= 256: the recurrent weights (3 H^2 values as fp16 hi / lo pairs: 786 KB at H = 256) do not fit one SM.
+// A thread-block CLUSTER of 4 CTAs keeps them on chip: CTA `rank` owns the units [rank * UC, (rank + 1) * UC) of all
+// three gates (A fragments of its 3 * UC weight rows in shared memory, 196 KB at H = 256) and every CTA holds a full
+// copy of the state operands h_{t-1} and r * h_{t-1} of the cluster's 8 sequences (packed fp16 hi / lo).  Per time step:
+//   phase 1   z and r warps: one 16-row tile each over all of K (mma.sync m16n8k16, three products per term);
+//             the r warps write r * h of their units into the CTA's own slice of the r*h operand
+//   exchange  cluster barrier, every CTA PULLS the other three slices through distributed shared memory
+//             (ld.shared::cluster, 128-bit), CTA barrier
+//   phase 2   c warps: candidate tile, blend with z (handed over in shared memory), h_t of the CTA's units -> fp32
+//             state, own slice of the h operand
+//   exchange  cluster barrier, pull the other slices of h, CTA barrier; the z / r warps store h_t to HBM
+// Same arithmetic as gru_h16_kernel (Gru.step, sloika/layers.py:1010-1021).  Replaces the step-by-step scan of
+// gru.cu (`gru_stepwise`: four launches per time step) for these sizes.
+__device__ __forceinline__ uint32_t cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint4 ld_dsmem_v4(const void *local_ptr, uint32_t rank) {
+    const uint32_t laddr = (uint32_t)__cvta_generic_to_shared(local_ptr);
+    uint32_t raddr;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(laddr), "r"(rank));
+    uint4 v;
+    asm volatile("ld.shared::cluster.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(raddr) : "memory");
+    return v;
+}
+
+constexpr int CLUSTER = 4;
+
+template <int HP>
+__global__ void __launch_bounds__(3 * (HP / CLUSTER / 16) * 32, 1)
+gru_cluster_kernel(const float *__restrict__ vI, long ldv, const float *__restrict__ sW, const float *__restrict__ sW2,
+                   float *__restrict__ y, long ldy, const int32_t *__restrict__ lengths, int T, int B, int H, int reverse)
+{
+    constexpr int UC = HP / CLUSTER;             // units per CTA
+    constexpr int NTU = UC / 16;                 // 16-row tiles per gate and CTA
+    constexpr int NW = 3 * NTU;                  // warps: z tiles, r tiles, candidate tiles
+    constexpr int NKC = HP / 16;
+    constexpr int PW = HP / 2 + 4;               // pitch (words) of the packed half2 [8][PW] operand arrays
+    constexpr int NTHREADS = NW * 32;
+    constexpr int SLICE_V4 = UC / 8;             // uint4 per sequence and array in one CTA's operand slice
+    extern __shared__ __align__(16) float smem[];
+    uint4 *Ahi = reinterpret_cast<uint4 *>(smem);                    // [NW][NKC][32] A fragments, hi
+    uint4 *Alo = Ahi + NW * NKC * 32;                                //                             lo
+    uint32_t *Hh = reinterpret_cast<uint32_t *>(Alo + NW * NKC * 32);   // [8][PW] h_{t-1}, fp16 hi pairs (all units)
+    uint32_t *Hl = Hh + BT * PW;
+    uint32_t *RHh = Hl + BT * PW;                                    // [8][PW] r * h_{t-1}
+    uint32_t *RHl = RHh + BT * PW;
+    float *Hf = reinterpret_cast<float *>(RHl + BT * PW);            // [8][UC] fp32 state of this CTA's units
+    float *Zs = Hf + BT * UC;                                        // [8][UC] update gate of this step
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t4 = lane & 3;
+    const int gate = warp / NTU, jt = warp - gate * NTU;
+    const uint32_t rank = cluster_rank();
+    const int unit0 = (int)rank * UC;
+    const int b_base = (blockIdx.x / CLUSTER) * BT;
+
+    // ---- A fragments of this warp's tile (zero padded, split once) ----
+    for (int kc = 0; kc < NKC; kc++) {
+        uint32_t fh[4], fl[4];
+        const int r0 = unit0 + 16 * jt + g, r1 = r0 + 8, k0 = 16 * kc + 2 * t4, k1 = k0 + 8;
+        auto wl = [&](int row, int k) -> float {
+            if (row >= H || k >= H) return 0.0f;
+            return gate < 2 ? __ldg(sW + (long)(gate * H + row) * H + k) : __ldg(sW2 + (long)row * H + k);
+        };
+        split2_f16(wl(r0, k0), wl(r0, k0 + 1), fh[0], fl[0]);
+        split2_f16(wl(r1, k0), wl(r1, k0 + 1), fh[1], fl[1]);
+        split2_f16(wl(r0, k1), wl(r0, k1 + 1), fh[2], fl[2]);
+        split2_f16(wl(r1, k1), wl(r1, k1 + 1), fh[3], fl[3]);
+        Ahi[(warp * NKC + kc) * 32 + lane] = make_uint4(fh[0], fh[1], fh[2], fh[3]);
+        Alo[(warp * NKC + kc) * 32 + lane] = make_uint4(fl[0], fl[1], fl[2], fl[3]);
+    }
+    for (int e = tid; e < 4 * BT * PW + 2 * BT * UC; e += NTHREADS) reinterpret_cast<uint32_t *>(Hh)[e] = 0u;
+
+    // fragment element i of this lane: local unit ul = 16*jt + g + 8*(i >> 1), sequence b = 2*t4 + (i & 1)
+    int len[4], ul[4], sb[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        ul[i] = 16 * jt + g + 8 * (i >> 1);
+        sb[i] = 2 * t4 + (i & 1);
+        const int bg = b_base + sb[i];
+        len[i] = (bg < B && unit0 + ul[i] < H) ? (lengths ? min(lengths[bg], T) : T) : 0;
+    }
+    const int tstep = reverse ? -1 : 1;
+    int t = reverse ? T - 1 : 0;
+    // this lane's four projection values of a step (gate block `gate`), clamped to valid addresses
+    auto load_vi = [&](int tt, float (&v)[4]) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int bg = b_base + sb[i], u = unit0 + ul[i];
+            v[i] = (tt >= 0 && tt < T && bg < B && u < H) ? __ldg(vI + ((long)tt * B + bg) * ldv + (long)gate * H + u) : 0.0f;
+        }
+    };
+    __half *Hh_h = reinterpret_cast<__half *>(Hh), *Hl_h = reinterpret_cast<__half *>(Hl);
+    __half *RHh_h = reinterpret_cast<__half *>(RHh), *RHl_h = reinterpret_cast<__half *>(RHl);
+    // pull the other CTAs' slices of an operand pair (hi, lo) into this CTA's copies
+    auto pull = [&](uint32_t *hi, uint32_t *lo) {
+        for (int e = tid; e < (CLUSTER - 1) * BT * 2 * SLICE_V4; e += NTHREADS) {
+            const int v4 = e % SLICE_V4, rest = e / SLICE_V4;
+            const int arr = rest & 1, b = (rest >> 1) % BT, rr = (rest >> 1) / BT;
+            const uint32_t src_rank = (rank + 1 + rr) % CLUSTER;
+            uint32_t *base = (arr ? lo : hi) + b * PW + (int)src_rank * (UC / 2) + 4 * v4;
+            *reinterpret_cast<uint4 *>(base) = ld_dsmem_v4(base, src_rank);
+        }
+    };
+    float vcur[4], vnext[4];
+    load_vi(t, vcur);
+    __syncthreads();
+    cluster_sync_all();                              // every CTA's operands are zeroed before anyone pulls
+
+    for (int s = 0; s < T; s++, t += tstep) {
+        load_vi(t + tstep, vnext);                   // next step's projection values, in flight during this step
+        // ---- phase 1 ----
+        if (gate < 2) {
+            float pre[4];
+            matvec_smemA<0, NKC, PW>(Ahi + warp * NKC * 32, Alo + warp * NKC * 32, lane, Hh, Hl, g, t4, pre);
+            if (gate == 0) {
+#pragma unroll
+                for (int i = 0; i < 4; i++) Zs[sb[i] * UC + ul[i]] = sigmoid_fast(pre[i] + vcur[i]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const float rh = sigmoid_fast(pre[i] + vcur[i]) * Hf[sb[i] * UC + ul[i]];
+                    __half hh, hl;
+                    split1_f16(rh, hh, hl);
+                    const int o = sb[i] * (2 * PW) + unit0 + ul[i];
+                    RHh_h[o] = hh;
+                    RHl_h[o] = hl;
+                }
+            }
+        }
+        cluster_sync_all();                          // every CTA's slice of r*h is written
+        pull(RHh, RHl);
+        __syncthreads();
+        // ---- phase 2 ----
+        if (gate == 2) {
+            float cpre[4];
+            matvec_smemA<0, NKC, PW>(Ahi + warp * NKC * 32, Alo + warp * NKC * 32, lane, RHh, RHl, g, t4, cpre);
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const int o = sb[i] * UC + ul[i];
+                const float z = Zs[o], hp = Hf[o];
+                const float hbar = tanh_fast(cpre[i] + vcur[i]);
+                float hn = z * hp + (1.0f - z) * hbar;
+                hn = t < len[i] ? hn : 0.0f;         // ragged batch: state stays 0 outside the read
+                Hf[o] = hn;
+                __half hh, hl;
+                split1_f16(hn, hh, hl);
+                const int oh = sb[i] * (2 * PW) + unit0 + ul[i];
+                Hh_h[oh] = hh;
+                Hl_h[oh] = hl;
+            }
+        }
+        cluster_sync_all();                          // every CTA's slice of h_t is written
+        pull(Hh, Hl);
+        // h_t of this CTA's units -> HBM (coalesced rows; Hf is next written in phase 2 of the next step, behind a barrier)
+        for (int e = tid; e < BT * UC; e += NTHREADS) {
+            const int b = e / UC, u = e - b * UC;
+            if (b_base + b < B && unit0 + u < H) y[((long)t * B + b_base + b) * ldy + unit0 + u] = Hf[e];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 4; i++) vcur[i] = vnext[i];
+    }
+    cluster_sync_all();                              // nobody leaves while a neighbour may still pull from it
+}
+
+template <int HP>
+static int launch_cluster(const float *vI, long ldv, const float *sW, const float *sW2, float *y, long ldy,
+                          const int32_t *lengths, int T, int B, int H, int reverse, cudaStream_t st)
+{
+    constexpr int UC = HP / CLUSTER, NW = 3 * (UC / 16), NKC = HP / 16, PW = HP / 2 + 4;
+    const size_t smem = (size_t)2 * NW * NKC * 32 * 16 + sizeof(float) * ((size_t)4 * BT * PW + (size_t)2 * BT * UC);
+    auto kern = gru_cluster_kernel<HP>;
+    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return (int)err;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(CLUSTER * ceil_div(B, BT)));
+    cfg.blockDim = dim3(NW * 32);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CLUSTER;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    err = cudaLaunchKernelEx(&cfg, kern, vI, ldv, sW, sW2, y, ldy, lengths, T, B, H, reverse);
+    if (err != cudaSuccess) return (int)err;
+    SLOIKA_RETURN_LAUNCH_STATUS();
+}
+
+// tanh / sigmoid GRUs with 144 < H <= 256 on a 4-CTA cluster; SLOIKA_ERR_UNSUPPORTED otherwise.
+int dispatch_cluster(const float *vI, long ldv, const float *sW, const float *sW2, float *y, long ldy, const int32_t *lengths,
+                     int T, int B, int H, int reverse, int act, int gate_act, cudaStream_t st)
+{
+    if (act != SLOIKA_ACT_TANH || gate_act != SLOIKA_ACT_SIGMOID) return SLOIKA_ERR_UNSUPPORTED;
+    if (H <= 144 || H > 256) return SLOIKA_ERR_UNSUPPORTED;
+    if (H <= 192) return launch_cluster<192>(vI, ldv, sW, sW2, y, ldy, lengths, T, B, H, reverse, st);
+    return launch_cluster<256>(vI, ldv, sW, sW2, y, ldy, lengths, T, B, H, reverse, st);
+}
+
 }  // namespace gru4
 }  // namespace sloika

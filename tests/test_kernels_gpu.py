@@ -575,11 +575,16 @@ def test_gru_one_call_entry_point(I, H, T, B, reverse, ragged):
     assert lib.sloika_gru_fwd(*args) == -3
 
 
+@pytest.mark.parametrize('stepwise', [False, True])
 @pytest.mark.parametrize('I,H,T,B,reverse,ragged', [(24, 160, 40, 6, False, False), (32, 200, 30, 130, True, True),
-                                                    (16, 256, 25, 3, False, True)])
-def test_gru_wider_than_one_sm_runs_step_by_step(I, H, T, B, reverse, ragged):
-    """H > 144 does not fit the persistent kernels: the scan runs as per-step GEMMs + gate kernels (gru.cu,
-    `gru_stepwise`); same results as the oracle, ragged and reversed included (B = 130 takes the tensor-core GEMM)."""
+                                                    (16, 256, 25, 3, False, True), (40, 300, 12, 5, True, True)])
+def test_gru_wider_than_one_sm(I, H, T, B, reverse, ragged, stepwise, monkeypatch):
+    """H > 144 does not fit one SM.  144 < H <= 256 runs on a 4-CTA cluster that keeps the weights in the four CTAs'
+    shared memory and exchanges the state through distributed shared memory (gru_h16.cu, `gru_cluster_kernel`); wider
+    still (and with SLOIKA_B200_GRU_STEPWISE) the scan runs as per-step GEMMs + gate kernels (gru.cu, `gru_stepwise`).
+    Same results as the oracle, ragged and reversed included (B = 130 takes the tensor-core GEMM)."""
+    if stepwise:
+        monkeypatch.setenv('SLOIKA_B200_GRU_STEPWISE', '1')
     np.random.seed(H + T)
     g = layers.Gru(I, H, init=_init(), has_bias=True)
     g.sW.set_value(g.sW.get_value() * 3)

@@ -1,11 +1,11 @@
-"""Time the GRU recurrence kernel alone on the benchmark shape (T'=800, B=1024, H=96)."""
+"""Time the GRU recurrence kernel alone (default: the benchmark shape T'=800, B=1024, H=96; env T, B, H)."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from sloika_b200 import cabi
 lib = cabi.load()
 dev = torch.device('cuda:0')
-T, B, H = 800, 1024, int(os.environ.get('H', '96'))
+T, B, H = int(os.environ.get('T', '800')), int(os.environ.get('B', '1024')), int(os.environ.get('H', '96'))
 vI = torch.randn(T, B, 3 * H, device=dev)
 sW = torch.randn(2 * H, H, device=dev) * 0.1
 sW2 = torch.randn(H, H, device=dev) * 0.1
