@@ -2,7 +2,7 @@
 //
 // Used for the GRU input projection over all time steps (sloika/layers.py:1011: vI = x iW' + b),
 // FeedForward.run (layers.py:157-158) and the logits of Softmax.run (layers.py:310).
-// M = T*B rows is huge (819 200), K <= 256 and N <= ~1100 are small: the weights are tiny and stay
+// M = T*B rows is huge (819 200), K <= 512 and N <= ~1100 are small: the weights are tiny and stay
 // resident on chip, x is streamed once per N slice (re-reads hit L2), y is written once.  HBM-bound by design.
 //
 // Accuracy: the reference multiplies in float32.  Plain TF32 (10-bit mantissa) would put ~1e-3 of error into the gate
@@ -483,7 +483,7 @@ static EncodeTiledFn encode_fn()
 // Column slices the kernel would use for (K, N) (0 = shape not supported): lets callers size `stats`.
 int plan_slices(int K, int N, int *bn_out, bool f16)
 {
-    if (K <= 0 || K > 256 || N <= 0) return 0;
+    if (K <= 0 || K > 512 || N <= 0) return 0;
     const int nkb = (K + KB - 1) / KB;
     // slice widths are multiples of 32 columns: the epilogue works in 32-column boxes (TMA stores clip at N)
     int bn_max = 256;
@@ -500,7 +500,7 @@ int launch(const float *x, long ldx, const float *W, const float *bias, float *y
            int act, float2 *stats, int rot, bool f16, cudaStream_t st, const unsigned *gate = nullptr,
            unsigned gate_limit = 0, int gate_mode = 0)
 {
-    if ((ldx & 3) != 0 || ((uintptr_t)x & 15) != 0 || K > 256 || M < BM || M > 0x7fffffffL) return SLOIKA_ERR_UNSUPPORTED;
+    if ((ldx & 3) != 0 || ((uintptr_t)x & 15) != 0 || K > 512 || M < BM || M > 0x7fffffffL) return SLOIKA_ERR_UNSUPPORTED;
     EncodeTiledFn enc = encode_fn();
     if (!enc) return SLOIKA_ERR_UNSUPPORTED;
     int dev = 0, sms = 0;

@@ -176,7 +176,7 @@ def _gemm_algo(act, *params):
 def _linear(name, lib, act, W, b, y, ldy, N, fun_code, dev):
     """y = fun(x W' + b) through sloika_linear_fwd_ex; the fp16-split request degrades to AUTO when the
     tensor-core kernel cannot take the shape."""
-    tc_ok = act.ld % 4 == 0 and act.data.data_ptr() % 16 == 0 and act.T * act.B >= 128 and act.F <= 256
+    tc_ok = act.ld % 4 == 0 and act.data.data_ptr() % 16 == 0 and act.T * act.B >= 128 and act.F <= 512
     if not act.bounded and act.absmax is not None and tc_ok and W.absmax() < _F16_WEIGHT_LIMIT \
             and not os.environ.get('SLOIKA_B200_NO_F16'):
         # range known only on the device: enqueue both tensor-core forms, the kernel-side gate runs exactly one

@@ -687,3 +687,15 @@ def test_window_and_events_model():
     post = net.compile()(x)
     ref = _oracle(net, x)
     assert post.shape == ref.shape and np.abs(post - ref).max() < 1e-4
+
+
+def test_feedforward_wide_input_on_tensor_cores():
+    """K up to 512 (the widened bigger_raw_gru joins two 256-unit GRUs into a FeedForward) runs on the tcgen05 GEMM."""
+    np.random.seed(31)
+    for K, N in ((512, 256), (384, 96), (300, 40)):
+        layer = layers.FeedForward(K, N, init=_init(), has_bias=True, fun=act.tanh)
+        x = np.tanh(np.random.standard_normal((40, 16, K))).astype(np.float32)
+        a = engine.Act(torch.from_numpy(x).to(DEV), bounded=True)
+        got = layer.run(a).data.cpu().numpy()
+        ref = _oracle(layer, x)
+        assert np.abs(got - ref).max() < 2e-5, (K, N)

@@ -42,6 +42,11 @@ def main():
         engine.run_gru(g, engine.Act(xg, None))
         engine.run_gru(g, engine.Act(xg, torch.randint(1, 51, (37,), dtype=torch.int32, device=DEV), reverse=True))
     os.environ.pop('SLOIKA_B200_GRU_TC')
+    # 144 < H <= 256: the 4-CTA cluster kernel (distributed shared memory), ragged and reversed
+    for H in (160, 256):
+        gw = layers.Gru(24, H, init=smt.partial(smt.truncated_normal, sd=0.5), has_bias=True)
+        xw = torch.tanh(torch.randn((20, 11, 24), device=DEV))
+        engine.run_gru(gw, engine.Act(xw, torch.randint(1, 21, (11,), dtype=torch.int32, device=DEV), reverse=(H == 256)))
     # events route: Window + birnn(Lstm), old decoder, transition estimates, scoring
     init = smt.partial(smt.truncated_normal, sd=0.5)
     lstm = lambda i, o: layers.Lstm(i, o, init=init, has_bias=True, has_peep=True)
