@@ -471,7 +471,14 @@ def run_b200_arm(args):
     alg = algorithmic_bytes_per_sample(net)
     # a GRU layer's algorithmic bytes (x read once, h written once) are charged to its recurrence kernel;
     # the projection kernel's vI round trip is extra (non-algorithmic) traffic by SURVEY section 8d
-    alg_by_kernel = {'conv1d': alg.get('conv1d', 0.0), 'gru_recurrence': alg.get('gru_layer', 0.0),
+    # GRU layers run either as projection GEMM + recurrence kernel or as one fused launch (csrc/gru_fused.cu); the
+    # layer's algorithmic bytes go to whichever kernel ran it, in proportion to the launches
+    def gru_share(kms, name):
+        calls = {k: kms.get(k, (0.0, 0))[1] for k in ('gru_recurrence', 'gru_fused')}
+        total = sum(calls.values())
+        return alg.get('gru_layer', 0.0) * calls[name] / total if total else 0.0
+    alg_by_kernel = {'conv1d': alg.get('conv1d', 0.0), 'gru_recurrence': gru_share(kernel_ms_single, 'gru_recurrence'),
+                     'gru_fused': gru_share(kernel_ms_single, 'gru_fused'),
                      'gru_projection': 0.0, 'feedforward': alg.get('feedforward', 0.0),
                      'softmax': alg.get('softmax', 0.0), 'viterbi': alg.get('viterbi', 0.0)}
     def table(kms, steps):
@@ -481,8 +488,12 @@ def run_b200_arm(args):
             out[name] = {"ms_per_step": ms / steps, "calls_per_step": calls / steps,
                          "algorithmic_GBps": (nbytes / (ms * 1e-3) / 1e9) if ms > 0 else None}
         return out
-    breakdown = table(kernel_ms, args.steps)               # spans inside the pipelined region: they overlap each other
     breakdown_single = table(kernel_ms_single, iso_steps)  # one batch in flight: undisturbed durations
+    alg_by_kernel['gru_recurrence'] = gru_share(kernel_ms, 'gru_recurrence')
+    alg_by_kernel['gru_fused'] = gru_share(kernel_ms, 'gru_fused')
+    breakdown = table(kernel_ms, args.steps)               # spans inside the pipelined region: they overlap each other
+    alg_by_kernel['gru_recurrence'] = gru_share(kernel_ms_single, 'gru_recurrence')
+    alg_by_kernel['gru_fused'] = gru_share(kernel_ms_single, 'gru_fused')
     # dominant kernel = largest share of the step when a batch has the GPU to itself; its roofline numbers come from
     # that pass (in the pipelined region several launches of the same kernel share the SMs, which stretches every
     # launch without saying anything about the kernel); the pipelined spans are reported beside them
@@ -509,8 +520,10 @@ def run_b200_arm(args):
         # the recurrence is bound by the latency of its dependent steps, not by HBM: say so on the line
         rec_ms, rec_calls = kernel_ms_single['gru_recurrence']
         steps_per_launch = T // stride_of(net)
+        pipe_name = 'gru_fused' if 'gru_fused' in kernel_ms else 'gru_recurrence'
         roofline["latency"] = {"kernel": "gru_recurrence", "us_per_time_step_one_batch": 1e3 * rec_ms / rec_calls / steps_per_launch,
-                               "us_per_time_step_pipelined": 1e3 * kernel_ms['gru_recurrence'][0] / kernel_ms['gru_recurrence'][1] / steps_per_launch,
+                               "pipelined_kernel": pipe_name,
+                               "us_per_time_step_pipelined": 1e3 * kernel_ms[pipe_name][0] / kernel_ms[pipe_name][1] / steps_per_launch,
                                "time_steps_per_launch": steps_per_launch,
                                "ncu": "profiles/r2_step_kernels_ncu.txt (warps active, issue active, tensor pipe)"}
     total_alg = sum(alg.values())

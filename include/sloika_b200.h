@@ -140,6 +140,19 @@ int sloika_gru_fwd(const float *x, long ldx, const float *iW, const float *sW, c
                    const float *b, float *y, long ldy, void *ws, size_t ws_bytes, const int32_t *lengths,
                    int T, int B, int I, int H, int reverse, int act, int gate_act, void *stream);
 
+/*
+ * The same layer with the projection computed INSIDE the recurrence launch (csrc/gru_fused.cu): clusters of three CTAs,
+ * two running the recurrence and one the projection, hand vI over through a ring of a few time steps that stays in L2,
+ * so the T*B*3H projection never reaches HBM.  tanh / sigmoid, H <= 96, I <= 96, x rows 16-byte aligned (ldx % 4 == 0),
+ * |x| far inside the fp16 range (outputs of tanh / sigmoid / GRU layers); SLOIKA_ERR_UNSUPPORTED otherwise (callers fall
+ * back to sloika_gru_fwd).  ws: sloika_gru_fused_workspace_bytes(B, H) bytes (the rings).  It packs 32 sequences per
+ * recurrence CTA: the throughput form, meant for callers that keep several batches in flight.
+ */
+size_t sloika_gru_fused_workspace_bytes(int B, int H);
+int sloika_gru_fused_fwd(const float *x, long ldx, const float *iW, const float *sW, const float *sW2,
+                         const float *b, float *y, long ldy, void *ws, size_t ws_bytes, const int32_t *lengths,
+                         int T, int B, int I, int H, int reverse, int act, int gate_act, void *stream);
+
 /* The recurrence alone, given vI: T*B rows of 3H floats with row pitch ld_vi >= 3H (what sloika_gru_fwd runs
  * after the projection; a pitch that is a multiple of 4 floats keeps every row 16-byte aligned for odd H). */
 int sloika_gru_recurrence_fwd(const float *vI, long ld_vi, const float *sW, const float *sW2, float *y, long ldy,

@@ -69,6 +69,13 @@ __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.w
 // all but the most recent bulk group of this thread have finished reading their shared-memory source
 __device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// all but the most recent bulk group of this thread are complete (their global writes performed)
+__device__ __forceinline__ void bulk_wait_all1() { asm volatile("cp.async.bulk.wait_group 1;" ::: "memory"); }
+// 1-D bulk copy shared -> global (bulk async-group completion): 16-byte aligned addresses, size a multiple of 16
+__device__ __forceinline__ void bulk_store_1d(void *gdst, const void *smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
 
 // ---------------------------------------------------------------- TMEM
 __device__ __forceinline__ void tmem_alloc(uint32_t *smem_dst, uint32_t ncols) {   // whole warp

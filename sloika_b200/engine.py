@@ -298,11 +298,36 @@ def run_softmax(layer, act, out=None):
     return act.like(y, bounded=True)
 
 
+def _fused_gru_ok(layer, act):
+    """The projection-in-the-recurrence launch (csrc/gru_fused.cu) applies: throughput mode (enough sequences in
+    flight on the device that 32 per recurrence CTA is the right packing, as in `sloika_gru_recurrence_fwd_ex`),
+    bounded input, sizes that fit the tensor memory / shared memory of its projection CTA.
+    SLOIKA_B200_FUSED_GRU=1 forces it for any batch, =0 turns it off."""
+    env = os.environ.get('SLOIKA_B200_FUSED_GRU', '')
+    if env == '0':
+        return False
+    busy = act.B * max(1, BATCHES_IN_FLIGHT) * _CONCURRENT_BRANCHES > 16 * 148
+    return (busy or env not in ('', '0')) and act.bounded and layer.size <= 96 and layer.insize <= 96 and act.ld % 4 == 0 \
+        and act.data.data_ptr() % 16 == 0 and code_of(layer.fun) == 1 and code_of(layer.gatefun) == 2 \
+        and layer.iW.absmax() < _F16_WEIGHT_LIMIT
+
+
 def run_gru(layer, act, out=None):
     lib = cabi.load()
     assert act.F == layer.insize
     y = _out_buffer(act, act.T, layer.size, out)
     dev = act.device
+    if _fused_gru_ok(layer, act):
+        import torch
+        nbytes = lib.sloika_gru_fused_workspace_bytes(act.B, layer.size)
+        ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=dev)
+        launch('gru_fused', 1, lib.sloika_gru_fused_fwd,
+               cabi.ptr(act.data), act.ld, cabi.ptr(layer.iW.device(dev)), cabi.ptr(layer.sW.device(dev)),
+               cabi.ptr(layer.sW2.device(dev)), cabi.ptr(layer.b.device(dev)), cabi.ptr(y), _row_stride(y), cabi.ptr(ws),
+               nbytes, cabi.ptr(act.lengths), act.T, act.B, layer.insize, layer.size, 1 if act.reverse else 0,
+               code_of(layer.fun), code_of(layer.gatefun), cabi.stream_ptr(dev))
+        ws.record_stream(torch.cuda.current_stream(dev))
+        return act.like(y, bounded=True)
     # sloika_gru_fwd == input projection for all steps + recurrence; issued as its two halves so
     # that each kernel can be timed on its own
     H = layer.size

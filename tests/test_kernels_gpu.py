@@ -699,3 +699,35 @@ def test_feedforward_wide_input_on_tensor_cores():
         got = layer.run(a).data.cpu().numpy()
         ref = _oracle(layer, x)
         assert np.abs(got - ref).max() < 2e-5, (K, N)
+
+
+@pytest.mark.parametrize('I,H,T,B,reverse,ragged', [(96, 96, 60, 70, False, False), (96, 96, 45, 64, True, True),
+                                                    (32, 96, 30, 5, False, True), (64, 64, 25, 130, True, False),
+                                                    (96, 80, 20, 33, False, True), (40, 50, 20, 17, True, True),
+                                                    (20, 32, 15, 200, False, False)])
+def test_gru_fused_projection(I, H, T, B, reverse, ragged, monkeypatch):
+    """The GRU layer with the projection inside the recurrence launch (csrc/gru_fused.cu: clusters of two recurrence
+    CTAs and one projection CTA, vI handed over through an L2-resident ring) against the oracle; batches that do not
+    fill a cluster, ragged and reversed included."""
+    monkeypatch.setenv('SLOIKA_B200_FUSED_GRU', '1')
+    np.random.seed(I + H + B)
+    g = layers.Gru(I, H, init=_init(), has_bias=True)
+    g.sW.set_value(g.sW.get_value() * 5)
+    g.sW2.set_value(g.sW2.get_value() * 5)
+    layer = layers.Reverse(g) if reverse else g
+    lengths = [int(v) for v in np.random.randint(1, T + 1, size=B)] if ragged else None
+    if lengths:
+        lengths[0] = T
+    x = np.tanh(np.random.standard_normal((T, B, I))).astype(np.float32)
+    a = engine.Act(torch.from_numpy(x).to(DEV), None if lengths is None else torch.as_tensor(lengths, dtype=torch.int32, device=DEV),
+                   bounded=True)
+    assert engine._fused_gru_ok(g, a)
+    engine.TIMER.reset()
+    out = layer.run(a)
+    torch.cuda.synchronize()
+    got = out.data.cpu().numpy()
+    for b in list(range(0, B, 7)) + [B - 1]:
+        n = T if lengths is None else lengths[b]
+        ref = _oracle(layer, x[:n, b:b + 1])
+        assert np.abs(got[:n, b] - ref[:, 0]).max() < 5e-5, b
+        assert np.all(got[n:, b] == 0)

@@ -42,6 +42,14 @@ def main():
         engine.run_gru(g, engine.Act(xg, None))
         engine.run_gru(g, engine.Act(xg, torch.randint(1, 51, (37,), dtype=torch.int32, device=DEV), reverse=True))
     os.environ.pop('SLOIKA_B200_GRU_TC')
+    # the 3-CTA cluster launch with the projection inside (csrc/gru_fused.cu): partial last cluster, ragged, reversed
+    os.environ['SLOIKA_B200_FUSED_GRU'] = '1'
+    for I, H, B in ((40, 96, 37), (96, 96, 70), (32, 50, 5)):
+        gf = layers.Gru(I, H, init=smt.partial(smt.truncated_normal, sd=0.5), has_bias=True)
+        xf = torch.tanh(torch.randn((50, B, I), device=DEV))
+        engine.run_gru(gf, engine.Act(xf, None, bounded=True))
+        engine.run_gru(gf, engine.Act(xf, torch.randint(1, 51, (B,), dtype=torch.int32, device=DEV), reverse=True, bounded=True))
+    os.environ.pop('SLOIKA_B200_FUSED_GRU')
     # 144 < H <= 256: the 4-CTA cluster kernel (distributed shared memory), ragged and reversed
     for H in (160, 256):
         gw = layers.Gru(24, H, init=smt.partial(smt.truncated_normal, sd=0.5), has_bias=True)
