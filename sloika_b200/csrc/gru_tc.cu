@@ -200,7 +200,7 @@ gru_tc_kernel(const float *__restrict__ vI, long ldv, const float *__restrict__ 
             float z[NS], vc[NS];
 #pragma unroll
             for (int n = 0; n < NS; n++) {
-                z[n] = sigmoid_pre(fmaf(vrow[n * VLD], -SLOIKA_LOG2E, __uint_as_float(dz[n])));
+                z[n] = gate_denominator(fmaf(vrow[n * VLD], -SLOIKA_LOG2E, __uint_as_float(dz[n])));   // 1 + 2^(-z log2 e)
                 vc[n] = vrow[n * VLD + 2 * H];
             }
             // ---- phase 2: candidate, blend, publish h_t ----
@@ -213,8 +213,7 @@ gru_tc_kernel(const float *__restrict__ vI, long ldv, const float *__restrict__ 
             if (warp == 0 && lane == 0) TRACE(8);
 #pragma unroll
             for (int n = 0; n < NS; n++) {
-                const float hbar = tanh_pre(fmaf(vc[n], 2.0f * SLOIKA_LOG2E, __uint_as_float(dc[n])));
-                const float hn = z[n] * h[n] + (1.0f - z[n]) * hbar;
+                const float hn = gru_blend(z[n], fmaf(vc[n], 2.0f * SLOIKA_LOG2E, __uint_as_float(dc[n])), h[n]);
                 h[n] = t < len[n] ? hn : 0.0f;                   // ragged batch: state stays 0 outside the read
             }
             if (jop) {

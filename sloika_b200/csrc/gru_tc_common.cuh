@@ -66,6 +66,21 @@ __device__ __forceinline__ float rcp_ftz(float x) {
 __device__ __forceinline__ float sigmoid_pre(float xs) { return rcp_ftz(1.0f + ex2_ftz(xs)); }
 __device__ __forceinline__ float tanh_pre(float xs) { return fmaf(-2.0f, rcp_ftz(1.0f + ex2_ftz(xs)), 1.0f); }
 
+// The update gate and the candidate share ONE reciprocal: z = 1 / (1 + a), tanh = 1 - 2 / (1 + c) with a = ex2(za),
+// c = ex2(zc) gives, from inv = 1 / ((1 + a)(1 + c)):  z = (1 + c) inv,  tanh = 1 - 2 (1 + a) inv.  Five MUFU operations
+// per hidden value and step instead of six -- with 16 sequences per group the kernel is bound by exactly that unit
+// (16 lanes per clock and SM).  The exponents are capped at 63 so that the product stays finite (a gate of 1e-19 is 0
+// to every digit that matters; the candidate is 1 - 2e-19 = 1).
+__device__ __forceinline__ float gate_denominator(float xs) { return 1.0f + ex2_ftz(fminf(xs, 63.0f)); }
+// h_new = z h + (1 - z) tanh, from the two denominators
+__device__ __forceinline__ float gru_blend(float za, float cs, float h) {
+    const float cc = gate_denominator(cs);
+    const float inv = rcp_ftz(za * cc);
+    const float z = cc * inv;
+    const float hbar = fmaf(-2.0f * za, inv, 1.0f);
+    return fmaf(z, h - hbar, hbar);
+}
+
 // (x0, x1) -> packed fp16 pairs hi = (hi0, hi1), lo = (lo0, lo1): hi_i = fp16(x_i) ROUNDED TO NEAREST, lo_i =
 // fp16(x_i - hi_i).  (Truncating hi instead would save two conversions, but its error is one-sided: the dropped
 // lo.lo products then all have the sign of w.h and the bias adds up over the K terms and the time steps -- measured as

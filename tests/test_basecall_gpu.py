@@ -70,9 +70,11 @@ def test_posteriors_of_real_read_within_bound(calls, golden_dir, pretrained):
     """Whole reads (2 898 .. 22 838 recurrent steps): float32 round-off is amplified by the recurrence, and two float32
     implementations drift apart by as much as either drifts from exact arithmetic -- the reference arithmetic (NumPy
     float32 oracle == the reference's own layers.py to 7e-6) is 4.6e-4 (read7) and 1.4e-4 (read5) max-abs away from
-    its float64 twin, the device path 1.3e-4 and 4.5e-5 (profiles/r2_accuracy_probe.txt).  Stated bounds for whole
-    reads: (a) no further from float64 than the float32 reference is itself (+2e-5), (b) within 5e-4 of the float32
-    reference, (c) identical called sequences (test_ragged_batch_basecalls_match_golden).  Chunk-sized inputs (the
+    its float64 twin, the device path 3.8e-5 and 3.7e-5 (profiles/r2_accuracy_probe.txt).  Stated bounds for whole
+    reads: (a) no further from float64 than the float32 reference is itself (+2e-5), (b) from the float32 reference no
+    further than that reference's own distance from float64 plus the north-star 1e-4 (and never more than 5e-4 from the
+    outputs the reference's layers.py produced, on the sampled rows), (c) identical called sequences
+    (test_ragged_batch_basecalls_match_golden).  Chunk-sized inputs (the
     benchmark's 800 steps) keep the north-star 1e-4 against the float32 reference (test_full_size_batch_properties,
     test_kernels_gpu.py)."""
     net, signals, _ = calls
@@ -88,8 +90,11 @@ def test_posteriors_of_real_read_within_bound(calls, golden_dir, pretrained):
         post = net(sig[:, None, None])
         ref = forward_ref.run(pretrained.json(params=True), sig[:, None, None])
         ref64 = forward_ref.run(pretrained.json(params=True), sig[:, None, None], np.float64)
-        assert np.abs(post - ref).max() < 5e-4, name
-        assert np.abs(post - ref64).max() < np.abs(ref - ref64).max() + 2e-5, name
+        err_ref, err_dev = np.abs(ref - ref64).max(), np.abs(post - ref64).max()
+        print("{}: float32 reference {:.3g} from float64, device path {:.3g}, device to reference {:.3g}"
+              .format(name, err_ref, err_dev, np.abs(post - ref).max()))
+        assert err_dev < err_ref + 2e-5, name
+        assert np.abs(post - ref).max() < err_ref + 1e-4, name
 
 
 def test_decode_post_dropin(calls, read_basecalls, pretrained):
