@@ -237,9 +237,11 @@ int sloika_viterbi_fwd(const float *post, long ld_t, long ld_b, const int32_t *l
  * applied inside the kernel, so the posterior matrix never exists in HBM.  nbase = 4, klen = 5 only.
  *   logits: element (t, b, j) at logits[t*ld_t + b*ld_b + j], j < 1024 k-mer states, j = 1024 stay;
  *   stats: [T*B][n_slices] float pairs as written by sloika_softmax_logits_fwd (rows in (t, b) order: ld_t = B*ld_b);
- *   they are first combined into one float per row in the tail of the workspace (two launches).
+ *   they are first combined into one float per row, which is WRITTEN INTO THE ROW'S FIRST PADDING COLUMN
+ *   (logits[t*ld_t + b*ld_b + 1025]; rows are 16-byte aligned, so ld_b >= 1028) -- the decoder then stages k-mer
+ *   logits, stay logit and statistic of an event with one contiguous bulk copy (two launches).
  */
-int sloika_viterbi_logits_fwd(const float *logits, long ld_t, long ld_b, const float *stats, int n_slices,
+int sloika_viterbi_logits_fwd(float *logits, long ld_t, long ld_b, const float *stats, int n_slices,
                               const int32_t *lengths, int T, int B, int nbase, int klen, double skip_pen,
                               double min_prob, void *tb_ws, size_t ws_bytes, int32_t *path_out, int32_t *path_len,
                               float *score_out, void *stream);

@@ -22,6 +22,7 @@
 // HBM-bound: 4*(K+1) bytes of posterior read + K/2 (K = 1024 kernel; K otherwise) bytes of traceback written per event.
 #include <cmath>
 #include <cstdlib>
+#include <type_traits>
 #include "common.cuh"
 
 namespace sloika {
@@ -197,6 +198,43 @@ __device__ __forceinline__ void cp_async4_v(void *smem_dst, const void *gsrc) {
     const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
 }
+// the same with the destination given as a 32-bit shared-memory address (computed once outside the event loop)
+__device__ __forceinline__ void cp_async16_sa(uint32_t d, const void *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async16_zfill_sa(uint32_t d, const void *gsrc, int nbytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(nbytes) : "memory");
+}
+__device__ __forceinline__ void cp_async4_sa(uint32_t d, const void *gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+// 1-D bulk copy (TMA without a tensor map) of one whole row, issued by ONE thread; completion is counted in bytes on an
+// mbarrier that every thread then waits on (try_wait suspends the thread in hardware)
+__device__ __forceinline__ void vit_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void vit_bulk_row(uint32_t dst, const void *gsrc, uint32_t bytes, uint32_t bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(gsrc), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ bool vit_elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void vit_mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "VWAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 200000;\n\t"
+        "@p bra VDONE_%=;\n\t"
+        "bra VWAIT_%=;\n\t"
+        "VDONE_%=:\n\t}"
+        ::"r"(bar), "r"(parity)
+        : "memory");
+}
 __device__ __forceinline__ void cp_async_wait0_v() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_commit_v() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait1_v() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
@@ -218,6 +256,7 @@ viterbi_k1024_kernel(const float *__restrict__ post, long ld_t, long ld_b, const
     // the second traceback chunk buffer of the backtrace.
     constexpr int XROW = K + 12;                     // K k-mer columns (+ up to 3 floats of alignment phase + 1 chunk), stay at [XROW - 1]
     __shared__ __align__(16) float xrow_s[2][XROW];
+    __shared__ __align__(8) uint64_t xbar[2];         // LOGITS mode: a row staged by one bulk copy (TMA) has landed
     uint8_t *tb_s2 = reinterpret_cast<uint8_t *>(&xrow_s[0][0]);
     static_assert(sizeof(float) * 2 * XROW >= 8 * 1024, "xrow_s doubles as a traceback chunk buffer");
     constexpr int TBROW = K / 4;                     // uint16 traceback entries (one per quad of states) per event
@@ -238,11 +277,10 @@ viterbi_k1024_kernel(const float *__restrict__ post, long ld_t, long ld_b, const
     const int swp = (r >> 2) & 1;
     const int qa = 2 * r + swp, qb = 2 * r + 1 - swp;                 // quad index (16-byte chunk) of slot A / B
 
-    // LOGITS mode: rowms[t*B + b] = -(row max * log2 e + log2 sum exp(logit - max)) of the softmax row, combined from the
-    // GEMM's per-slice statistics by softmax_rowms_kernel; it is staged with the row (xrow[XROW - 2]) like the stay
-    // column.  (It used to be reduced here, by warp 0 with ten shuffles per event, which every other warp then waited
-    // for at the barrier.)
-    const float *msp = MODE == IN_LOGITS ? rowms + b : nullptr;       // advanced by B per event
+    // LOGITS mode: -(row max * log2 e + log2 sum exp(logit - max)) of the softmax row, combined from the GEMM's per-slice
+    // statistics by softmax_rowms_kernel, sits in the first padding column of the row (column K + 1) and is staged with it.
+    // (It used to be reduced here, by warp 0 with ten shuffles per event, which every other warp then waited for at the
+    // barrier.)
     // stage the row of the next event.  The k-mer columns of a row start at `a` = row (logits layout) or row + 1
     // (posterior layout), which is 16-byte aligned only in the first case; in general the row is copied as the
     // 16-byte ALIGNED chunks that cover it (257 128-bit cp.async per row instead of 1024 32-bit ones), keeping its
@@ -250,36 +288,67 @@ viterbi_k1024_kernel(const float *__restrict__ post, long ld_t, long ld_b, const
     // copied with its valid byte count only (zero filled), so nothing is read past the row's end; the first chunk
     // starts at most 3 floats before `a`, inside the tensor because its base is 16-byte aligned (checked: otherwise
     // 32-bit copies).  Thread 0 also stages the stay column at xrow[XROW - 1].
+    //
+    // The event loop below is unrolled by two so that every buffer index (row staging, v ping-pong) is a compile-time
+    // constant, and the staging addresses are 32-bit shared-memory addresses computed once: with run-time buffer
+    // pointers the compiler rebuilt generic addresses from the shared window base every event (~50 of the ~285
+    // instructions a thread issued per event; the kernel is issue-bound).
     const float *rowp = pb;                                           // advanced by ld_t per event
     constexpr int KOFF = MODE == IN_LOGITS ? 0 : 1;                    // first k-mer column of a row
     const bool span_rows = (((uintptr_t)post & 15) == 0);
-    auto phase_of = [&](const float *row) -> int { return span_rows ? (int)(((uintptr_t)(row + KOFF) >> 2) & 3) : 0; };
-    auto stage_row = [&](int buf) {
-        float *dst = xrow_s[buf];
+    // LOGITS rows are 16-byte aligned by contract (sloika_viterbi_logits_fwd checks base and pitches): phase 0
+    auto phase_of = [&](const float *row) -> int {
+        return MODE == IN_LOGITS ? 0 : (span_rows ? (int)(((uintptr_t)(row + KOFF) >> 2) & 3) : 0);
+    };
+    const uint32_t xs_sa = (uint32_t)__cvta_generic_to_shared(&xrow_s[0][0]);
+    const uint32_t xs_own = xs_sa + 32u * (uint32_t)r;                // this thread's two chunks of a staged row
+    constexpr uint32_t XROWB = XROW * sizeof(float);
+    const uint32_t xbar_sa = (uint32_t)__cvta_generic_to_shared(&xbar[0]);
+    if (MODE == IN_LOGITS) {
+        if (r == 0) {
+            vit_mbar_init(xbar_sa, 1);
+            vit_mbar_init(xbar_sa + 8u, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncthreads();
+    }
+    // row j is the (j >> 1)-th fill of buffer j & 1: its barrier phase has parity (j >> 1) & 1
+    auto wait_row = [&](auto buf_c, int j) {
+        if (MODE == IN_LOGITS) vit_mbar_wait(xbar_sa + 8u * (uint32_t)decltype(buf_c)::value, (uint32_t)(j >> 1) & 1u);
+    };
+    constexpr int MSCOL = MODE == IN_LOGITS ? K + 1 : XROW - 2;       // where the row statistic of a staged row lands
+    auto stage_row = [&](auto buf_c) {
+        constexpr uint32_t boff = (uint32_t)decltype(buf_c)::value * XROWB;
         const float *row = rowp;
         rowp += ld_t;
+        if (MODE == IN_LOGITS) {
+            // aligned rows [kmer 0..1023, stay, row statistic, pad, pad] (the statistic was put into the first padding
+            // column by softmax_rowms_kernel): ONE bulk copy of 4112 bytes by thread 0 instead of two cp.async per
+            // thread (each of which the compiler pads with three dummy shared-memory loads) plus two special cases
+            // (warp-uniform condition + elect.sync: with `r == 0` the compiler wraps the uniform-datapath copy in a loop over lanes)
+            if (r < 32 && vit_elect_one())
+                vit_bulk_row(xs_sa + boff, row, (uint32_t)(K + 4) * 4u, xbar_sa + 8u * (uint32_t)decltype(buf_c)::value);
+            return;
+        }
         const float *a = row + KOFF;
         if (span_rows) {
             const int ph = (int)(((uintptr_t)a >> 2) & 3);
             const float *a0 = a - ph;                                  // 16-byte aligned
-            cp_async16_v(dst + 4 * qa, a0 + 4 * qa);
-            cp_async16_v(dst + 4 * qb, a0 + 4 * qb);
-            if (r == 0 && ph != 0) cp_async16_zfill_v(dst + K, a0 + K, 4 * ph);
+            cp_async16_sa(xs_own + boff, a0 + 8 * r);
+            cp_async16_sa(xs_own + boff + 16u, a0 + 8 * r + 4);
+            if (r == 0 && ph != 0) cp_async16_zfill_sa(xs_sa + boff + 4u * K, a0 + K, 4 * ph);
         } else {
 #pragma unroll
-            for (int c = 0; c < 8; c++) cp_async4_v(dst + 8 * r + c, a + 8 * r + c);
+            for (int c = 0; c < 8; c++) cp_async4_sa(xs_own + boff + 4u * c, a + 8 * r + c);
         }
-        if (r == 0) cp_async4_v(dst + XROW - 1, MODE == IN_LOGITS ? row + K : row);
-        if (MODE == IN_LOGITS && r == 32) {
-            cp_async4_v(dst + XROW - 2, msp);
-            msp += B;
-        }
+        if (r == 0) cp_async4_sa(xs_sa + boff + 4u * (XROW - 1), row);
         cp_async_commit_v();
     };
+    constexpr int STAY = MODE == IN_LOGITS ? K : XROW - 1;            // where the stay column of a staged row lands
     // this thread's 8 k-mer columns of a staged row: three aligned 128-bit loads (conflict free; 32-bit loads at a
     // stride of 8 floats would hit 4 banks), then a shift by the row's phase (uniform over the CTA)
     auto load_cols = [&](const float *xr, int ph, float (&x)[8]) {
-        if (ph == 0) {          // slot order (A then B), see qa / qb
+        if (MODE == IN_LOGITS || ph == 0) {          // slot order (A then B), see qa / qb
             const float4 xa = reinterpret_cast<const float4 *>(xr)[qa], xb = reinterpret_cast<const float4 *>(xr)[qb];
             x[0] = xa.x; x[1] = xa.y; x[2] = xa.z; x[3] = xa.w; x[4] = xb.x; x[5] = xb.y; x[6] = xb.z; x[7] = xb.w;
             return;
@@ -315,13 +384,16 @@ viterbi_k1024_kernel(const float *__restrict__ post, long ld_t, long ld_b, const
         }
         return logf(__fadd_rn(__fadd_rn(c0, __fmul_rn(c1, v)), VIT_ETA));
     };
+    using buf0 = std::integral_constant<int, 0>;
+    using buf1 = std::integral_constant<int, 1>;
 
     const float *rowq = pb;                                           // row of the event being consumed (phase only)
-    stage_row(0);
+    stage_row(buf0());
     cp_async_wait0_v();
+    wait_row(buf0(), 0);
     __syncthreads();
     {
-        const float2 ms = make_float2(xrow_s[0][XROW - 2], 0.0f);
+        const float2 ms = make_float2(xrow_s[0][MSCOL], 0.0f);
         float q[8];
         load_cols(xrow_s[0], phase_of(rowq), q);
         rowq += ld_t;
@@ -331,21 +403,24 @@ viterbi_k1024_kernel(const float *__restrict__ post, long ld_t, long ld_b, const
         reinterpret_cast<float4 *>(vbuf[0])[qa] = va;                // v_0 = lpost[0][1:]   (decode.py:57); q[] is in slot order
         reinterpret_cast<float4 *>(vbuf[0])[qb] = vb;
     }
-    if (nev > 1) stage_row(1);
+    if (nev > 1) stage_row(buf1());
     cp_async_wait0_v();
     __syncthreads();
 
-    int cur = 0;
     uint32_t *tbp = reinterpret_cast<uint32_t *>(tbb) + r;            // this thread's two traceback entries, advanced per event
-    for (int i = 1; i < nev; i++) {
-        const float *xr = xrow_s[i & 1];
+    // one event: its row is staged in xrow_s[XB] (XB = i & 1), v_{i-1} is vbuf[XB ^ 1], v_i goes to vbuf[XB]
+    auto event = [&](auto xb_c, const int i, const bool more) {
+        constexpr int XB = decltype(xb_c)::value;
+        constexpr int CUR = XB ^ 1;
+        const float *xr = xrow_s[XB];
+        wait_row(xb_c, i);                                           // LOGITS mode; the others waited an event ago
         float x[8];
         load_cols(xr, phase_of(rowq), x);
         rowq += ld_t;
-        const float x0 = xr[XROW - 1];
-        const float2 ms = make_float2(xr[XROW - 2], 0.0f);
-        if (i + 1 < nev) stage_row((i + 1) & 1);                        // next event, asynchronous
-        const float *p = vbuf[cur];
+        const float x0 = xr[STAY];
+        const float2 ms = make_float2(xr[MSCOL], 0.0f);
+        if (more) stage_row(std::integral_constant<int, CUR>());     // next event, asynchronous
+        const float *p = vbuf[CUR];
         // step: first maximum over a of p[a*256 + q4] for the two quads q4 = 2r, 2r+1; published as (value, 4*a)
         float2 ss = reinterpret_cast<const float2 *>(p)[r];
         int as0 = 0, as1 = 0;
@@ -384,9 +459,8 @@ viterbi_k1024_kernel(const float *__restrict__ post, long ld_t, long ld_b, const
         sk = __fsub_rn(sk, skip_pen);
         const float pj[8] = {pa.x, pa.y, pa.z, pa.w, pb4.x, pb4.y, pb4.z, pb4.w};
         float vo[8];
-        unsigned packed = 0;
-#pragma unroll
         unsigned ent[2];
+#pragma unroll
         for (int h = 0; h < 2; h++) {                                    // h = slot (A, B)
             const float ssh = h == 0 ? ssA : ssB;
             const bool use_step = ssh > sk;                              // tie -> skip (decode.py:76)
@@ -402,15 +476,24 @@ viterbi_k1024_kernel(const float *__restrict__ post, long ld_t, long ld_b, const
             }
             ent[h] = e;
         }
-        packed = swp ? (ent[1] | (ent[0] << 16)) : (ent[0] | (ent[1] << 16));      // even quad in the low half
-        reinterpret_cast<float4 *>(vbuf[cur ^ 1])[qa] = make_float4(vo[0], vo[1], vo[2], vo[3]);
-        reinterpret_cast<float4 *>(vbuf[cur ^ 1])[qb] = make_float4(vo[4], vo[5], vo[6], vo[7]);
+        const unsigned packed = swp ? (ent[1] | (ent[0] << 16)) : (ent[0] | (ent[1] << 16));      // even quad in the low half
+        reinterpret_cast<float4 *>(vbuf[XB])[qa] = make_float4(vo[0], vo[1], vo[2], vo[3]);
+        reinterpret_cast<float4 *>(vbuf[XB])[qb] = make_float4(vo[4], vo[5], vo[6], vo[7]);
         tbp += TBROW / 2;
         *tbp = packed;
-        cur ^= 1;
-        cp_async_wait0_v();                                          // the next row has landed (issued an event ago)
+        if (MODE != IN_LOGITS) cp_async_wait0_v();                   // the next row has landed (issued an event ago)
         __syncthreads();
+    };
+    {
+        int i = 1;
+        for (; i + 2 < nev; i += 2) {                                  // events i (odd) and i + 1, both with a successor
+            event(buf1(), i, true);
+            event(buf0(), i + 1, true);
+        }
+        if (i < nev) event(buf1(), i, i + 1 < nev);
+        if (i + 1 < nev) event(buf0(), i + 1, false);
     }
+    const int cur = (nev - 1) & 1;                                       // v of the last event
 
     // ---- argmax of v_T (first maximum), backtrace, left-align: as in the generic kernel ----
     const float *v = vbuf[cur];
@@ -502,7 +585,10 @@ viterbi_k1024_kernel(const float *__restrict__ post, long ld_t, long ld_b, const
 
 // One float per softmax row from the GEMM's per-slice (max, sum exp) pairs: -(M log2 e + log2 S) with M the row maximum
 // and S = sum_j exp(logit_j - M), so that posterior_j = 2^(logit_j * log2 e + rowms).
-__global__ void softmax_rowms_kernel(const float2 *__restrict__ stats, int n_slices, long M, float *__restrict__ rowms)
+// It is stored in the first PADDING column of the row it belongs to (column K + 1 = 1025 of a row pitch that is a multiple
+// of 4 floats), so that the decoder stages k-mer logits, stay logit and statistic with one contiguous copy.
+__global__ void softmax_rowms_kernel(const float2 *__restrict__ stats, int n_slices, long M, float *__restrict__ logits,
+                                     long ld_t, long ld_b, int B, int col)
 {
     for (long m = blockIdx.x * (long)blockDim.x + threadIdx.x; m < M; m += (long)gridDim.x * blockDim.x) {
         const float2 *st = stats + m * n_slices;
@@ -513,7 +599,7 @@ __global__ void softmax_rowms_kernel(const float2 *__restrict__ stats, int n_sli
             const float2 v = __ldg(&st[s]);
             tot += v.y * ex2_ftz((v.x - mx) * SLOIKA_LOG2E);
         }
-        rowms[m] = -(mx * SLOIKA_LOG2E + lg2_ftz(tot));
+        logits[(m / B) * ld_t + (m % B) * ld_b + col] = -(mx * SLOIKA_LOG2E + lg2_ftz(tot));
     }
 }
 
@@ -590,7 +676,7 @@ extern "C" int sloika_viterbi_fwd(const float *post, long ld_t, long ld_b, const
     SLOIKA_RETURN_LAUNCH_STATUS();
 }
 
-extern "C" int sloika_viterbi_logits_fwd(const float *logits, long ld_t, long ld_b, const float *stats, int n_slices,
+extern "C" int sloika_viterbi_logits_fwd(float *logits, long ld_t, long ld_b, const float *stats, int n_slices,
                                          const int32_t *lengths, int T, int B, int nbase, int klen, double skip_pen,
                                          double min_prob, void *tb_ws, size_t ws_bytes, int32_t *path_out,
                                          int32_t *path_len, float *score_out, void *stream)
@@ -605,13 +691,14 @@ extern "C" int sloika_viterbi_logits_fwd(const float *logits, long ld_t, long ld
     const float c0 = (float)min_prob + 1e-10f, c1 = (float)(1.0 - min_prob), sp = (float)skip_pen;
     // the logits rows are (t, b) ordered: ld_t == B * ld_b is what the engine produces and what the statistics index
     if (ld_t != (long)B * ld_b && B > 1) return SLOIKA_ERR_UNSUPPORTED;
-    float *rowms = reinterpret_cast<float *>(static_cast<uint8_t *>(tb_ws) + (size_t)T * (size_t)B * 512);
+    if (ld_b < 1028 && B > 1) return SLOIKA_ERR_UNSUPPORTED;             // the row statistic lives in padding column 1025
+    if (ld_t < 1028) return SLOIKA_ERR_UNSUPPORTED;
     const long M = (long)T * B;
     long blocks = ceil_div(M, 256);
     if (blocks > 148L * 16) blocks = 148L * 16;
     softmax_rowms_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float2 *>(stats), n_slices, M,
-                                                                             rowms);
+                                                                             logits, ld_t, ld_b, B, 1025);
     viterbi_k1024_kernel<IN_LOGITS><<<B, VIT_THREADS, 0, (cudaStream_t)stream>>>(
-        logits, ld_t, ld_b, rowms, lengths, T, B, sp, c0, c1, (uint8_t *)tb_ws, path_out, path_len, score_out);
+        logits, ld_t, ld_b, nullptr, lengths, T, B, sp, c0, c1, (uint8_t *)tb_ws, path_out, path_len, score_out);
     SLOIKA_RETURN_LAUNCH_STATUS();
 }
