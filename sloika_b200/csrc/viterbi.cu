@@ -384,6 +384,16 @@ viterbi_k1024_kernel(const float *__restrict__ post, long ld_t, long ld_b, const
         }
         return logf(__fadd_rn(__fadd_rn(c0, __fmul_rn(c1, v)), VIT_ETA));
     };
+    // inside the event loop the LOGITS form keeps log2 of the floored posterior and folds the factor ln 2 into the
+    // addition of the predecessor's score (one FFMA instead of FMUL + FADD per state; the log-posterior is a MUFU
+    // approximation on this path anyway, and the fused product is the more accurate one)
+    auto lpost2_of = [&](float v, float2 ms) -> float {
+        if (MODE == IN_LOGITS) return lg2_ftz(fmaf(c1, ex2_ftz(fmaf(v, SLOIKA_LOG2E, ms.x)), c0));
+        return lpost_of(v, ms);
+    };
+    auto add_lpost = [&](float lq, float best) -> float {
+        return MODE == IN_LOGITS ? fmaf(lq, SLOIKA_LN2, best) : __fadd_rn(lq, best);
+    };
     using buf0 = std::integral_constant<int, 0>;
     using buf1 = std::integral_constant<int, 1>;
 
@@ -438,7 +448,7 @@ viterbi_k1024_kernel(const float *__restrict__ post, long ld_t, long ld_b, const
         const float lp0 = lpost_of(x0, ms);
         float lp[8];
 #pragma unroll
-        for (int c = 0; c < 8; c++) lp[c] = lpost_of(x[c], ms);
+        for (int c = 0; c < 8; c++) lp[c] = lpost2_of(x[c], ms);
         __syncthreads();
         // skip: predecessor a*64 + q with a = 4*a_hi + a_lo is p[a_hi*256 + (a_lo*64 + q)], so its maximum is
         // the maximum over a_lo of the published step maxima of quads a_lo*64 + q; "first maximum" = smallest a
@@ -468,7 +478,7 @@ viterbi_k1024_kernel(const float *__restrict__ post, long ld_t, long ld_b, const
             unsigned e = (use_step ? (1u + (unsigned)(h == 0 ? asA : asB)) : (5u + (unsigned)ak)) << 4;
 #pragma unroll
             for (int c = 0; c < 4; c++) {
-                const float move = __fadd_rn(lp[4 * h + c], best);
+                const float move = add_lpost(lp[4 * h + c], best);
                 const float stay = __fadd_rn(pj[4 * h + c], lp0);
                 const bool mv = move > stay;                             // tie -> stay (decode.py:81)
                 vo[4 * h + c] = mv ? move : stay;
