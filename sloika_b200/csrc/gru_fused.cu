@@ -17,6 +17,10 @@
 // "slot ready" (projection -> recurrence, after the writers' CTA barrier and a device fence) and "slot free"
 // (recurrence -> projection, when the step that read it has published its h).  One projection CTA serves two
 // recurrence CTAs because its step (216 MMAs, no dependent phases) is shorter than theirs.
+// (Tried: a CTA-wide lock so that only one issuing warp at a time feeds the tensor pipe -- the two panels' / groups' MMAs
+// then no longer alternate between accumulators.  The issue of a phase did not get faster -- an N = 32 instruction costs
+// ~24 cycles here with or without interleaving, the projection CTA's tensor pipe is ~80 % busy -- and the lock's
+// serialisation added 130 cycles per step: 3061 -> 3191.  Not kept.)
 #include <cstdio>
 #include <cstdlib>
 #include <cuda_fp16.h>

@@ -5,10 +5,12 @@ import torch
 from sloika_b200 import cabi
 lib = cabi.load()
 dev = torch.device('cuda:0')
+PITCH = int(os.environ.get('PITCH', '0'))
 def run(M, K, N, algo, reps=5):
     pad = lambda n: (n + 3) // 4 * 4
+    padn = (lambda n: (n + PITCH - 1) // PITCH * PITCH) if PITCH else pad      # env PITCH: output row pitch a multiple of this many floats
     x = torch.tanh(torch.randn(M, pad(K), device=dev))[:, :K]; W = torch.randn(N, K, device=dev); b = torch.randn(N, device=dev)
-    y = torch.empty(M, pad(N), device=dev)[:, :N]
+    y = torch.empty(M, padn(N), device=dev)[:, :N]
     st = cabi.stream_ptr(dev)
     for _ in range(2):
         rc = lib.sloika_linear_fwd_ex(cabi.ptr(x), x.stride(0), cabi.ptr(W), cabi.ptr(b), cabi.ptr(y), y.stride(0), M, K, N, 0, algo, st)
