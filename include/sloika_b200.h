@@ -153,6 +153,18 @@ int sloika_gru_fused_fwd(const float *x, long ldx, const float *iW, const float 
                          const float *b, float *y, long ldy, void *ws, size_t ws_bytes, const int32_t *lengths,
                          int T, int B, int I, int H, int reverse, int act, int gate_act, void *stream);
 
+/*
+ * The layer for an input whose range is known only on the device: `absmax` points at max |x| as written by the
+ * producing kernel (sloika_conv1d_fwd_ex for an elu / linear convolution).  Both forms are enqueued and that word picks
+ * one: below `limit` the fused launch above, otherwise a tf32-split projection GEMM into vI (T*B rows of pitch ldv >= 3H,
+ * 16-byte aligned) followed by the recurrence kernel; the CTAs of the form that is ruled out return at once.  Same
+ * shape limits as sloika_gru_fused_fwd; `seqs_in_flight` as in sloika_gru_recurrence_fwd_ex.
+ */
+int sloika_gru_fwd_gated(const float *x, long ldx, const float *iW, const float *sW, const float *sW2,
+                         const float *b, float *y, long ldy, float *vI, long ldv, void *ws, size_t ws_bytes,
+                         const int32_t *lengths, int T, int B, int I, int H, int reverse, int act, int gate_act,
+                         long seqs_in_flight, const float *absmax, float limit, void *stream);
+
 /* The recurrence alone, given vI: T*B rows of 3H floats with row pitch ld_vi >= 3H (what sloika_gru_fwd runs
  * after the projection; a pitch that is a multiple of 4 floats keeps every row 16-byte aligned for odd H). */
 int sloika_gru_recurrence_fwd(const float *vI, long ld_vi, const float *sW, const float *sW2, float *y, long ldy,

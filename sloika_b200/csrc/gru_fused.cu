@@ -23,6 +23,7 @@
 // serialisation added 130 cycles per step: 3061 -> 3191.  Not kept.)
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <cuda_fp16.h>
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -95,8 +96,10 @@ template <int HP, int IP, int G>
 __global__ void __launch_bounds__(2 * G *(CWP + 1) * 32, 1)
 gru_fused_kernel(const float *__restrict__ x, long ldx, const float *__restrict__ iW, const float *__restrict__ bias,
                  const float *__restrict__ sW, const float *__restrict__ sW2, float *__restrict__ y, long ldy,
-                 float *__restrict__ ring, const int32_t *__restrict__ lengths, int T, int B, int I, int H, int reverse)
+                 float *__restrict__ ring, const int32_t *__restrict__ lengths, int T, int B, int I, int H, int reverse,
+                 const Gate gate)
 {
+    if (gate_closed(gate)) return;                // every CTA of every cluster alike: nobody is left waiting
     constexpr int KC = HP / 16, KCP = IP / 16;
     constexpr int ACOLS = HP / 2, ACOLS_P = IP / 2;
     constexpr int OPB = HP * 2 * N;               // bytes of one recurrence operand array [k][N]
@@ -543,7 +546,7 @@ static size_t smem_bytes()
 
 template <int HP, int IP, int G>
 static int launch(const float *x, long ldx, const float *iW, const float *bias, const float *sW, const float *sW2, float *y,
-                  long ldy, float *ring, const int32_t *lengths, int T, int B, int I, int H, int reverse, cudaStream_t st)
+                  long ldy, float *ring, const int32_t *lengths, int T, int B, int I, int H, int reverse, cudaStream_t st, Gate gate)
 {
     const size_t smem = smem_bytes<HP, IP, G>();
     auto kern = gru_fused_kernel<HP, IP, G>;
@@ -561,7 +564,7 @@ static int launch(const float *x, long ldx, const float *iW, const float *bias, 
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    err = cudaLaunchKernelEx(&cfg, kern, x, ldx, iW, bias, sW, sW2, y, ldy, ring, lengths, T, B, I, H, reverse);
+    err = cudaLaunchKernelEx(&cfg, kern, x, ldx, iW, bias, sW, sW2, y, ldy, ring, lengths, T, B, I, H, reverse, gate);
     if (err != cudaSuccess) return (int)err;
     SLOIKA_RETURN_LAUNCH_STATUS();
 }
@@ -595,9 +598,9 @@ extern "C" size_t sloika_gru_fused_workspace_bytes(int B, int H)
     return gru6::ring_bytes(B, hp_of(H));
 }
 
-extern "C" int sloika_gru_fused_fwd(const float *x, long ldx, const float *iW, const float *sW, const float *sW2,
-                                    const float *b, float *y, long ldy, void *ws, size_t ws_bytes, const int32_t *lengths,
-                                    int T, int B, int I, int H, int reverse, int act, int gate_act, void *stream)
+static int fused_fwd(const float *x, long ldx, const float *iW, const float *sW, const float *sW2, const float *b, float *y,
+                     long ldy, void *ws, size_t ws_bytes, const int32_t *lengths, int T, int B, int I, int H, int reverse,
+                     int act, int gate_act, void *stream, gru5::Gate gate)
 {
     if (!x || !iW || !sW || !sW2 || !b || !y || T < 0 || B <= 0 || I <= 0 || H <= 0 || ldx < I || ldy < H) return SLOIKA_ERR_ARG;
     if (act != SLOIKA_ACT_TANH || gate_act != SLOIKA_ACT_SIGMOID) return SLOIKA_ERR_UNSUPPORTED;
@@ -610,10 +613,54 @@ extern "C" int sloika_gru_fused_fwd(const float *x, long ldx, const float *iW, c
     float *ring = static_cast<float *>(ws);
     const int HP = hp_of(H), IP = padded16(I) <= 32 ? 32 : padded16(I) <= 64 ? 64 : 96;
 #define FUSED_CASE(HP_, IP_) \
-    if (HP == HP_ && IP == IP_) return gru6::launch<HP_, IP_, gru6::GF>(x, ldx, iW, b, sW, sW2, y, ldy, ring, lengths, T, B, I, H, reverse, st)
+    if (HP == HP_ && IP == IP_) return gru6::launch<HP_, IP_, gru6::GF>(x, ldx, iW, b, sW, sW2, y, ldy, ring, lengths, T, B, I, H, reverse, st, gate)
     FUSED_CASE(32, 32); FUSED_CASE(32, 64); FUSED_CASE(32, 96);
     FUSED_CASE(64, 32); FUSED_CASE(64, 64); FUSED_CASE(64, 96);
     FUSED_CASE(96, 32); FUSED_CASE(96, 64); FUSED_CASE(96, 96);
 #undef FUSED_CASE
     return SLOIKA_ERR_UNSUPPORTED;
+}
+
+extern "C" int sloika_gru_fused_fwd(const float *x, long ldx, const float *iW, const float *sW, const float *sW2,
+                                    const float *b, float *y, long ldy, void *ws, size_t ws_bytes, const int32_t *lengths,
+                                    int T, int B, int I, int H, int reverse, int act, int gate_act, void *stream)
+{
+    return fused_fwd(x, ldx, iW, sW, sW2, b, y, ldy, ws, ws_bytes, lengths, T, B, I, H, reverse, act, gate_act, stream,
+                     gru5::Gate{nullptr, 0u, 0});
+}
+
+namespace sloika {
+namespace gemm_tc {
+int launch(const float *x, long ldx, const float *W, const float *bias, float *y, long ldy, long M, int K, int N, int act,
+           float2 *stats, int rot, bool f16, cudaStream_t st, const unsigned *gate, unsigned gate_limit, int gate_mode);
+}
+namespace gru5 {
+int dispatch_gated(const float *vI, long ldv, const float *sW, const float *sW2, float *y, long ldy, const int32_t *lengths,
+                   int T, int B, int H, int reverse, int act, int gate_act, long seqs_in_flight, cudaStream_t st, Gate gate);
+}
+}  // namespace sloika
+
+// The layer for an input whose range is known only on the device (`absmax`: max |x| written by the producing kernel, e.g.
+// sloika_conv1d_fwd_ex for an elu convolution): BOTH forms are enqueued and the device word picks one --
+//   max |x| <  limit : the fused launch above (fp16 hi / lo operands are exact enough only inside the fp16 range)
+//   max |x| >= limit : tf32-split projection GEMM into `vI`, then the recurrence kernel
+// The CTAs of the form that is ruled out return at once (a few microseconds per launch).
+extern "C" int sloika_gru_fwd_gated(const float *x, long ldx, const float *iW, const float *sW, const float *sW2,
+                                    const float *b, float *y, long ldy, float *vI, long ldv, void *ws, size_t ws_bytes,
+                                    const int32_t *lengths, int T, int B, int I, int H, int reverse, int act, int gate_act,
+                                    long seqs_in_flight, const float *absmax, float limit, void *stream)
+{
+    if (!absmax || !vI || !(limit > 0.0f) || ldv < 3L * H) return SLOIKA_ERR_ARG;
+    if ((ldv & 3) != 0 || ((uintptr_t)vI & 15) != 0 || (long)T * B < 128) return SLOIKA_ERR_UNSUPPORTED;
+    unsigned limit_bits;
+    memcpy(&limit_bits, &limit, sizeof(limit_bits));
+    const unsigned *word = reinterpret_cast<const unsigned *>(absmax);
+    int rc = fused_fwd(x, ldx, iW, sW, sW2, b, y, ldy, ws, ws_bytes, lengths, T, B, I, H, reverse, act, gate_act, stream,
+                       gru5::Gate{word, limit_bits, 1});
+    if (rc != SLOIKA_OK || T == 0) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    rc = gemm_tc::launch(x, ldx, iW, b, vI, ldv, (long)T * B, I, 3 * H, SLOIKA_ACT_LINEAR, nullptr, 0, false, st, word, limit_bits, 2);
+    if (rc != SLOIKA_OK) return rc;
+    return gru5::dispatch_gated(vI, ldv, sW, sW2, y, ldy, lengths, T, B, H, reverse, act, gate_act, seqs_in_flight, st,
+                                gru5::Gate{word, limit_bits, 2});
 }

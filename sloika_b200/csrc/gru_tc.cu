@@ -52,8 +52,9 @@ struct Bars {                 // per group
 template <int HP, int G, int CW, int N>
 __global__ void __launch_bounds__(G *(CW + 1) * 32, 1)
 gru_tc_kernel(const float *__restrict__ vI, long ldv, const float *__restrict__ sW, const float *__restrict__ sW2,
-              float *__restrict__ y, long ldy, const int32_t *__restrict__ lengths, int T, int B, int H, int reverse)
+              float *__restrict__ y, long ldy, const int32_t *__restrict__ lengths, int T, int B, int H, int reverse, const Gate gate)
 {
+    if (gate_closed(gate)) return;
     constexpr int KC = HP / 16;                   // K = 16 chunks
     constexpr int ACOLS = HP / 2;                 // TMEM columns of one A tile
     constexpr int D_BASE = 6 * ACOLS;             // accumulators behind the 6 weight tiles
@@ -314,7 +315,7 @@ gru_tc_kernel(const float *__restrict__ vI, long ldv, const float *__restrict__ 
 
 template <int HP, int G, int CW, int N>
 static int launch(const float *vI, long ldv, const float *sW, const float *sW2, float *y, long ldy, const int32_t *lengths,
-                  int T, int B, int H, int reverse, cudaStream_t st)
+                  int T, int B, int H, int reverse, cudaStream_t st, Gate gate)
 {
     size_t smem = 128 + (size_t)G * 4 * HP * 2 * N + (size_t)G * 3 * N * 3 * HP * 4 + (size_t)G * sizeof(Bars) + 64;
     // every CTA of this kernel owns the whole tensor memory of its SM: ask for more than half of the shared memory
@@ -324,16 +325,16 @@ static int launch(const float *vI, long ldv, const float *sW, const float *sW2, 
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (err != cudaSuccess) return (int)err;
     const unsigned grid = (unsigned)ceil_div(B, G * N);
-    kern<<<grid, G *(CW + 1) * 32, smem, st>>>(vI, ldv, sW, sW2, y, ldy, lengths, T, B, H, reverse);
+    kern<<<grid, G *(CW + 1) * 32, smem, st>>>(vI, ldv, sW, sW2, y, ldy, lengths, T, B, H, reverse, gate);
     SLOIKA_RETURN_LAUNCH_STATUS();
 }
 
 template <int HP>
 static int launch_hp(int g, int cw, int n, const float *vI, long ldv, const float *sW, const float *sW2, float *y, long ldy,
-                     const int32_t *lengths, int T, int B, int H, int reverse, cudaStream_t st)
+                     const int32_t *lengths, int T, int B, int H, int reverse, cudaStream_t st, Gate gate)
 {
 #define TC_SHAPE(G_, CW_, N_) \
-    if (g == G_ && cw == CW_ && n == N_) return launch<HP, G_, CW_, N_>(vI, ldv, sW, sW2, y, ldy, lengths, T, B, H, reverse, st)
+    if (g == G_ && cw == CW_ && n == N_) return launch<HP, G_, CW_, N_>(vI, ldv, sW, sW2, y, ldy, lengths, T, B, H, reverse, st, gate)
     TC_SHAPE(1, 4, 8); TC_SHAPE(1, 8, 8); TC_SHAPE(1, 16, 8);
     TC_SHAPE(2, 4, 8); TC_SHAPE(2, 8, 8);
     TC_SHAPE(4, 4, 8);
@@ -347,8 +348,8 @@ static int launch_hp(int g, int cw, int n, const float *vI, long ldv, const floa
 // (this batch times the batches it pipelines on other streams): it picks how many groups of 8 sequences share a
 // CTA, i.e. whether the SMs are spread over one batch (latency) or packed (throughput).
 // SLOIKA_B200_GRU_TC="G,CW[,N]" overrides (groups per CTA, compute warps per group, sequences per group).
-int dispatch(const float *vI, long ldv, const float *sW, const float *sW2, float *y, long ldy, const int32_t *lengths, int T,
-             int B, int H, int reverse, int act, int gate_act, long seqs_in_flight, cudaStream_t st)
+int dispatch_gated(const float *vI, long ldv, const float *sW, const float *sW2, float *y, long ldy, const int32_t *lengths,
+                   int T, int B, int H, int reverse, int act, int gate_act, long seqs_in_flight, cudaStream_t st, Gate gate)
 {
     if (act != SLOIKA_ACT_TANH || gate_act != SLOIKA_ACT_SIGMOID) return SLOIKA_ERR_UNSUPPORTED;
     if (H > 128 || (ldv & 3) != 0 || ((uintptr_t)vI & 15) != 0) return SLOIKA_ERR_UNSUPPORTED;
@@ -361,13 +362,19 @@ int dispatch(const float *vI, long ldv, const float *sW, const float *sW2, float
         const int got = sscanf(ov, "%d,%d,%d", &og, &ocw, &on);
         if (got >= 2) { g = og; cw = ocw; n = got == 3 ? on : 8; }
     }
-#define TC_CASE(HP_) return launch_hp<HP_>(g, cw, n, vI, ldv, sW, sW2, y, ldy, lengths, T, B, H, reverse, st)
+#define TC_CASE(HP_) return launch_hp<HP_>(g, cw, n, vI, ldv, sW, sW2, y, ldy, lengths, T, B, H, reverse, st, gate)
     if (H <= 32) TC_CASE(32);
     if (H <= 64) TC_CASE(64);
     if (H <= 96) TC_CASE(96);
     if (H <= 112) TC_CASE(112);
     TC_CASE(128);
 #undef TC_CASE
+}
+
+int dispatch(const float *vI, long ldv, const float *sW, const float *sW2, float *y, long ldy, const int32_t *lengths, int T,
+             int B, int H, int reverse, int act, int gate_act, long seqs_in_flight, cudaStream_t st)
+{
+    return dispatch_gated(vI, ldv, sW, sW2, y, ldy, lengths, T, B, H, reverse, act, gate_act, seqs_in_flight, st, Gate{nullptr, 0u, 0});
 }
 
 }  // namespace gru5

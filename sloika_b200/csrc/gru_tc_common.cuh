@@ -47,6 +47,20 @@ __device__ __forceinline__ void wait_bar(uint64_t *bar, uint32_t parity) {
 __device__ __forceinline__ void nbar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void nbar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
+// Device-side choice between two enqueued forms of the same layer (as in gemm_tc.cu): `word` holds the bits of a
+// non-negative float (max |x| reported by the producing kernel); mode 1 runs only if it is below `limit`, mode 2 only if
+// it is not, mode 0 always.  Every CTA of the form that is ruled out returns at once.
+struct Gate {
+    const unsigned *word;
+    unsigned limit;
+    int mode;
+};
+__device__ __forceinline__ bool gate_closed(const Gate &g) {
+    if (g.mode == 0) return false;
+    const bool below = *g.word < g.limit;
+    return below != (g.mode == 1);
+}
+
 template <int NS>
 __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t (&r)[NS]) {
     if constexpr (NS == 8) tmem_ld_32x32b_x8(taddr, r);

@@ -232,9 +232,11 @@ def run_feedforward(layer, act, out=None):
 
 
 def _padded_rows(T, B, F, device):
-    """[T, B, F] view of a buffer whose rows are padded to a multiple of 4 floats (16-byte aligned rows
-    let the kernels use 128-bit accesses; 1025 posterior columns become a pitch of 1028)."""
-    pitch = (F + 3) // 4 * 4
+    """[T, B, F] view of a buffer whose rows are padded to a multiple of 8 floats: 16-byte aligned rows let the kernels
+    use 128-bit accesses and TMA, and 32-byte (one L2 sector) aligned rows keep the 128-byte row segments of the GEMM's
+    TMA-store boxes from straddling sectors (the 1025-column logits GEMM is 8 % faster at a pitch of 1032 floats than
+    at 1028, tools/gemm_bench.py with PITCH=8)."""
+    pitch = (F + 7) // 8 * 8
     return _empty((T, B, pitch), device)[:, :, :F]
 
 
@@ -301,15 +303,24 @@ def run_softmax(layer, act, out=None):
 def _fused_gru_ok(layer, act):
     """The projection-in-the-recurrence launch (csrc/gru_fused.cu) applies: throughput mode (enough sequences in
     flight on the device that 32 per recurrence CTA is the right packing, as in `sloika_gru_recurrence_fwd_ex`),
-    bounded input, sizes that fit the tensor memory / shared memory of its projection CTA.
+    sizes that fit the tensor memory / shared memory of its projection CTA, and an input inside the fp16 range:
+    returns 'fused' when that is known here (bounded activations), 'gated' when only the device knows (the producing
+    kernel left max |x| in `act.absmax`: both forms are enqueued, `sloika_gru_fwd_gated`), else None.
     SLOIKA_B200_FUSED_GRU=1 forces it for any batch, =0 turns it off."""
     env = os.environ.get('SLOIKA_B200_FUSED_GRU', '')
     if env == '0':
-        return False
+        return None
     busy = act.B * max(1, BATCHES_IN_FLIGHT) * _CONCURRENT_BRANCHES > 16 * 148
-    return (busy or env not in ('', '0')) and act.bounded and layer.size <= 96 and layer.insize <= 96 and act.ld % 4 == 0 \
+    shape_ok = (busy or env not in ('', '0')) and layer.size <= 96 and layer.insize <= 96 and act.ld % 4 == 0 \
         and act.data.data_ptr() % 16 == 0 and code_of(layer.fun) == 1 and code_of(layer.gatefun) == 2 \
         and layer.iW.absmax() < _F16_WEIGHT_LIMIT
+    if not shape_ok:
+        return None
+    if act.bounded:
+        return 'fused'
+    if act.absmax is not None and act.T * act.B >= 128 and not os.environ.get('SLOIKA_B200_NO_F16'):
+        return 'gated'
+    return None
 
 
 def run_gru(layer, act, out=None):
@@ -317,7 +328,24 @@ def run_gru(layer, act, out=None):
     assert act.F == layer.insize
     y = _out_buffer(act, act.T, layer.size, out)
     dev = act.device
-    if _fused_gru_ok(layer, act):
+    form = _fused_gru_ok(layer, act)
+    if form == 'gated':
+        import torch
+        nbytes = lib.sloika_gru_fused_workspace_bytes(act.B, layer.size)
+        ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=dev)
+        vI = _padded_rows(act.T, act.B, 3 * layer.size, dev)     # written only if the input leaves the fp16 range
+        launch('gru_fused', 3, lib.sloika_gru_fwd_gated,
+               cabi.ptr(act.data), act.ld, cabi.ptr(layer.iW.device(dev)), cabi.ptr(layer.sW.device(dev)),
+               cabi.ptr(layer.sW2.device(dev)), cabi.ptr(layer.b.device(dev)), cabi.ptr(y), _row_stride(y), cabi.ptr(vI),
+               _row_stride(vI), cabi.ptr(ws), nbytes, cabi.ptr(act.lengths), act.T, act.B, layer.insize, layer.size,
+               1 if act.reverse else 0, code_of(layer.fun), code_of(layer.gatefun),
+               act.B * max(1, BATCHES_IN_FLIGHT) * _CONCURRENT_BRANCHES, cabi.ptr(act.absmax), _F16_INPUT_LIMIT,
+               cabi.stream_ptr(dev))
+        stream = torch.cuda.current_stream(dev)
+        ws.record_stream(stream)
+        vI.record_stream(stream)
+        return act.like(y, bounded=True)
+    if form == 'fused':
         import torch
         nbytes = lib.sloika_gru_fused_workspace_bytes(act.B, layer.size)
         ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=dev)

@@ -721,7 +721,7 @@ def test_gru_fused_projection(I, H, T, B, reverse, ragged, monkeypatch):
     x = np.tanh(np.random.standard_normal((T, B, I))).astype(np.float32)
     a = engine.Act(torch.from_numpy(x).to(DEV), None if lengths is None else torch.as_tensor(lengths, dtype=torch.int32, device=DEV),
                    bounded=True)
-    assert engine._fused_gru_ok(g, a)
+    assert engine._fused_gru_ok(g, a) == 'fused'
     engine.TIMER.reset()
     out = layer.run(a)
     torch.cuda.synchronize()
@@ -731,3 +731,32 @@ def test_gru_fused_projection(I, H, T, B, reverse, ragged, monkeypatch):
         ref = _oracle(layer, x[:n, b:b + 1])
         assert np.abs(got[:n, b] - ref[:, 0]).max() < 5e-5, b
         assert np.all(got[n:, b] == 0)
+
+
+@pytest.mark.parametrize('scale,reverse', [(1.0, False), (3.0e4, True)])
+def test_gru_gated_between_fused_and_projection(scale, reverse, monkeypatch):
+    """An input whose range only the device knows (the elu convolution's output, max |x| in `Act.absmax`): both forms of
+    the layer are enqueued (sloika_gru_fwd_gated) and the device word picks the fused launch (inside the fp16 range) or
+    the tf32 projection + recurrence (outside); either way the result is the oracle's."""
+    monkeypatch.setenv('SLOIKA_B200_FUSED_GRU', '1')
+    np.random.seed(77)
+    I, H, T, B = 96, 96, 40, 70
+    g = layers.Gru(I, H, init=_init(), has_bias=True)
+    if scale > 1:
+        g.iW.set_value(g.iW.get_value() / scale * 4)              # keep the gates out of saturation for huge inputs
+    layer = layers.Reverse(g) if reverse else g
+    x = (np.random.standard_normal((T, B, I)) * scale).astype(np.float32)
+    xd = torch.from_numpy(x).to(DEV)
+    a = engine.Act(xd, None, bounded=False, absmax=xd.abs().max().reshape(1))
+    assert engine._fused_gru_ok(g, a) == 'gated'
+    engine.TIMER.reset()
+    got = layer.run(a).data.cpu().numpy()
+    assert engine.TIMER.launches == 3
+    ref = _oracle(layer, x)
+    tol = 5e-5 if scale == 1.0 else 2e-4                          # tf32-split products of inputs of magnitude 1e5
+    assert np.abs(got - ref).max() < tol
+    if scale == 1.0:
+        # the other verdict on the same input: projection + recurrence
+        other = engine.Act(xd, None, bounded=False, absmax=torch.tensor([1.0e9], dtype=torch.float32, device=DEV))
+        got2 = layer.run(other).data.cpu().numpy()
+        assert np.abs(got2 - ref).max() < 5e-5
