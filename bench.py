@@ -501,21 +501,39 @@ def run_b200_arm(args):
     dom_ms, dom_calls = kernel_ms_single[dominant]
     dom_bytes_per_launch = alg_by_kernel.get(dominant, 0.0) * samples_per_step * iso_steps / dom_calls
     achieved = dom_bytes_per_launch / (dom_ms / dom_calls * 1e-3) / 1e9
-    traffic = None
+    traffic_table = {}
     try:
         if args.workload == 'raw_rgrgr' and B == BATCH_PER_GPU and T == CHUNK_LEN:
-            with open(os.path.join(ROOT, 'profiles', 'r2_traffic.json')) as fh:
-                traffic = json.load(fh).get(dominant)
+            with open(os.path.join(ROOT, 'profiles', 'r2f_traffic.json')) as fh:
+                traffic_table = json.load(fh)
     except Exception:
-        traffic = None
-    pipe_ms, pipe_calls = kernel_ms.get(dominant, (0.0, 1))
+        traffic_table = {}
+    traffic = traffic_table.get(dominant)
+    pipe_ms, pipe_calls = kernel_ms.get(dominant, (0.0, 0))
     roofline = {"kernel": dominant, "bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                 "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peaks_src,
                 "algorithmic_bytes_per_launch": dom_bytes_per_launch,
                 "avg_launch_ms": dom_ms / dom_calls,
                 "measured_in": "single_batch pass of this run (CUDA events on the launching stream, one batch in flight)",
-                "share_of_kernel_time": dom_ms / sum(v[0] for v in kernel_ms_single.values()),
-                "pipelined_avg_launch_ms": pipe_ms / max(pipe_calls, 1), "pipelined_launches_in_flight": K}
+                "share_of_kernel_time": dom_ms / sum(v[0] for v in kernel_ms_single.values())}
+    # the same figures for the kernel with the largest share INSIDE the timed (pipelined) region, from the spans recorded
+    # there: `in_flight` batches share the SMs and HBM, so a launch is stretched by its neighbours -- the fraction says
+    # how much of the device's bandwidth one launch uses while it runs, not how good the kernel is
+    tr_alg = dict(alg_by_kernel, gru_recurrence=gru_share(kernel_ms, 'gru_recurrence'), gru_fused=gru_share(kernel_ms, 'gru_fused'))
+    tr_dom = max(kernel_ms, key=lambda k: kernel_ms[k][0])
+    tr_ms, tr_calls = kernel_ms[tr_dom]
+    tr_bytes = tr_alg.get(tr_dom, 0.0) * samples_per_step * args.steps / tr_calls
+    tr_achieved = tr_bytes / (tr_ms / tr_calls * 1e-3) / 1e9
+    roofline["timed_region"] = {"kernel": tr_dom, "achieved": tr_achieved, "frac": tr_achieved / hbm_peak,
+                                "algorithmic_bytes_per_launch": tr_bytes, "avg_launch_ms": tr_ms / tr_calls,
+                                "traffic": traffic_table.get(tr_dom), "batches_in_flight": K,
+                                "share_of_kernel_time": tr_ms / sum(v[0] for v in kernel_ms.values())}
+    # and for the step as a whole: all algorithmic bytes of a batch over the device time per batch
+    step_bytes = sum(alg.values()) * samples_per_step
+    step_gbps = step_bytes / (ms_dev / args.steps * 1e-3) / 1e9
+    roofline["step"] = {"algorithmic_bytes": step_bytes, "achieved": step_gbps, "frac": step_gbps / hbm_peak,
+                        "traffic": (sum(traffic_table.get(k, 0.0) * c / args.steps for k, (_, c) in kernel_ms.items())
+                                    if traffic_table else None)}
     if 'gru_recurrence' in kernel_ms_single:
         # the recurrence is bound by the latency of its dependent steps, not by HBM: say so on the line
         rec_ms, rec_calls = kernel_ms_single['gru_recurrence']
@@ -525,7 +543,7 @@ def run_b200_arm(args):
                                "pipelined_kernel": pipe_name,
                                "us_per_time_step_pipelined": 1e3 * kernel_ms[pipe_name][0] / kernel_ms[pipe_name][1] / steps_per_launch,
                                "time_steps_per_launch": steps_per_launch,
-                               "ncu": "profiles/r2_step_kernels_ncu.txt (warps active, issue active, tensor pipe)"}
+                               "ncu": "profiles/r2f_step_kernels_ncu.txt (warps active, issue active, tensor pipe)"}
     total_alg = sum(alg.values())
     paper = min(hbm_peak * 1e9 / total_alg, float(peaks.get('bf16_tflops_sustained', 1400.0)) * 1e12 / flops_per_sample(net))
 
