@@ -16,6 +16,7 @@ owns its own 1024 chunks; no data-path collective).  Prints ONE JSON line on ran
 import argparse
 import json
 import os
+os.environ.setdefault('CUDA_DEVICE_MAX_CONNECTIONS', '32')     # one hardware queue per stream of the pipelined step (sloika_b200/__init__.py)
 import subprocess
 import sys
 import threading
@@ -48,8 +49,9 @@ def parse_args():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'],
                     help='weak: --batch chunks per GPU; strong: --batch chunks in total, split over the GPUs')
-    ap.add_argument('--in-flight', type=int, default=4,
-                    help='batches pipelined on separate CUDA streams (1 = one batch after the other)')
+    ap.add_argument('--in-flight', type=int, default=None,
+                    help='batches pipelined on separate CUDA streams (1 = one batch after the other); default: 16 for the '
+                         'stride-5 workloads (~6 GB per batch), 4 otherwise')
     return ap.parse_args()
 
 
@@ -360,6 +362,15 @@ def run_b200_arm(args):
     x_host = torch.randn((T, B, 1), generator=gen, dtype=torch.float32).pin_memory()
     x_dev = x_host.to(dev)
     samples_per_step = T * B
+    if args.in_flight is None:
+        # stride-5 workloads (~6.5 GB per batch): up to 20 batches in flight, and a count that divides the timed steps so
+        # that the last round is a full one (a GRU layer holds 8 SMs per batch for ~5 ms: a lone batch at the end of the
+        # run would leave the device idle behind it); the stride-2 workloads need 2.5 x the memory per batch
+        if args.workload in ('raw_rgrgr', 'pretrained_like'):
+            rounds = -(-max(args.steps, 1) // 20)
+            args.in_flight = -(-max(args.steps, 1) // rounds)
+        else:
+            args.in_flight = 4
     K = max(1, args.in_flight)
     calc_post.prepare()
     main = torch.cuda.current_stream(dev)
@@ -474,11 +485,12 @@ def run_b200_arm(args):
     # GRU layers run either as projection GEMM + recurrence kernel or as one fused launch (csrc/gru_fused.cu); the
     # layer's algorithmic bytes go to whichever kernel ran it, in proportion to the launches
     def gru_share(kms, name):
-        calls = {k: kms.get(k, (0.0, 0))[1] for k in ('gru_recurrence', 'gru_fused')}
+        calls = {k: kms.get(k, (0.0, 0))[1] for k in ('gru_recurrence', 'gru_fused', 'gru_seq')}
         total = sum(calls.values())
         return alg.get('gru_layer', 0.0) * calls[name] / total if total else 0.0
     alg_by_kernel = {'conv1d': alg.get('conv1d', 0.0), 'gru_recurrence': gru_share(kernel_ms_single, 'gru_recurrence'),
-                     'gru_fused': gru_share(kernel_ms_single, 'gru_fused'),
+                     'gru_fused': gru_share(kernel_ms_single, 'gru_fused'), 'gru_seq': gru_share(kernel_ms_single, 'gru_seq'),
+                     'block_layout': 0.0,
                      'gru_projection': 0.0, 'feedforward': alg.get('feedforward', 0.0),
                      'softmax': alg.get('softmax', 0.0), 'viterbi': alg.get('viterbi', 0.0)}
     def table(kms, steps):
@@ -491,9 +503,11 @@ def run_b200_arm(args):
     breakdown_single = table(kernel_ms_single, iso_steps)  # one batch in flight: undisturbed durations
     alg_by_kernel['gru_recurrence'] = gru_share(kernel_ms, 'gru_recurrence')
     alg_by_kernel['gru_fused'] = gru_share(kernel_ms, 'gru_fused')
+    alg_by_kernel['gru_seq'] = gru_share(kernel_ms, 'gru_seq')
     breakdown = table(kernel_ms, args.steps)               # spans inside the pipelined region: they overlap each other
     alg_by_kernel['gru_recurrence'] = gru_share(kernel_ms_single, 'gru_recurrence')
     alg_by_kernel['gru_fused'] = gru_share(kernel_ms_single, 'gru_fused')
+    alg_by_kernel['gru_seq'] = gru_share(kernel_ms_single, 'gru_seq')
     # dominant kernel = largest share of the step when a batch has the GPU to itself; its roofline numbers come from
     # that pass (in the pipelined region several launches of the same kernel share the SMs, which stretches every
     # launch without saying anything about the kernel); the pipelined spans are reported beside them
@@ -519,7 +533,8 @@ def run_b200_arm(args):
     # the same figures for the kernel with the largest share INSIDE the timed (pipelined) region, from the spans recorded
     # there: `in_flight` batches share the SMs and HBM, so a launch is stretched by its neighbours -- the fraction says
     # how much of the device's bandwidth one launch uses while it runs, not how good the kernel is
-    tr_alg = dict(alg_by_kernel, gru_recurrence=gru_share(kernel_ms, 'gru_recurrence'), gru_fused=gru_share(kernel_ms, 'gru_fused'))
+    tr_alg = dict(alg_by_kernel, gru_recurrence=gru_share(kernel_ms, 'gru_recurrence'), gru_fused=gru_share(kernel_ms, 'gru_fused'),
+                  gru_seq=gru_share(kernel_ms, 'gru_seq'))
     tr_dom = max(kernel_ms, key=lambda k: kernel_ms[k][0])
     tr_ms, tr_calls = kernel_ms[tr_dom]
     tr_bytes = tr_alg.get(tr_dom, 0.0) * samples_per_step * args.steps / tr_calls
@@ -538,7 +553,7 @@ def run_b200_arm(args):
         # the recurrence is bound by the latency of its dependent steps, not by HBM: say so on the line
         rec_ms, rec_calls = kernel_ms_single['gru_recurrence']
         steps_per_launch = T // stride_of(net)
-        pipe_name = 'gru_fused' if 'gru_fused' in kernel_ms else 'gru_recurrence'
+        pipe_name = 'gru_seq' if 'gru_seq' in kernel_ms else ('gru_fused' if 'gru_fused' in kernel_ms else 'gru_recurrence')
         roofline["latency"] = {"kernel": "gru_recurrence", "us_per_time_step_one_batch": 1e3 * rec_ms / rec_calls / steps_per_launch,
                                "pipelined_kernel": pipe_name,
                                "us_per_time_step_pipelined": 1e3 * kernel_ms[pipe_name][0] / kernel_ms[pipe_name][1] / steps_per_launch,

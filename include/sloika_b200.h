@@ -165,6 +165,31 @@ int sloika_gru_fwd_gated(const float *x, long ldx, const float *iW, const float 
                          const int32_t *lengths, int T, int B, int I, int H, int reverse, int act, int gate_act,
                          long seqs_in_flight, const float *absmax, float limit, void *stream);
 
+/*
+ * The same layer, throughput form with the SEQUENCES on the tensor-memory lanes (csrc/gru_seq.cu): one CTA per 128
+ * sequences, activations (x_t, h, r*h) as tensor-memory operands, all three weight matrices resident in shared memory, the
+ * projection accumulated in place by MMAs issued a step ahead -- one launch, no workspace, no cluster.  tanh / sigmoid,
+ * H <= 96, I <= 96, x rows 16-byte aligned, |x| inside the fp16 range; SLOIKA_ERR_UNSUPPORTED otherwise.  It uses
+ * ceil(B / 128) SMs: meant for callers that keep several batches in flight.
+ * layout bit 0: x is in the BLOCKED layout, bit 1: y is written in it -- element (t, b, f) at
+ * (((t * ceil(B / 128) + b / 128) * ceil(F / 4) + f / 4) * 128 + b % 128) * 4 + f % 4, padding features zero, 16-byte aligned
+ * (ldx / ldy are ignored for a blocked tensor): the layout in which a warp's 128-bit accesses are contiguous when its lanes
+ * are sequences.  sloika_blocked_bytes gives the size of such a tensor, sloika_block_layout_fwd converts (to_blocked = 1:
+ * row-major src with row pitch ld -> blocked dst; 0: blocked src -> row-major dst with row pitch ld).
+ * sloika_gru_seq_fwd_gated is the layer for a ROW-MAJOR input whose range only the device knows (absmax / limit as in
+ * sloika_gru_fwd_gated) with the output in the blocked layout yb either way: below the limit x -> xb (blocked scratch) and
+ * this kernel, otherwise tf32 projection into vI, recurrence into the row-major scratch y, y -> yb.
+ */
+size_t sloika_blocked_bytes(int T, int B, int F);
+int sloika_block_layout_fwd(const float *src, float *dst, long ld, int T, int B, int F, int to_blocked, void *stream);
+int sloika_gru_seq_fwd_gated(const float *x, long ldx, const float *iW, const float *sW, const float *sW2,
+                             const float *b, float *yb, float *xb, float *y, long ldy, float *vI, long ldv,
+                             const int32_t *lengths, int T, int B, int I, int H, int reverse, int act, int gate_act,
+                             long seqs_in_flight, const float *absmax, float limit, void *stream);
+int sloika_gru_seq_fwd(const float *x, long ldx, const float *iW, const float *sW, const float *sW2,
+                       const float *b, float *y, long ldy, const int32_t *lengths, int T, int B, int I, int H,
+                       int reverse, int act, int gate_act, int layout, void *stream);
+
 /* The recurrence alone, given vI: T*B rows of 3H floats with row pitch ld_vi >= 3H (what sloika_gru_fwd runs
  * after the projection; a pitch that is a multiple of 4 floats keeps every row 16-byte aligned for odd H). */
 int sloika_gru_recurrence_fwd(const float *vI, long ld_vi, const float *sW, const float *sW2, float *y, long ldy,

@@ -7,6 +7,14 @@ in `sys.modules` for unmodified model scripts and pickles.
 """
 __version__ = '0.1.0'
 
+import os as _os
+
+# The throughput path keeps up to 16 batches in flight, each on its own CUDA stream.  The driver maps streams onto
+# CUDA_DEVICE_MAX_CONNECTIONS hardware queues (default 8): streams that share a queue serialise each other's kernels
+# (measured: 12 batches in flight 4.9 ms per batch with 8 queues, 4.2 ms with 32).  Read when the CUDA context is
+# created, so it has to be in the environment before the first CUDA call of the process.
+_os.environ.setdefault('CUDA_DEVICE_MAX_CONNECTIONS', '32')
+
 
 def install_as_sloika():
     """Alias this package as `sloika` so `models/*.py` (`import sloika.module_tools as smt`) run as is."""

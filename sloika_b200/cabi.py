@@ -45,6 +45,11 @@ EXPORTS = {
     'sloika_gru_fused_fwd': (_i, [_p, _l, _p, _p, _p, _p, _p, _l, _p, _z, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     'sloika_gru_fwd_gated': (_i, [_p, _l, _p, _p, _p, _p, _p, _l, _p, _l, _p, _z, _p, _i, _i, _i, _i, _i, _i, _i, _l, _p,
                                   ctypes.c_float, _p]),
+    'sloika_blocked_bytes': (_z, [_i, _i, _i]),
+    'sloika_block_layout_fwd': (_i, [_p, _p, _l, _i, _i, _i, _i, _p]),
+    'sloika_gru_seq_fwd_gated': (_i, [_p, _l, _p, _p, _p, _p, _p, _p, _p, _l, _p, _l, _p, _i, _i, _i, _i, _i, _i, _i, _l, _p,
+                                      ctypes.c_float, _p]),
+    'sloika_gru_seq_fwd': (_i, [_p, _l, _p, _p, _p, _p, _p, _l, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     'sloika_gru_recurrence_fwd_ex': (_i, [_p, _l, _p, _p, _p, _l, _p, _i, _i, _i, _i, _i, _i, _l, _p]),
     'sloika_viterbi_workspace_bytes': (_z, [_i, _i, _i, _i]),
     'sloika_viterbi_fwd': (_i, [_p, _l, _l, _p, _i, _i, _i, _i, _d, _d, _i, _p, _z, _p, _p, _p, _p]),

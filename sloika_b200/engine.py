@@ -29,6 +29,14 @@ class Act(object):
     """
 
     def __init__(self, data, lengths=None, reverse=False, bounded=False, absmax=None):
+        self._blocked = None
+        self._set_data(data)
+        self.lengths = lengths
+        self.reverse = reverse
+        self.bounded = bounded
+        self.absmax = absmax
+
+    def _set_data(self, data):
         assert data.dim() == 3
         T, B, F = data.shape
         # strides of size-1 dimensions are meaningless in torch; derive the row distance from a
@@ -41,35 +49,62 @@ class Act(object):
         else:
             ld = F
         assert (F == 1 or data.stride(2) == 1) and ld >= F, "feature axis must be contiguous"
-        self.data = data
+        self._data = data
         self._ld = ld
-        self.lengths = lengths
-        self.reverse = reverse
-        self.bounded = bounded
-        self.absmax = absmax
+        self._shape = (T, B, F)
+
+    @classmethod
+    def from_blocked(cls, blocked, shape, lengths=None, reverse=False, bounded=False):
+        """An activation that so far exists only in the BLOCKED layout of the sequences-on-lanes GRU kernel
+        (include/sloika_b200.h, `sloika_gru_seq_fwd`): the next such layer reads it as it is, anybody else asks for
+        `.data` and gets a row-major copy made on the spot (`sloika_block_layout_fwd`)."""
+        self = cls.__new__(cls)
+        self._blocked, self._data, self._ld, self._shape = blocked, None, None, tuple(int(v) for v in shape)
+        self.lengths, self.reverse, self.bounded, self.absmax = lengths, reverse, bounded, None
+        return self
+
+    @property
+    def blocked(self):
+        return self._blocked
+
+    @property
+    def data(self):
+        if self._data is None:
+            T, B, F = self._shape
+            y = _padded_rows(T, B, F, self._blocked.device)
+            launch('block_layout', 1, cabi.load().sloika_block_layout_fwd, cabi.ptr(self._blocked), cabi.ptr(y),
+                   _row_stride(y), T, B, F, 0, cabi.stream_ptr(y.device))
+            self._set_data(y)
+        return self._data
 
     @property
     def T(self):
-        return self.data.shape[0]
+        return self._shape[0]
 
     @property
     def B(self):
-        return self.data.shape[1]
+        return self._shape[1]
 
     @property
     def F(self):
-        return self.data.shape[2]
+        return self._shape[2]
 
     @property
     def ld(self):
+        if self._data is None:
+            self.data
         return self._ld
 
     @property
     def device(self):
-        return self.data.device
+        return self._blocked.device if self._data is None else self._data.device
 
     def flipped(self):
-        return Act(self.data, self.lengths, not self.reverse, self.bounded, self.absmax)
+        if self._data is None:
+            return Act.from_blocked(self._blocked, self._shape, self.lengths, not self.reverse, self.bounded)
+        other = Act(self._data, self.lengths, not self.reverse, self.bounded, self.absmax)
+        other._blocked = self._blocked
+        return other
 
     def like(self, data, lengths='same', bounded=False, absmax=None):
         return Act(data, self.lengths if lengths == 'same' else lengths, self.reverse, bounded, absmax)
@@ -113,7 +148,12 @@ def set_batches_in_flight(k, gemm_sms=None):
     BATCHES_IN_FLIGHT = k
     if gemm_sms is None:
         env = os.environ.get('SLOIKA_B200_GEMM_SMS')
-        gemm_sms = int(env) if env else (0 if k == 1 else max(37, 148 - 32 * (k - 1)))
+        if env:
+            gemm_sms = int(env)
+        elif k >= SEQ_MIN_IN_FLIGHT:
+            gemm_sms = 92            # the GRU layers run 128 sequences per CTA (8 SMs per 1024-sequence batch): most SMs stay free
+        else:
+            gemm_sms = 0 if k == 1 else max(37, 148 - 32 * (k - 1))
     cabi.check(cabi.load().sloika_b200_set_gemm_sm_budget(int(gemm_sms)), 'set_gemm_sm_budget')
     return k
 
@@ -311,24 +351,77 @@ def _fused_gru_ok(layer, act):
     if env == '0':
         return None
     busy = act.B * max(1, BATCHES_IN_FLIGHT) * _CONCURRENT_BRANCHES > 16 * 148
-    shape_ok = (busy or env not in ('', '0')) and layer.size <= 96 and layer.insize <= 96 and act.ld % 4 == 0 \
-        and act.data.data_ptr() % 16 == 0 and code_of(layer.fun) == 1 and code_of(layer.gatefun) == 2 \
-        and layer.iW.absmax() < _F16_WEIGHT_LIMIT
+    aligned = act.blocked is not None or (act.ld % 4 == 0 and act.data.data_ptr() % 16 == 0)
+    shape_ok = (busy or env not in ('', '0')) and layer.size <= 96 and layer.insize <= 96 and aligned \
+        and code_of(layer.fun) == 1 and code_of(layer.gatefun) == 2 and layer.iW.absmax() < _F16_WEIGHT_LIMIT
     if not shape_ok:
         return None
+    # with many batches in flight the sequences-on-lanes launch (csrc/gru_seq.cu: 128 sequences per CTA, ~60 % of the SM
+    # time per sequence, but 3.5 x the latency per layer) is the better form; SLOIKA_B200_GRU_SEQ=1 / 0 forces / forbids it
+    seq_env = os.environ.get('SLOIKA_B200_GRU_SEQ', '')
+    seq = seq_env == '1' or (seq_env != '0' and max(1, BATCHES_IN_FLIGHT) * _CONCURRENT_BRANCHES >= SEQ_MIN_IN_FLIGHT)
     if act.bounded:
-        return 'fused'
+        return 'seq' if seq else 'fused'
     if act.absmax is not None and act.T * act.B >= 128 and not os.environ.get('SLOIKA_B200_NO_F16'):
-        return 'gated'
+        return 'seq_gated' if seq else 'gated'
     return None
+
+
+SEQ_MIN_IN_FLIGHT = 6
+
+
+def _blocked_empty(T, B, F, dev):
+    import torch
+    n = cabi.load().sloika_blocked_bytes(T, B, F) // 4
+    return torch.empty(max(n, 1), dtype=torch.float32, device=dev)
+
+
+def _run_gru_seq(layer, act, form, out):
+    """The layer as the sequences-on-lanes launch: blocked activations in and out (`Act.from_blocked`)."""
+    import torch
+    lib = cabi.load()
+    dev = act.device
+    T, B, I, H = act.T, act.B, layer.insize, layer.size
+    yb = _blocked_empty(T, B, H, dev)
+    stream = torch.cuda.current_stream(dev)
+    common = (cabi.ptr(layer.iW.device(dev)), cabi.ptr(layer.sW.device(dev)), cabi.ptr(layer.sW2.device(dev)),
+              cabi.ptr(layer.b.device(dev)))
+    if form == 'seq_gated':
+        xb = _blocked_empty(T, B, I, dev)
+        y = _padded_rows(T, B, H, dev)                       # written only if the input leaves the fp16 range
+        vI = _padded_rows(T, B, 3 * H, dev)
+        launch('gru_seq', 5, lib.sloika_gru_seq_fwd_gated, cabi.ptr(act.data), act.ld, *common, cabi.ptr(yb), cabi.ptr(xb),
+               cabi.ptr(y), _row_stride(y), cabi.ptr(vI), _row_stride(vI), cabi.ptr(act.lengths), T, B, I, H,
+               1 if act.reverse else 0, code_of(layer.fun), code_of(layer.gatefun),
+               B * max(1, BATCHES_IN_FLIGHT) * _CONCURRENT_BRANCHES, cabi.ptr(act.absmax), _F16_INPUT_LIMIT, cabi.stream_ptr(dev))
+        for t in (xb, y, vI):
+            t.record_stream(stream)
+    else:
+        xb = act.blocked
+        if xb is None:
+            xb = _blocked_empty(T, B, I, dev)
+            launch('block_layout', 1, lib.sloika_block_layout_fwd, cabi.ptr(act.data), cabi.ptr(xb), act.ld, T, B, I, 1,
+                   cabi.stream_ptr(dev))
+            xb.record_stream(stream)
+        launch('gru_seq', 1, lib.sloika_gru_seq_fwd, cabi.ptr(xb), 0, *common, cabi.ptr(yb), 0, cabi.ptr(act.lengths), T, B, I, H,
+               1 if act.reverse else 0, code_of(layer.fun), code_of(layer.gatefun), 3, cabi.stream_ptr(dev))
+    res = Act.from_blocked(yb, (T, B, H), act.lengths, act.reverse, bounded=True)
+    if out is not None:                                      # a Parallel branch: its column slice of the shared buffer
+        launch('block_layout', 1, lib.sloika_block_layout_fwd, cabi.ptr(yb), cabi.ptr(out), _row_stride(out), T, B, H, 0,
+               cabi.stream_ptr(dev))
+        yb.record_stream(stream)
+        return act.like(out, bounded=True)
+    return res
 
 
 def run_gru(layer, act, out=None):
     lib = cabi.load()
     assert act.F == layer.insize
+    form = _fused_gru_ok(layer, act)
+    if form in ('seq', 'seq_gated'):
+        return _run_gru_seq(layer, act, form, out)
     y = _out_buffer(act, act.T, layer.size, out)
     dev = act.device
-    form = _fused_gru_ok(layer, act)
     if form == 'gated':
         import torch
         nbytes = lib.sloika_gru_fused_workspace_bytes(act.B, layer.size)

@@ -760,3 +760,113 @@ def test_gru_gated_between_fused_and_projection(scale, reverse, monkeypatch):
         other = engine.Act(xd, None, bounded=False, absmax=torch.tensor([1.0e9], dtype=torch.float32, device=DEV))
         got2 = layer.run(other).data.cpu().numpy()
         assert np.abs(got2 - ref).max() < 5e-5
+
+
+def _to_blocked(x):
+    """NumPy restatement of the blocked layout of include/sloika_b200.h (sloika_gru_seq_fwd)."""
+    T, B, F = x.shape
+    nblk, fg = (B + 127) // 128, (F + 3) // 4
+    out = np.zeros((T, nblk, fg, 128, 4), dtype=np.float32)
+    pad = np.zeros((T, nblk * 128, fg * 4), dtype=np.float32)
+    pad[:, :B, :F] = x
+    out[:] = pad.reshape(T, nblk, 128, fg, 4).transpose(0, 1, 3, 2, 4)
+    return out.reshape(-1)
+
+
+def _from_blocked(flat, T, B, F):
+    nblk, fg = (B + 127) // 128, (F + 3) // 4
+    v = flat.reshape(T, nblk, fg, 128, 4).transpose(0, 1, 3, 2, 4).reshape(T, nblk * 128, fg * 4)
+    return v[:, :B, :F]
+
+
+@pytest.mark.parametrize('T,B,F', [(5, 300, 96), (3, 128, 50), (4, 7, 1), (2, 129, 110)])
+def test_block_layout_round_trip(T, B, F):
+    lib = cabi.load()
+    rng = np.random.default_rng(T * B + F)
+    x = rng.standard_normal((T, B, F)).astype(np.float32)
+    pitch = (F + 7) // 8 * 8
+    xd = torch.zeros((T, B, pitch), dtype=torch.float32, device=DEV)
+    xd[:, :, :F] = torch.from_numpy(x).to(DEV)
+    n = lib.sloika_blocked_bytes(T, B, F) // 4
+    bd = torch.full((n,), 9.0, dtype=torch.float32, device=DEV)
+    assert lib.sloika_block_layout_fwd(cabi.ptr(xd), cabi.ptr(bd), pitch, T, B, F, 1, cabi.stream_ptr(DEV)) == 0
+    assert np.array_equal(bd.cpu().numpy(), _to_blocked(x))
+    yd = torch.full((T, B, F), -3.0, dtype=torch.float32, device=DEV)          # dense rows: the unaligned store path for odd F
+    assert lib.sloika_block_layout_fwd(cabi.ptr(bd), cabi.ptr(yd), F, T, B, F, 0, cabi.stream_ptr(DEV)) == 0
+    assert np.array_equal(yd.cpu().numpy(), x)
+
+
+@pytest.mark.parametrize('layout', [0, 3])
+@pytest.mark.parametrize('I,H,T,B,reverse,ragged', [(96, 96, 40, 130, False, False), (96, 96, 33, 128, True, True),
+                                                    (32, 96, 20, 5, False, True), (64, 64, 25, 200, True, False),
+                                                    (96, 80, 20, 33, False, True), (40, 50, 20, 17, True, True),
+                                                    (20, 32, 15, 300, False, False), (96, 96, 1, 3, False, False)])
+def test_gru_sequences_on_lanes(I, H, T, B, reverse, ragged, layout):
+    """The GRU layer with 128 sequences on the tensor-memory lanes (csrc/gru_seq.cu: activations as TMEM operands,
+    weights in shared memory, projection accumulated in place) through the C ABI against the oracle, with row-major and
+    with blocked tensors; batches that do not fill a CTA, ragged and reversed included."""
+    np.random.seed(I + H + B + 1)
+    g = layers.Gru(I, H, init=_init(), has_bias=True)
+    g.sW.set_value(g.sW.get_value() * 5)
+    g.sW2.set_value(g.sW2.get_value() * 5)
+    layer = layers.Reverse(g) if reverse else g
+    lengths = [int(v) for v in np.random.randint(1, T + 1, size=B)] if ragged else None
+    if lengths:
+        lengths[0] = T
+    x = np.tanh(np.random.standard_normal((T, B, I))).astype(np.float32)
+    lib = cabi.load()
+    pitch = (I + 3) // 4 * 4
+    if layout & 1:
+        xd = torch.from_numpy(_to_blocked(x)).to(DEV)
+    else:
+        xd = torch.zeros((T, B, pitch), dtype=torch.float32, device=DEV)
+        xd[:, :, :I] = torch.from_numpy(x).to(DEV)
+    if layout & 2:
+        yd = torch.full((lib.sloika_blocked_bytes(T, B, H) // 4,), 7.0, dtype=torch.float32, device=DEV)
+    else:
+        yd = torch.full((T, B, H), 7.0, dtype=torch.float32, device=DEV)
+    ld = None if lengths is None else torch.as_tensor(lengths, dtype=torch.int32, device=DEV)
+    rc = lib.sloika_gru_seq_fwd(cabi.ptr(xd), pitch, cabi.ptr(g.iW.device(DEV)), cabi.ptr(g.sW.device(DEV)),
+                                cabi.ptr(g.sW2.device(DEV)), cabi.ptr(g.b.device(DEV)), cabi.ptr(yd), H, cabi.ptr(ld),
+                                T, B, I, H, 1 if reverse else 0, 1, 2, layout, cabi.stream_ptr(DEV))
+    assert rc == 0
+    torch.cuda.synchronize()
+    got = _from_blocked(yd.cpu().numpy(), T, B, H) if layout & 2 else yd.cpu().numpy()
+    for b in list(range(0, B, 7)) + [B - 1]:
+        n = T if lengths is None else lengths[b]
+        ref = _oracle(layer, x[:n, b:b + 1])
+        assert np.abs(got[:n, b] - ref[:, 0]).max() < 5e-5, b
+        assert np.all(got[n:, b] == 0)
+
+
+@pytest.mark.parametrize('scale', [1.0, 3.0e4])
+def test_network_through_sequences_on_lanes(scale, monkeypatch):
+    """A conv -> Reverse(Gru) -> Gru -> Gru stack with the GRU layers forced onto the sequences-on-lanes launch: the first
+    one takes the convolution's row-major output through the gated entry (either verdict), the others pass blocked
+    activations to each other, the caller reads a row-major result; ragged batch."""
+    monkeypatch.setenv('SLOIKA_B200_FUSED_GRU', '1')
+    monkeypatch.setenv('SLOIKA_B200_GRU_SEQ', '1')
+    np.random.seed(5)
+    net = layers.Serial([layers.Convolution(1, 96, 11, 5, init=_init(), has_bias=True, fun=act.elu),
+                         layers.Reverse(layers.Gru(96, 96, init=_init(), has_bias=True)),
+                         layers.Gru(96, 64, init=_init(), has_bias=True),
+                         layers.Reverse(layers.Gru(64, 80, init=_init(), has_bias=True))])
+    if scale > 1:
+        W = net.layers[0].W.get_value()
+        net.layers[0].W.set_value(W * scale)
+        net.layers[1].layer.iW.set_value(net.layers[1].layer.iW.get_value() / scale * 4)
+    T, B = 400, 150
+    x = np.random.standard_normal((T, B, 1)).astype(np.float32)
+    lengths = np.random.randint(50, T + 1, size=B).astype(np.int32)
+    lengths[0] = T
+    engine.TIMER.reset()
+    out = net.run(engine.Act(torch.from_numpy(x).to(DEV), torch.from_numpy(lengths).to(DEV)))
+    assert out.blocked is not None
+    got = out.data.cpu().numpy()
+    olen = out.lengths.cpu().numpy()
+    for b in (0, 1, 77, B - 1):
+        ref = _oracle(net, x[:lengths[b], b:b + 1])
+        assert ref.shape[0] == olen[b]
+        assert np.abs(got[:olen[b], b] - ref[:, 0]).max() < (5e-5 if scale == 1.0 else 3e-4), b
+        assert np.all(got[olen[b]:, b] == 0)
+

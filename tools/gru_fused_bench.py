@@ -3,6 +3,7 @@ batch and with K batches on K streams.  Env: T, B, H, I, K."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
+LAYOUT = int(os.environ.get('LAYOUT', '0'))   # sloika_gru_seq_fwd: bit 0 x blocked, bit 1 y blocked (timing only here)
 from sloika_b200 import cabi
 lib = cabi.load()
 dev = torch.device('cuda:0')
@@ -34,6 +35,12 @@ def fused(i, st, hint):
     assert rc == 0, rc
 
 
+def seq(i, st, hint):
+    rc = lib.sloika_gru_seq_fwd(cabi.ptr(xs[i]), I, cabi.ptr(iW), cabi.ptr(sW), cabi.ptr(sW2), cabi.ptr(b), cabi.ptr(ys[i]), H,
+                                None, T, B, I, H, 0, 1, 2, LAYOUT, st)
+    assert rc == 0, rc
+
+
 def timeit(fn, k, reps=3):
     for _ in range(2):
         for i in range(k):
@@ -56,9 +63,13 @@ def timeit(fn, k, reps=3):
 
 
 for k in (1, K):
-    u, f = timeit(unfused, k), timeit(fused, k)
-    print("T=%d B=%d H=%d I=%d  %d batch(es) in flight: projection+recurrence %.3f ms, fused %.3f ms (per round of %d)" % (T, B, H, I, k, u, f, k))
+    u, f, q = timeit(unfused, k), timeit(fused, k), timeit(seq, k)
+    print("T=%d B=%d H=%d I=%d  %d batch(es) in flight: projection+recurrence %.3f ms, fused %.3f ms, sequences-on-lanes %.3f ms (per round of %d)" % (T, B, H, I, k, u, f, q, k))
 unfused(0, streams[0].cuda_stream, B); fused(1, streams[1].cuda_stream, B)
 torch.cuda.synchronize()
 xs[1].copy_(xs[0]); fused(1, streams[1].cuda_stream, B); torch.cuda.synchronize()
 print("max |fused - unfused| = %.3g" % (ys[0] - ys[1]).abs().max().item())
+seq(2 % K, streams[0].cuda_stream, B) if K > 2 else None
+if K > 2:
+    xs[2].copy_(xs[0]); seq(2, streams[2].cuda_stream, B); torch.cuda.synchronize()
+    print("max |sequences-on-lanes - unfused| = %.3g" % (ys[0] - ys[2]).abs().max().item())
