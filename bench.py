@@ -518,7 +518,7 @@ def run_b200_arm(args):
     traffic_table = {}
     try:
         if args.workload == 'raw_rgrgr' and B == BATCH_PER_GPU and T == CHUNK_LEN:
-            with open(os.path.join(ROOT, 'profiles', 'r2f_traffic.json')) as fh:
+            with open(os.path.join(ROOT, 'profiles', 'r2g_traffic.json')) as fh:
                 traffic_table = json.load(fh)
     except Exception:
         traffic_table = {}
@@ -558,7 +558,7 @@ def run_b200_arm(args):
                                "pipelined_kernel": pipe_name,
                                "us_per_time_step_pipelined": 1e3 * kernel_ms[pipe_name][0] / kernel_ms[pipe_name][1] / steps_per_launch,
                                "time_steps_per_launch": steps_per_launch,
-                               "ncu": "profiles/r2f_step_kernels_ncu.txt (warps active, issue active, tensor pipe)"}
+                               "ncu": "profiles/r2g_step_kernels_ncu.txt (warps active, issue active, tensor pipe)"}
     total_alg = sum(alg.values())
     paper = min(hbm_peak * 1e9 / total_alg, float(peaks.get('bf16_tflops_sustained', 1400.0)) * 1e12 / flops_per_sample(net))
 

@@ -17,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, 'tools'))
 import ncu_summary          # noqa: E402
 
-CLASSES = [('gru_fused_kernel', 'gru_fused'), ('gru_tc_kernel', 'gru_recurrence'), ('gru_h16_kernel', 'gru_recurrence'), ('viterbi', 'viterbi'),
+CLASSES = [('gru_seq_kernel', 'gru_seq'), ('block_layout', 'block_layout'), ('gru_fused_kernel', 'gru_fused'), ('gru_tc_kernel', 'gru_recurrence'), ('gru_h16_kernel', 'gru_recurrence'), ('viterbi', 'viterbi'),
            ('conv1d', 'conv1d')]
 
 
@@ -41,7 +41,9 @@ def main():
                  "# `python bench.py` (raw_rgrgr, 1024 chunks x 4000 samples), kernels serialised by the profiler.\n"
                  "# gru_if1 = recurrence as launched with one batch in flight (G = 1 group of 8 sequences per CTA, 128 CTAs),\n"
                  "# gru_if4 = first GRU layer with four batches in flight (G = 2 groups of 16 sequences per CTA, 32 CTAs per batch),\n"
-                 "# gru_fused = layers 2-5 with four batches in flight: projection inside the launch (3-CTA clusters, 48 CTAs).\n")
+                 "# gru_fused = layers 2-5 with four batches in flight: projection inside the launch (3-CTA clusters, 48 CTAs),\n"
+                 "# gru_seq = the layers with >= 6 batches in flight: 128 sequences on the TMEM lanes (8 CTAs per batch), layout = the\n"
+                 "# row-major <-> blocked conversions around them.\n")
         for path in reps:
             fh.write("# {}\n".format(os.path.basename(path)))
             for d, u in ncu_summary.rows_of(path):
