@@ -20,11 +20,11 @@
 //
 // Warps: 16 compute warps (warp w: lanes 32 (w & 3).., units HP/4 (w >> 2)..; a thread owns one sequence x HP/4 units,
 // its h values live in registers) + one issuing warp.  Per step t:
-//   compute  wait d1 (r, z complete) -> r = sigmoid -> r*h -> operand (tcgen05.st) -> arrive RH
-//            wait dx (projection of step t has read the x operand) -> x_{t+1} (loaded a step ago) -> operand;
-//            load x_{t+2};  z -> denominators;  arrive ZFREE (z | r accumulators and the x operand are handed over)
+//   compute  wait d1 (r complete) -> r = sigmoid -> r*h -> operand (tcgen05.st) -> arrive RH;  load x_{t+1} (in L2 since t - 2)
+//            wait d1z -> z raw;  wait dx (projection of step t has read the x operand) -> x_{t+1} -> operand;
+//            arrive ZFREE (z | r accumulators and the x operand are handed over);  prefetch x_{t+3};  z -> denominators
 //            wait d2 (candidate complete) -> blend -> h_t -> operand, arrive H;  h_t -> HBM
-//   issuer   sync H: z | r += sW . h_{t-1}, commit d1;  c = iW_c . x_t (accumulate = 0), commit dx
+//   issuer   sync H: r += sW_r . h_{t-1}, commit d1;  z += sW_z . h_{t-1}, commit d1z;  c = iW_c . x_t (accumulate = 0), commit dx
 //            sync RH: c += sW2 . (r*h), commit d2
 //            sync ZFREE: z | r = iW_zr . x_{t+1} (accumulate = 0)      -- off the dependent chain
 #include <cstdio>
@@ -53,7 +53,7 @@ constexpr int CW = 16;                // compute warps
 constexpr int NTHREADS = (CW + 1) * 32;
 
 struct SBars {
-    uint64_t d1, dx, d2;
+    uint64_t d1, dx, d2, d1z;
     uint32_t tmem_base;
     uint32_t pad;
 };
@@ -109,7 +109,7 @@ gru_seq_kernel(const float *__restrict__ x, long ldx, const float *__restrict__ 
 
     // ---------------- prologue ----------------
     if (tid == 0) {
-        mbar_init(&bars->d1, 1); mbar_init(&bars->dx, 1); mbar_init(&bars->d2, 1);
+        mbar_init(&bars->d1, 1); mbar_init(&bars->dx, 1); mbar_init(&bars->d2, 1); mbar_init(&bars->d1z, 1);
         mbar_fence_init();
     }
     if (warp == CW) tmem_alloc(&bars->tmem_base, 512);
@@ -257,8 +257,9 @@ gru_seq_kernel(const float *__restrict__ x, long ldx, const float *__restrict__ 
             wait_bar(&bars->d1, par);
             if (tid == 0) STRACE(0);
             tc_fence_after();
+            uint32_t rhi[UPT / 2], rlo[UPT / 2];          // r*h as packed fp16 hi / lo pairs
 #pragma unroll
-            for (int c = 0; c < NCH; c++) {               // phase 1 has completed: the h operand is free, chunk by chunk
+            for (int c = 0; c < NCH; c++) {
                 uint32_t d[8];
                 tmem_ld_32x32b_x8(lane_addr + (uint32_t)(D_R + u0 + 8 * c), d);
                 tmem_ld_wait();
@@ -268,7 +269,19 @@ gru_seq_kernel(const float *__restrict__ x, long ldx, const float *__restrict__ 
                 float rh[8];
 #pragma unroll
                 for (int i = 0; i < 8; i++) rh[i] = sigmoid_pre(__uint_as_float(d[i]) + bb[i]) * h[8 * c + i];
-                store_operand8(lane_addr + (uint32_t)(A_H_HI + (u0 + 8 * c) / 2), lane_addr + (uint32_t)(A_H_LO + (u0 + 8 * c) / 2), rh);
+#pragma unroll
+                for (int i = 0; i < 4; i++) split_pair(rh[2 * i], rh[2 * i + 1], rhi[4 * c + i], rlo[4 * c + i]);
+            }
+            // r*h takes the place of h in tensor memory, and the z MMAs (issued behind the r MMAs) still read h: they have
+            // completed by now (they run while the r gate is being computed), the wait makes it certain
+            wait_bar(&bars->d1z, par);
+            tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < NCH; c++) {
+                const uint32_t hi4[4] = {rhi[4 * c], rhi[4 * c + 1], rhi[4 * c + 2], rhi[4 * c + 3]};
+                const uint32_t lo4[4] = {rlo[4 * c], rlo[4 * c + 1], rlo[4 * c + 2], rlo[4 * c + 3]};
+                tmem_st_32x32b_x4(lane_addr + (uint32_t)(A_H_HI + (u0 + 8 * c) / 2), hi4);
+                tmem_st_32x32b_x4(lane_addr + (uint32_t)(A_H_LO + (u0 + 8 * c) / 2), lo4);
             }
             tmem_st_wait();
             tc_fence_before();
@@ -382,8 +395,11 @@ gru_seq_kernel(const float *__restrict__ x, long ldx, const float *__restrict__ 
             tc_fence_after();
             if (elect_one()) {
                 if (s == 0) mma_set(d_zr, a_xh, a_xl, s_iw_hi, s_iw_lo, 3 * HP, 0, KBI, id_zr, false);   // z | r = iW_zr . x_0
-                mma_set(d_zr, a_hh, a_hl, s_swzr_hi, s_swzr_lo, 2 * HP, 0, KBH, id_zr, true);             // z | r += sW . h
+                // r first and on its own: the dependent chain (r -> r*h -> candidate) waits for it, z is needed later
+                mma_set(d_zr + HP, a_hh, a_hl, s_swzr_hi, s_swzr_lo, 2 * HP, HP, KBH, id_c, true);        // r += sW_r . h
                 umma_commit(&bars->d1);
+                mma_set(d_zr, a_hh, a_hl, s_swzr_hi, s_swzr_lo, 2 * HP, 0, KBH, id_c, true);              // z += sW_z . h
+                umma_commit(&bars->d1z);
                 mma_set(d_c, a_xh, a_xl, s_iw_hi, s_iw_lo, 3 * HP, 2 * HP, KBI, id_c, false);              // c = iW_c . x_s
                 umma_commit(&bars->dx);
                 STRACE(9);
