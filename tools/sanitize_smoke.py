@@ -49,6 +49,18 @@ def main():
         xf = torch.tanh(torch.randn((50, B, I), device=DEV))
         engine.run_gru(gf, engine.Act(xf, None, bounded=True))
         engine.run_gru(gf, engine.Act(xf, torch.randint(1, 51, (B,), dtype=torch.int32, device=DEV), reverse=True, bounded=True))
+    # the sequences-on-lanes launch (csrc/gru_seq.cu) with its layout conversions: a conv -> GRU x 3 stack (gated first layer,
+    # blocked activations between the layers), partial last block of 128, ragged, reversed
+    os.environ['SLOIKA_B200_GRU_SEQ'] = '1'
+    init = smt.partial(smt.truncated_normal, sd=0.5)
+    seq_net = layers.Serial([layers.Convolution(1, 96, 11, 5, init=init, has_bias=True, fun=smt.elu),
+                             layers.Reverse(layers.Gru(96, 96, init=init, has_bias=True)),
+                             layers.Gru(96, 50, init=init, has_bias=True),
+                             layers.Reverse(layers.Gru(50, 80, init=init, has_bias=True))])
+    xs = torch.randn((300, 150, 1), device=DEV)
+    seq_net.run(engine.Act(xs, torch.randint(20, 301, (150,), dtype=torch.int32, device=DEV))).data
+    seq_net.run(engine.Act(xs * 3.0e4, None)).data                      # outside the fp16 range: the other verdict of the gate
+    os.environ.pop('SLOIKA_B200_GRU_SEQ')
     os.environ.pop('SLOIKA_B200_FUSED_GRU')
     # 144 < H <= 256: the 4-CTA cluster kernel (distributed shared memory), ragged and reversed
     for H in (160, 256):
