@@ -268,6 +268,11 @@ int sloika_viterbi_fwd(const float *post, long ld_t, long ld_b, const int32_t *l
                        size_t ws_bytes, int32_t *path_out, int32_t *path_len, float *score_out,
                        void *stream);
 
+/* sloika_softmax_logits_fwd (fp16-split form) with x in the BLOCKED layout of sloika_gru_seq_fwd; M = T * B with B a multiple
+ * of 128 (whole blocks).  The last GRU layer's output enters the logits GEMM without a layout conversion. */
+int sloika_softmax_logits_blocked_fwd(const float *xb, const float *W, const float *bias, float *logits, long ldl,
+                                      float *stats, long M, int K, int N, int stay_last, void *stream);
+
 /*
  * Same decode fed by the un-normalised network output of sloika_softmax_logits_fwd(stay_last = 1):
  * the softmax division (layers.py:314), the min_prob floor (decode.py:36) and the log (decode.py:56) are

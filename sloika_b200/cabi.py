@@ -30,6 +30,7 @@ EXPORTS = {
     'sloika_softmax_fwd': (_i, [_p, _l, _p, _p, _p, _l, _l, _i, _i, _p]),
     'sloika_softmax_slices': (_i, [_i, _i, _i]),
     'sloika_softmax_logits_fwd': (_i, [_p, _l, _p, _p, _p, _l, _p, _l, _i, _i, _i, _i, _p]),
+    'sloika_softmax_logits_blocked_fwd': (_i, [_p, _p, _p, _p, _l, _p, _l, _i, _i, _i, _p]),
     'sloika_softmax_normalise_fwd': (_i, [_p, _l, _p, _i, _l, _i, _p]),
     'sloika_gru_workspace_bytes': (_z, [_i, _i, _i]),
     'sloika_gru_fwd': (_i, [_p, _l, _p, _p, _p, _p, _p, _l, _p, _z, _p, _i, _i, _i, _i, _i, _i, _i, _p]),

@@ -62,6 +62,7 @@ struct Params {
     const unsigned *gate;   // optional device word (bits of a non-negative float, e.g. max |x| from the producer):
     unsigned gate_limit;    // gate_mode 1: run only if *gate < gate_limit; 2: only if *gate >= gate_limit; 0: always
     int gate_mode;
+    int x_blocked;    // x is in the blocked layout of gru_seq.cu (F16 form, M a multiple of 128): a raw tile is [k / 4][128 rows][4 k]
     int dbg;          // timing experiments only (SLOIKA_B200_GEMM_DBG): 1 no split math, 2 no stores, 4 no MMA
 };
 
@@ -157,7 +158,8 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
                     const uint32_t ph = (it / STAGES) & 1;
                     tc::mbar_wait(&empty[s], ph ^ 1);
                     tc::mbar_arrive_expect_tx(&full_raw[s], A_TILE_BYTES);
-                    tc::tma_load_2d(Abase + (size_t)s * STAGE_BYTES, &tmap_x, &full_raw[s], kb * KB, (int)(mt * BM));
+                    if (p.x_blocked) tc::tma_load_4d(Abase + (size_t)s * STAGE_BYTES, &tmap_x, &full_raw[s], 0, 0, kb * (KB / 4), (int)mt);
+                    else tc::tma_load_2d(Abase + (size_t)s * STAGE_BYTES, &tmap_x, &full_raw[s], kb * KB, (int)(mt * BM));
                 }
             }
         }
@@ -241,17 +243,24 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_cons
                         continue;
                     }
                     float4 va[4], vb[4];
+                    // blocked input: the raw tile is [k / 4][128 rows][4 k] (no swizzle); thread = row tt, pair i
+                    const bool xb = p.x_blocked != 0;
 #pragma unroll
                     for (int i = 0; i < 4; i++) {
-                        const int q = tt + 128 * i, r = q >> 2, pp = q & 3;
-                        const uint32_t rb = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128);
-                        va[i] = *reinterpret_cast<const float4 *>(raw + rb + (((2 * pp) ^ (r & 7)) << 4));
-                        vb[i] = *reinterpret_cast<const float4 *>(raw + rb + (((2 * pp + 1) ^ (r & 7)) << 4));
+                        const int q = tt + 128 * i, r = xb ? tt : q >> 2, pp = xb ? i : q & 3;
+                        if (xb) {
+                            va[i] = *reinterpret_cast<const float4 *>(raw + (((2 * pp) * 128 + r) << 4));
+                            vb[i] = *reinterpret_cast<const float4 *>(raw + (((2 * pp + 1) * 128 + r) << 4));
+                        } else {
+                            const uint32_t rb = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128);
+                            va[i] = *reinterpret_cast<const float4 *>(raw + rb + (((2 * pp) ^ (r & 7)) << 4));
+                            vb[i] = *reinterpret_cast<const float4 *>(raw + rb + (((2 * pp + 1) ^ (r & 7)) << 4));
+                        }
                     }
                     asm volatile("bar.sync 3, 128;" ::: "memory");
 #pragma unroll
                     for (int i = 0; i < 4; i++) {
-                        const int q = tt + 128 * i, r = q >> 2, pp = q & 3;
+                        const int q = tt + 128 * i, r = xb ? tt : q >> 2, pp = xb ? i : q & 3;
                         const float v[8] = {va[i].x, va[i].y, va[i].z, va[i].w, vb[i].x, vb[i].y, vb[i].z, vb[i].w};
                         uint32_t hw[4], lw[4];
 #pragma unroll
@@ -500,7 +509,11 @@ int launch(const float *x, long ldx, const float *W, const float *bias, float *y
            int act, float2 *stats, int rot, bool f16, cudaStream_t st, const unsigned *gate = nullptr,
            unsigned gate_limit = 0, int gate_mode = 0)
 {
-    if ((ldx & 3) != 0 || ((uintptr_t)x & 15) != 0 || K > 512 || M < BM || M > 0x7fffffffL) return SLOIKA_ERR_UNSUPPORTED;
+    // ldx == -1: x is in the blocked layout (sloika_b200.h, sloika_gru_seq_fwd): fp16-split form only, whole blocks of 128 rows
+    const bool x_blocked = ldx == -1;
+    if (x_blocked) {
+        if (!f16 || (M % BM) != 0 || ((uintptr_t)x & 15) != 0 || K > 512 || M > 0x7fffffffL) return SLOIKA_ERR_UNSUPPORTED;
+    } else if ((ldx & 3) != 0 || ((uintptr_t)x & 15) != 0 || K > 512 || M < BM || M > 0x7fffffffL) return SLOIKA_ERR_UNSUPPORTED;
     EncodeTiledFn enc = encode_fn();
     if (!enc) return SLOIKA_ERR_UNSUPPORTED;
     int dev = 0, sms = 0;
@@ -520,7 +533,18 @@ int launch(const float *x, long ldx, const float *W, const float *bias, float *y
     const cuuint64_t gstride[1] = {(cuuint64_t)ldx * 4};
     const cuuint32_t box[2] = {(cuuint32_t)KB, (cuuint32_t)BM};
     const cuuint32_t estr[2] = {1, 1};
-    if (enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(x), gdim, gstride, box, estr,
+    if (x_blocked) {
+        // [M / 128 blocks][K / 4 groups][128 rows][4 floats]: one box = 8 groups x 128 rows x 16 bytes = a 16 KB raw tile
+        const cuuint64_t groups = (cuuint64_t)((K + 3) / 4);
+        const cuuint64_t bdim[4] = {4, 128, groups, (cuuint64_t)(M / BM)};
+        const cuuint64_t bstride[3] = {16, 128 * 16, groups * 128 * 16};
+        const cuuint32_t bbox[4] = {4, 128, (cuuint32_t)(KB / 4), 1};
+        const cuuint32_t bestr[4] = {1, 1, 1, 1};
+        if (enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float *>(x), bdim, bstride, bbox, bestr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return SLOIKA_ERR_UNSUPPORTED;
+    } else if (enc(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(x), gdim, gstride, box, estr,
             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
         return SLOIKA_ERR_UNSUPPORTED;
@@ -530,6 +554,7 @@ int launch(const float *x, long ldx, const float *W, const float *bias, float *y
     p.BN = BN; p.n_slices = n_slices; p.nkb = nkb;
     p.stats = stats; p.rot = rot;
     p.gate = gate; p.gate_limit = gate_limit; p.gate_mode = gate ? gate_mode : 0;
+    p.x_blocked = x_blocked ? 1 : 0;
     p.vec_out = ((ldy & 3) == 0) && (((uintptr_t)y & 15) == 0);
     const char *direct = getenv("SLOIKA_B200_GEMM_DIRECT");
     p.direct = (p.vec_out && direct && atoi(direct) != 0) ? 1 : 0;

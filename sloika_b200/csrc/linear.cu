@@ -257,6 +257,18 @@ extern "C" int sloika_softmax_logits_fwd(const float *x, long ldx, const float *
                            stay_last ? 1 : 0, algo == SLOIKA_GEMM_TC_F16, (cudaStream_t)stream);
 }
 
+// the same with x in the blocked layout of sloika_gru_seq_fwd (M a multiple of 128, fp16-split form): the last GRU layer's
+// output goes into the logits GEMM as it is
+extern "C" int sloika_softmax_logits_blocked_fwd(const float *xb, const float *W, const float *bias, float *logits, long ldl,
+                                                 float *stats, long M, int K, int N, int stay_last, void *stream)
+{
+    if (!xb || !W || !logits || !stats || M < 0 || K <= 0 || N <= 0 || ldl < N) return SLOIKA_ERR_ARG;
+    if (M == 0) return SLOIKA_OK;
+    if (sloika_softmax_slices(K, N, SLOIKA_GEMM_TC_F16) <= 0) return SLOIKA_ERR_UNSUPPORTED;
+    return gemm_tc::launch(xb, -1, W, bias, logits, ldl, M, K, N, SLOIKA_ACT_LINEAR, reinterpret_cast<float2 *>(stats),
+                           stay_last ? 1 : 0, true, (cudaStream_t)stream);
+}
+
 extern "C" int sloika_softmax_normalise_fwd(float *logits, long ldl, const float *stats, int n_slices, long M, int N,
                                             void *stream)
 {

@@ -301,10 +301,22 @@ def run_softmax_logits(layer, act):
     import torch
     lib = cabi.load()
     assert act.F == layer.insize
+    dev = act.device
+    if act.blocked is not None and act._data is None and act.B % 128 == 0 and act.bounded and \
+            layer.W.absmax() < _F16_WEIGHT_LIMIT and not os.environ.get('SLOIKA_B200_NO_F16') and \
+            lib.sloika_softmax_slices(layer.insize, layer.size, GEMM_TC_F16) > 0:
+        # the last GRU layer left its output in the blocked layout: the GEMM's TMA reads it as it is
+        nsl = lib.sloika_softmax_slices(layer.insize, layer.size, GEMM_TC_F16)
+        y = _padded_rows(act.T, act.B, layer.size, dev)
+        stats = torch.empty((act.T * act.B, nsl, 2), dtype=torch.float32, device=dev)
+        launch('softmax', 1, lib.sloika_softmax_logits_blocked_fwd,
+               cabi.ptr(act.blocked), cabi.ptr(layer.W.device(dev)), cabi.ptr(layer.b.device(dev)),
+               cabi.ptr(y), _row_stride(y), cabi.ptr(stats), act.T * act.B, layer.insize, layer.size, 1, cabi.stream_ptr(dev))
+        act.blocked.record_stream(torch.cuda.current_stream(dev))
+        return LogitsAct(y, stats, nsl, act.lengths)
     algo = _gemm_algo(act, layer.W)
     if not _softmax_tc_ok(lib, layer, act, algo):
         return None
-    dev = act.device
     nsl = lib.sloika_softmax_slices(layer.insize, layer.size, algo)
     y = _padded_rows(act.T, act.B, layer.size, dev)
     stats = torch.empty((act.T * act.B, nsl, 2), dtype=torch.float32, device=dev)
@@ -359,7 +371,10 @@ def _fused_gru_ok(layer, act):
     # with many batches in flight the sequences-on-lanes launch (csrc/gru_seq.cu: 128 sequences per CTA, ~60 % of the SM
     # time per sequence, but 3.5 x the latency per layer) is the better form; SLOIKA_B200_GRU_SEQ=1 / 0 forces / forbids it
     seq_env = os.environ.get('SLOIKA_B200_GRU_SEQ', '')
-    seq = seq_env == '1' or (seq_env != '0' and max(1, BATCHES_IN_FLIGHT) * _CONCURRENT_BRANCHES >= SEQ_MIN_IN_FLIGHT)
+    # (small batches -- strong scaling splits one over the GPUs -- would put a single CTA to work for 4 ms per layer: they
+    # keep the fused form)
+    seq = seq_env == '1' or (seq_env != '0' and act.B >= 512 and
+                             max(1, BATCHES_IN_FLIGHT) * _CONCURRENT_BRANCHES >= SEQ_MIN_IN_FLIGHT)
     if act.bounded:
         return 'seq' if seq else 'fused'
     if act.absmax is not None and act.T * act.B >= 128 and not os.environ.get('SLOIKA_B200_NO_F16'):

@@ -870,3 +870,38 @@ def test_network_through_sequences_on_lanes(scale, monkeypatch):
         assert np.abs(got[:olen[b], b] - ref[:, 0]).max() < (5e-5 if scale == 1.0 else 3e-4), b
         assert np.all(got[olen[b]:, b] == 0)
 
+
+def test_softmax_logits_from_blocked_input(monkeypatch):
+    """The logits GEMM fed by a blocked activation (what the last sequences-on-lanes GRU layer leaves behind) gives the
+    logits and row statistics of the row-major path, and the fused decode the same paths."""
+    monkeypatch.setenv('SLOIKA_B200_FUSED_GRU', '1')
+    monkeypatch.setenv('SLOIKA_B200_GRU_SEQ', '1')
+    np.random.seed(23)
+    T, B, K = 30, 256, 96
+    layer = layers.Softmax(K, 1025, init=_init(), has_bias=True)
+    layer.W.set_value(layer.W.get_value() * 4)
+    x = np.tanh(np.random.standard_normal((T, B, K))).astype(np.float32)
+    xb = torch.from_numpy(_to_blocked(x)).to(DEV)
+    a_blk = engine.Act.from_blocked(xb, (T, B, K), None, False, bounded=True)
+    a_row = engine.Act(torch.from_numpy(x).to(DEV), None, bounded=True)
+    l_blk = engine.run_softmax_logits(layer, a_blk)
+    assert a_blk._data is None                                   # no row-major copy was made
+    l_row = engine.run_softmax_logits(layer, a_row)
+    torch.cuda.synchronize()
+    assert torch.equal(l_blk.data, l_row.data)
+    assert torch.equal(l_blk.stats, l_row.stats)
+    # a whole network: conv -> 5 GRU (sequences on lanes) -> logits from the blocked activation -> fused decode
+    net = zoo.raw_rgrgr()
+    net.layers[-1].W.set_value(net.layers[-1].W.get_value() * 4)
+    calc = net.compile()
+    xs = torch.randn((1000, 128, 1), device=DEV)
+    engine.TIMER.reset()
+    fused = calc.forward_device(xs, None, fused_decode=True)
+    monkeypatch.setenv('SLOIKA_B200_GRU_SEQ', '0')
+    monkeypatch.setenv('SLOIKA_B200_FUSED_GRU', '0')
+    plain = calc.forward_device(xs, None, fused_decode=True)
+    s1, p1 = decode.viterbi_batch(fused, None, min_prob=1e-5)
+    s2, p2 = decode.viterbi_batch(plain, None, min_prob=1e-5)
+    assert (fused.data - plain.data).abs().max().item() < 2e-4
+    assert sum(a != b for a, b in zip(p1, p2)) <= 1            # two float32 roundings of the same network: near-ties may flip
+    np.testing.assert_allclose(s1, s2, rtol=1e-4, atol=5e-2)
