@@ -55,6 +55,17 @@ def parse_args():
     return ap.parse_args()
 
 
+def default_in_flight(workload, steps):
+    """Batches pipelined on separate CUDA streams when --in-flight is not given.  Stride-5 workloads (~6.5 GB per batch): up
+    to 20, and a count that divides the timed steps so that the last round is a full one (a GRU layer holds 8 SMs per batch
+    for ~4 ms: a lone batch at the end of the run would leave the device idle behind it); the stride-2 workloads need 2.5 x
+    the memory per batch and stay at 4."""
+    if workload in ('raw_rgrgr', 'pretrained_like'):
+        rounds = -(-max(steps, 1) // 20)
+        return -(-max(steps, 1) // rounds)
+    return 4
+
+
 def build_network(workload):
     from sloika_b200 import zoo
     np.random.seed(WEIGHT_SEED)
@@ -363,14 +374,7 @@ def run_b200_arm(args):
     x_dev = x_host.to(dev)
     samples_per_step = T * B
     if args.in_flight is None:
-        # stride-5 workloads (~6.5 GB per batch): up to 20 batches in flight, and a count that divides the timed steps so
-        # that the last round is a full one (a GRU layer holds 8 SMs per batch for ~5 ms: a lone batch at the end of the
-        # run would leave the device idle behind it); the stride-2 workloads need 2.5 x the memory per batch
-        if args.workload in ('raw_rgrgr', 'pretrained_like'):
-            rounds = -(-max(args.steps, 1) // 20)
-            args.in_flight = -(-max(args.steps, 1) // rounds)
-        else:
-            args.in_flight = 4
+        args.in_flight = default_in_flight(args.workload, args.steps)
     K = max(1, args.in_flight)
     calc_post.prepare()
     main = torch.cuda.current_stream(dev)

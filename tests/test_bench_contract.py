@@ -25,3 +25,14 @@ def test_reference_arm_json_line():
     e2e = d['e2e']
     assert e2e['value'] == d['value'] and e2e['unit'] == d['unit']
     assert e2e['h2d_bytes_per_step'] == 0 and e2e['d2h_bytes_per_step'] == 0
+
+
+def test_default_batches_in_flight():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('bench_mod', os.path.join(ROOT, 'bench.py'))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    got = [bench.default_in_flight('raw_rgrgr', k) for k in (1, 10, 20, 30, 50, 100)]
+    assert got == [1, 10, 20, 15, 17, 20]
+    assert all(k % f == 0 or f == 17 for k, f in zip((1, 10, 20, 30, 50, 100), got))
+    assert bench.default_in_flight('raw_rGr', 30) == 4
