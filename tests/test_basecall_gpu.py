@@ -308,3 +308,37 @@ def test_full_size_batch_properties():
     sd, pd_ = decode.viterbi_batch(lp, None, log=True)
     ref_s, ref_p = cbind.viterbi_batch(lp.cpu().numpy(), None)
     assert np.array_equal(sd, ref_s) and pd_ == ref_p
+
+
+@pytest.mark.parametrize('form', ['fused', 'seq'])
+def test_full_size_batch_throughput_forms(form, monkeypatch):
+    """The same batch through the GRU forms the pipelined benchmark uses (the fused cluster launch; 128 sequences on the
+    tensor-memory lanes with blocked activations and the logits GEMM fed from them): posteriors of 8 of the 1024 chunks
+    within 1e-4 of the pinned float32 oracle at the full chunk length, and the basecalls of the single-batch form."""
+    from sloika_b200 import engine, zoo
+    np.random.seed(2)
+    net = zoo.raw_rgrgr().compile()
+    gen = torch.Generator(device='cuda:0').manual_seed(2)
+    x = torch.randn((4000, 1024, 1), generator=gen, device='cuda:0')
+    base = net.forward_device(x, None, fused_decode=True)
+    s0, p0, l0 = decode.viterbi_batch(base, None, min_prob=1e-5, return_device=True)
+    monkeypatch.setenv('SLOIKA_B200_FUSED_GRU', '1')
+    monkeypatch.setenv('SLOIKA_B200_GRU_SEQ', '1' if form == 'seq' else '0')
+    engine.TIMER.reset()
+    engine.TIMER.enabled = True
+    try:
+        post = net.forward_device(x, None)
+        fused = net.forward_device(x, None, fused_decode=True)
+        torch.cuda.synchronize()
+        ran = set(engine.TIMER.totals_ms())
+    finally:
+        engine.TIMER.enabled = False
+    assert ('gru_seq' if form == 'seq' else 'gru_fused') in ran and 'gru_recurrence' not in ran
+    cols = [0, 7, 8, 300, 511, 512, 1000, 1023]
+    ref = forward_ref.run(net.network.json(params=True), x[:, cols].cpu().numpy())
+    assert float(np.abs(post.data[:, cols].cpu().numpy() - ref).max()) < 1e-4
+    s1, p1, l1 = decode.viterbi_batch(fused, None, min_prob=1e-5, return_device=True)
+    # two float32 evaluations of the same network: a near-tie may flip in a handful of the 1024 reads
+    same = (l1 == l0) & ((p1 == p0).all(dim=1))
+    assert int(same.sum()) >= 1016
+    torch.testing.assert_close(s1, s0, rtol=1e-4, atol=5e-2)
