@@ -77,14 +77,16 @@ __device__ __forceinline__ void store_operand8(uint32_t hi_col, uint32_t lo_col,
 __host__ __device__ constexpr int tile_bytes(int rows, int kblocks) { return rows * 64 * kblocks; }
 
 // HP / IP: hidden / input size padded to a multiple of 32 (32, 64, 96)
-template <int HP, int IP>
+// BLK: both tensors are in the blocked layout (known at compile time: the row-major access code and its registers are gone)
+template <int HP, int IP, bool BLK>
 __global__ void __launch_bounds__(NTHREADS, 1)   // 96 registers: the fifth warp of a sub-partition has to fit its 16 K file
 gru_seq_kernel(const float *__restrict__ x, long ldx, const float *__restrict__ iW, const float *__restrict__ bias,
                const float *__restrict__ sW, const float *__restrict__ sW2, float *__restrict__ y, long ldy,
-               const int32_t *__restrict__ lengths, int T, int B, int I, int H, int reverse, int xblocked, int yblocked,
+               const int32_t *__restrict__ lengths, int T, int B, int I, int H, int reverse, int xblocked_rt, int yblocked_rt,
                const Gate gate)
 {
     if (gate_closed(gate)) return;
+    const bool xblocked = BLK || xblocked_rt != 0, yblocked = BLK || yblocked_rt != 0;
     constexpr int KBH = HP / 32, KBI = IP / 32;          // K blocks of 32
     constexpr int UPT = HP / 4, XPT = IP / 4;            // units / input features per thread
     constexpr int NCH = UPT / 8, NXC = XPT / 8;          // chunks of 8
@@ -439,7 +441,7 @@ static int launch(const float *x, long ldx, const float *iW, const float *bias, 
     const size_t smem = 1024 + 2 * (size_t)(tile_bytes(2 * HP, HP / 32) + tile_bytes(HP, HP / 32) + tile_bytes(3 * HP, IP / 32)) +
                         (size_t)3 * HP * 4 + sizeof(SBars) + 64;
     size_t ask = smem < 116 * 1024 ? 116 * 1024 : smem;     // one CTA per SM: it owns the SM's tensor memory
-    auto kern = gru_seq_kernel<HP, IP>;
+    auto kern = (xblocked && yblocked) ? gru_seq_kernel<HP, IP, true> : gru_seq_kernel<HP, IP, false>;
     cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ask);
     if (err != cudaSuccess) return (int)err;
     kern<<<(unsigned)ceil_div(B, MSEQ), NTHREADS, ask, st>>>(x, ldx, iW, bias, sW, sW2, y, ldy, lengths, T, B, I, H, reverse, xblocked, yblocked, gate);
