@@ -66,7 +66,9 @@ int sloika_conv1d_fwd(const float *x, const float *W, const float *bias, float *
                       const int32_t *lengths, int T, int B, int Cin, int Cout, int winlen, int stride,
                       int pad_l, int pad_r, int act, void *stream);
 /* Same, and additionally folds max |y| into *absmax (atomic max; the caller zeroes it first; NULL = off): lets the next
- * layer pick the cheaper operand format for outputs that are not bounded by construction (elu). */
+ * layer pick the cheaper operand format for outputs that are not bounded by construction (elu).
+ * ldy = -1: y is written in the BLOCKED layout of sloika_gru_seq_fwd (sloika_blocked_bytes(T_out, B, Cout) bytes, 16-byte
+ * aligned); raw-signal shape only (Cin = 1, winlen = 11, Cout a multiple of 4), SLOIKA_ERR_UNSUPPORTED otherwise. */
 int sloika_conv1d_fwd_ex(const float *x, const float *W, const float *bias, float *y, long ldy,
                       const int32_t *lengths, int T, int B, int Cin, int Cout, int winlen, int stride,
                       int pad_l, int pad_r, int act, float *absmax, void *stream);
@@ -176,16 +178,19 @@ int sloika_gru_fwd_gated(const float *x, long ldx, const float *iW, const float 
  * (ldx / ldy are ignored for a blocked tensor): the layout in which a warp's 128-bit accesses are contiguous when its lanes
  * are sequences.  sloika_blocked_bytes gives the size of such a tensor, sloika_block_layout_fwd converts (to_blocked = 1:
  * row-major src with row pitch ld -> blocked dst; 0: blocked src -> row-major dst with row pitch ld).
- * sloika_gru_seq_fwd_gated is the layer for a ROW-MAJOR input whose range only the device knows (absmax / limit as in
- * sloika_gru_fwd_gated) with the output in the blocked layout yb either way: below the limit x -> xb (blocked scratch) and
- * this kernel, otherwise tf32 projection into vI, recurrence into the row-major scratch y, y -> yb.
+ * sloika_gru_seq_fwd_gated is the layer for an input whose range only the device knows (absmax / limit as in
+ * sloika_gru_fwd_gated) with the output in the blocked layout yb either way.  x is row-major with pitch ldx (x_blocked = 0,
+ * `scratch` receives its blocked copy) or already blocked (x_blocked = 1, as sloika_conv1d_fwd_ex writes it with ldy = -1;
+ * `scratch` is then a row-major buffer of pitch ldx, written only if the range check fails).  Below the limit: this kernel;
+ * otherwise tf32 projection into vI, recurrence into the row-major scratch y, y -> yb.
  */
 size_t sloika_blocked_bytes(int T, int B, int F);
 int sloika_block_layout_fwd(const float *src, float *dst, long ld, int T, int B, int F, int to_blocked, void *stream);
-int sloika_gru_seq_fwd_gated(const float *x, long ldx, const float *iW, const float *sW, const float *sW2,
-                             const float *b, float *yb, float *xb, float *y, long ldy, float *vI, long ldv,
-                             const int32_t *lengths, int T, int B, int I, int H, int reverse, int act, int gate_act,
-                             long seqs_in_flight, const float *absmax, float limit, void *stream);
+int sloika_gru_seq_fwd_gated(const float *x, long ldx, int x_blocked, const float *iW, const float *sW,
+                             const float *sW2, const float *b, float *yb, float *scratch, float *y, long ldy,
+                             float *vI, long ldv, const int32_t *lengths, int T, int B, int I, int H, int reverse,
+                             int act, int gate_act, long seqs_in_flight, const float *absmax, float limit,
+                             void *stream);
 int sloika_gru_seq_fwd(const float *x, long ldx, const float *iW, const float *sW, const float *sW2,
                        const float *b, float *y, long ldy, const int32_t *lengths, int T, int B, int I, int H,
                        int reverse, int act, int gate_act, int layout, void *stream);

@@ -48,7 +48,7 @@ EXPORTS = {
                                   ctypes.c_float, _p]),
     'sloika_blocked_bytes': (_z, [_i, _i, _i]),
     'sloika_block_layout_fwd': (_i, [_p, _p, _l, _i, _i, _i, _i, _p]),
-    'sloika_gru_seq_fwd_gated': (_i, [_p, _l, _p, _p, _p, _p, _p, _p, _p, _l, _p, _l, _p, _i, _i, _i, _i, _i, _i, _i, _l, _p,
+    'sloika_gru_seq_fwd_gated': (_i, [_p, _l, _i, _p, _p, _p, _p, _p, _p, _p, _l, _p, _l, _p, _i, _i, _i, _i, _i, _i, _i, _l, _p,
                                       ctypes.c_float, _p]),
     'sloika_gru_seq_fwd': (_i, [_p, _l, _p, _p, _p, _p, _p, _l, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     'sloika_gru_recurrence_fwd_ex': (_i, [_p, _l, _p, _p, _p, _l, _p, _i, _i, _i, _i, _i, _i, _l, _p]),

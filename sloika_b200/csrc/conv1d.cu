@@ -106,6 +106,78 @@ conv1d_raw_kernel(const float *__restrict__ x, const float *__restrict__ W, cons
     }
 }
 
+// The same convolution writing the BLOCKED layout of the sequences-on-lanes GRU (include/sloika_b200.h, sloika_gru_seq_fwd):
+// element (t, b, c) at (((t * nblk + b / 128) * (Cout / 4) + c / 4) * 128 + b % 128) * 4 + c % 4.  For the stores to be
+// contiguous the lanes of a warp must be consecutive SEQUENCES, so the mapping is turned: lane = sequence (BT = 32), warp =
+// group of four channels; a warp walks the channel groups, reloading its 44 weights per group, and the time tile inside.
+template <int WIN, int ACT>
+__global__ void __launch_bounds__(256, 2)
+conv1d_raw_blocked_kernel(const float *__restrict__ x, const float *__restrict__ W, const float *__restrict__ bias,
+                          float *__restrict__ y, const int32_t *__restrict__ lengths, int T, int B, int Cout, int stride,
+                          int pad_l, int Tout, int TT, unsigned *__restrict__ absmax_bits)
+{
+    constexpr int BT = 32;
+    extern __shared__ float xs[];                    // [rows][BT]
+    const int b0 = blockIdx.y * BT;
+    const int t0 = blockIdx.x * TT;
+    const int rows = (TT - 1) * stride + WIN;
+    const int nc4 = Cout >> 2;
+    for (int e = threadIdx.x; e < rows * BT; e += blockDim.x) {
+        const int r = e / BT, b = e - r * BT;
+        const int tin = t0 * stride - pad_l + r;
+        const int bg = b0 + b;
+        float v = 0.0f;
+        if (bg < B && tin >= 0 && tin < T) {
+            const int len = lengths ? lengths[bg] : T;
+            if (tin < len) v = __ldg(x + (long)tin * B + bg);
+        }
+        xs[e] = v;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int bg = b0 + lane;
+    const long nblk = (B + 127) / 128;
+    float4 *y4 = reinterpret_cast<float4 *>(y);
+    float amax = 0.0f;
+    for (int c4 = warp; c4 < nc4; c4 += nwarps) {
+        float2 wa[WIN], wb[WIN];
+#pragma unroll
+        for (int k = 0; k < WIN; k++) {
+            wa[k].x = __ldg(W + (4 * c4 + 0) * WIN + k);
+            wa[k].y = __ldg(W + (4 * c4 + 1) * WIN + k);
+            wb[k].x = __ldg(W + (4 * c4 + 2) * WIN + k);
+            wb[k].y = __ldg(W + (4 * c4 + 3) * WIN + k);
+        }
+        const float4 bv = __ldg(reinterpret_cast<const float4 *>(bias) + c4);
+        if (bg >= B) continue;
+        for (int tl = 0; tl < TT; tl++) {
+            const int t = t0 + tl;
+            if (t >= Tout) break;
+            float2 a0 = make_float2(bv.x, bv.y), a1 = make_float2(bv.z, bv.w);
+            const float *xp = xs + (tl * stride) * BT + lane;
+#pragma unroll
+            for (int k = 0; k < WIN; k++) {
+                const float xv = xp[k * BT];
+                const float2 x2 = make_float2(xv, xv);
+                a0 = fma2(wa[k], x2, a0);
+                a1 = fma2(wb[k], x2, a1);
+            }
+            float4 acc;
+            acc.x = conv_act<ACT>(a0.x);
+            acc.y = conv_act<ACT>(a0.y);
+            acc.z = conv_act<ACT>(a1.x);
+            acc.w = conv_act<ACT>(a1.y);
+            __stcs(y4 + (((long)t * nblk + (bg >> 7)) * nc4 + c4) * 128 + (bg & 127), acc);
+            amax = fmaxf(amax, fmaxf(fmaxf(fabsf(acc.x), fabsf(acc.y)), fmaxf(fabsf(acc.z), fabsf(acc.w))));
+        }
+    }
+    if (absmax_bits) {
+        const unsigned mask = __activemask();
+        const unsigned wmax = __reduce_max_sync(mask, __float_as_uint(amax));
+        if ((threadIdx.x & 31) == (unsigned)(__ffs(mask) - 1)) atomicMax(absmax_bits, wmax);
+    }
+}
+
 // General case (any Cin / winlen / Cout): one thread per output element, operands through L1/L2.
 // Not on the raw-signal hot path; kept so the operator covers the reference's full signature.
 __global__ void conv1d_generic_kernel(const float *__restrict__ x, const float *__restrict__ W,
@@ -157,14 +229,34 @@ extern "C" int sloika_conv1d_fwd_ex(const float *x, const float *W, const float 
 {
     unsigned *absmax_bits = reinterpret_cast<unsigned *>(absmax);
     if (!x || !W || !bias || !y) return SLOIKA_ERR_ARG;
+    const bool blocked_out = ldy == -1;               // y in the blocked layout of sloika_gru_seq_fwd (raw-signal shape only)
     if (T < 0 || B <= 0 || Cin <= 0 || Cout <= 0 || winlen <= 0 || stride <= 0 || pad_l < 0 || pad_r < 0 ||
-        ldy < Cout)
+        (!blocked_out && ldy < Cout))
         return SLOIKA_ERR_ARG;
     if (!act_known(act)) return SLOIKA_ERR_UNSUPPORTED;
     const long span = (long)T + pad_l + pad_r - winlen;
     const int Tout = span < 0 ? 0 : (int)(span / stride + 1);
     if (Tout == 0) return SLOIKA_OK;
     cudaStream_t st = (cudaStream_t)stream;
+
+    if (blocked_out) {
+        const int TT = 16;
+        const size_t smem = sizeof(float) * ((size_t)(TT - 1) * stride + winlen) * 32;
+        if (Cin != 1 || winlen != 11 || Cout % 4 != 0 || ((uintptr_t)y & 15) != 0 || ((uintptr_t)bias & 15) != 0 ||
+            smem > 48 * 1024 || ceil_div(B, 32) > 65535)
+            return SLOIKA_ERR_UNSUPPORTED;
+        dim3 grid((unsigned)ceil_div(Tout, TT), (unsigned)ceil_div(B, 32));
+#define CONV_BLK(A) conv1d_raw_blocked_kernel<11, A><<<grid, 256, smem, st>>>(x, W, bias, y, lengths, T, B, Cout, stride, pad_l, \
+                                                                               Tout, TT, absmax_bits)
+        switch (act) {
+            case SLOIKA_ACT_ELU: CONV_BLK(SLOIKA_ACT_ELU); break;
+            case SLOIKA_ACT_TANH: CONV_BLK(SLOIKA_ACT_TANH); break;
+            case SLOIKA_ACT_SIGMOID: CONV_BLK(SLOIKA_ACT_SIGMOID); break;
+            default: CONV_BLK(SLOIKA_ACT_LINEAR); break;
+        }
+#undef CONV_BLK
+        SLOIKA_RETURN_LAUNCH_STATUS();
+    }
 
     const bool aligned = (Cout % 4 == 0) && (ldy % 4 == 0) && (((uintptr_t)y & 15) == 0) &&
                          (((uintptr_t)bias & 15) == 0) && (Cout / 4 <= 256);

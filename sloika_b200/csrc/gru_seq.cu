@@ -590,28 +590,41 @@ int dispatch_gated(const float *vI, long ldv, const float *sW, const float *sW2,
 }
 }  // namespace sloika
 
-// The layer for a ROW-MAJOR input whose range only the device knows (the elu convolution's output; `absmax` as in
-// sloika_gru_fwd_gated), with the output in the BLOCKED layout `yb` either way:
-//   max |x| <  limit : x -> blocked (xb), then the sequences-on-lanes launch xb -> yb
-//   max |x| >= limit : tf32-split projection GEMM into vI, the recurrence kernel into the row-major scratch y, y -> yb
+// The layer for an input whose range only the device knows (the elu convolution's output; `absmax` as in
+// sloika_gru_fwd_gated), with the output in the BLOCKED layout `yb` either way.  x is row-major with pitch ldx
+// (x_blocked = 0; `scratch` then holds its blocked copy) or already blocked (x_blocked = 1; `scratch` is a row-major
+// [T][B] buffer of pitch ldx that is written only if the range check fails):
+//   max |x| <  limit : (x -> blocked scratch,) then the sequences-on-lanes launch -> yb
+//   max |x| >= limit : (x -> row-major scratch,) tf32-split projection GEMM into vI, the recurrence kernel into the row-major
+//                      scratch y, y -> yb
 // Every launch of the form that is ruled out returns at once.
-extern "C" int sloika_gru_seq_fwd_gated(const float *x, long ldx, const float *iW, const float *sW, const float *sW2,
-                                        const float *b, float *yb, float *xb, float *y, long ldy, float *vI, long ldv,
-                                        const int32_t *lengths, int T, int B, int I, int H, int reverse, int act, int gate_act,
-                                        long seqs_in_flight, const float *absmax, float limit, void *stream)
+extern "C" int sloika_gru_seq_fwd_gated(const float *x, long ldx, int x_blocked, const float *iW, const float *sW,
+                                        const float *sW2, const float *b, float *yb, float *scratch, float *y, long ldy,
+                                        float *vI, long ldv, const int32_t *lengths, int T, int B, int I, int H, int reverse,
+                                        int act, int gate_act, long seqs_in_flight, const float *absmax, float limit,
+                                        void *stream)
 {
-    if (!absmax || !vI || !xb || !yb || !y || !(limit > 0.0f) || ldv < 3L * H || ldy < H) return SLOIKA_ERR_ARG;
-    if ((ldv & 3) != 0 || ((uintptr_t)vI & 15) != 0 || (long)T * B < 128) return SLOIKA_ERR_UNSUPPORTED;
+    if (!absmax || !vI || !scratch || !yb || !y || !(limit > 0.0f) || ldv < 3L * H || ldy < H || ldx < I) return SLOIKA_ERR_ARG;
+    if ((ldv & 3) != 0 || ((uintptr_t)vI & 15) != 0 || (ldx & 3) != 0 || (long)T * B < 128) return SLOIKA_ERR_UNSUPPORTED;
     unsigned limit_bits;
     memcpy(&limit_bits, &limit, sizeof(limit_bits));
     const unsigned *word = reinterpret_cast<const unsigned *>(absmax);
     const gru5::Gate below{word, limit_bits, 1}, above{word, limit_bits, 2};
     cudaStream_t st = (cudaStream_t)stream;
-    int rc = gru7::block_layout(x, xb, ldx, T, B, I, 1, st, below);
-    if (rc != SLOIKA_OK || T == 0) return rc;
+    int rc;
+    const float *xb = x_blocked ? x : scratch;
+    const float *xr = x_blocked ? scratch : x;
+    if (!x_blocked) {
+        rc = gru7::block_layout(x, scratch, ldx, T, B, I, 1, st, below);
+        if (rc != SLOIKA_OK || T == 0) return rc;
+    }
     rc = gru7::dispatch(xb, 0, iW, sW, sW2, b, yb, 0, lengths, T, B, I, H, reverse, act, gate_act, 3, st, below);
-    if (rc != SLOIKA_OK) return rc;
-    rc = gemm_tc::launch(x, ldx, iW, b, vI, ldv, (long)T * B, I, 3 * H, SLOIKA_ACT_LINEAR, nullptr, 0, false, st, word, limit_bits, 2);
+    if (rc != SLOIKA_OK || T == 0) return rc;
+    if (x_blocked) {
+        rc = gru7::block_layout(x, scratch, ldx, T, B, I, 0, st, above);
+        if (rc != SLOIKA_OK) return rc;
+    }
+    rc = gemm_tc::launch(xr, ldx, iW, b, vI, ldv, (long)T * B, I, 3 * H, SLOIKA_ACT_LINEAR, nullptr, 0, false, st, word, limit_bits, 2);
     if (rc != SLOIKA_OK) return rc;
     rc = gru5::dispatch_gated(vI, ldv, sW, sW2, y, ldy, lengths, T, B, H, reverse, act, gate_act, seqs_in_flight, st, above);
     if (rc != SLOIKA_OK) return rc;

@@ -54,13 +54,13 @@ class Act(object):
         self._shape = (T, B, F)
 
     @classmethod
-    def from_blocked(cls, blocked, shape, lengths=None, reverse=False, bounded=False):
+    def from_blocked(cls, blocked, shape, lengths=None, reverse=False, bounded=False, absmax=None):
         """An activation that so far exists only in the BLOCKED layout of the sequences-on-lanes GRU kernel
         (include/sloika_b200.h, `sloika_gru_seq_fwd`): the next such layer reads it as it is, anybody else asks for
         `.data` and gets a row-major copy made on the spot (`sloika_block_layout_fwd`)."""
         self = cls.__new__(cls)
         self._blocked, self._data, self._ld, self._shape = blocked, None, None, tuple(int(v) for v in shape)
-        self.lengths, self.reverse, self.bounded, self.absmax = lengths, reverse, bounded, None
+        self.lengths, self.reverse, self.bounded, self.absmax = lengths, reverse, bounded, absmax
         return self
 
     @property
@@ -101,7 +101,7 @@ class Act(object):
 
     def flipped(self):
         if self._data is None:
-            return Act.from_blocked(self._blocked, self._shape, self.lengths, not self.reverse, self.bounded)
+            return Act.from_blocked(self._blocked, self._shape, self.lengths, not self.reverse, self.bounded, self.absmax)
         other = Act(self._data, self.lengths, not self.reverse, self.bounded, self.absmax)
         other._blocked = self._blocked
         return other
@@ -243,23 +243,32 @@ def run_convolution(layer, act, out=None):
         # conv(x) for even windows, asymmetric padding or stride > 1, and no shipped model reverses a convolution
         raise NotImplementedError("Reverse(Convolution) is not implemented on the device")
     Tout = output_length(act.T, layer.winlen, layer.stride, layer.padding)
-    y = _out_buffer(act, Tout, layer.size, out)
     dev = act.device
     bounded = _bounded_fun(layer.fun)
     absmax = None
     if not bounded:                              # elu / linear outputs: let the kernel report their range
         import torch
         absmax = torch.zeros(1, dtype=torch.float32, device=dev)
-    launch('conv1d', 1, lib.sloika_conv1d_fwd_ex,
-           cabi.ptr(act.data), cabi.ptr(layer.W.device(dev)), cabi.ptr(layer.b.device(dev)), cabi.ptr(y),
-           _row_stride(y), cabi.ptr(act.lengths), act.T, act.B, layer.insize, layer.size, layer.winlen,
-           layer.stride, layer.padding[0], layer.padding[1], code_of(layer.fun), cabi.ptr(absmax),
-           cabi.stream_ptr(dev))
     lengths = None
     if act.lengths is not None:
         # per-read output length: each read is padded/convolved on its own (conv.py:66-111)
         span = act.lengths + (layer.padding[0] + layer.padding[1] - layer.winlen)
         lengths = (span.clamp(min=-layer.stride) // layer.stride + 1).clamp(min=0).to(act.lengths.dtype)
+    if out is None and layer.insize == 1 and layer.winlen == 11 and layer.size % 4 == 0 and layer.size <= 96 and Tout > 0 \
+            and layer.stride <= 24 and act.B <= 32 * 65535 and _seq_mode(act.B):
+        # the GRU stack behind it runs with sequences on the lanes: write the blocked layout straight away
+        yb = _blocked_empty(Tout, act.B, layer.size, dev)
+        launch('conv1d', 1, lib.sloika_conv1d_fwd_ex, cabi.ptr(act.data), cabi.ptr(layer.W.device(dev)),
+               cabi.ptr(layer.b.device(dev)), cabi.ptr(yb), -1, cabi.ptr(act.lengths), act.T, act.B, layer.insize,
+               layer.size, layer.winlen, layer.stride, layer.padding[0], layer.padding[1], code_of(layer.fun),
+               cabi.ptr(absmax), cabi.stream_ptr(dev))
+        return Act.from_blocked(yb, (Tout, act.B, layer.size), lengths, act.reverse, bounded, absmax)
+    y = _out_buffer(act, Tout, layer.size, out)
+    launch('conv1d', 1, lib.sloika_conv1d_fwd_ex,
+           cabi.ptr(act.data), cabi.ptr(layer.W.device(dev)), cabi.ptr(layer.b.device(dev)), cabi.ptr(y),
+           _row_stride(y), cabi.ptr(act.lengths), act.T, act.B, layer.insize, layer.size, layer.winlen,
+           layer.stride, layer.padding[0], layer.padding[1], code_of(layer.fun), cabi.ptr(absmax),
+           cabi.stream_ptr(dev))
     return act.like(y, lengths, bounded=bounded, absmax=absmax)
 
 
@@ -370,11 +379,7 @@ def _fused_gru_ok(layer, act):
         return None
     # with many batches in flight the sequences-on-lanes launch (csrc/gru_seq.cu: 128 sequences per CTA, ~60 % of the SM
     # time per sequence, but 3.5 x the latency per layer) is the better form; SLOIKA_B200_GRU_SEQ=1 / 0 forces / forbids it
-    seq_env = os.environ.get('SLOIKA_B200_GRU_SEQ', '')
-    # (small batches -- strong scaling splits one over the GPUs -- would put a single CTA to work for 4 ms per layer: they
-    # keep the fused form)
-    seq = seq_env == '1' or (seq_env != '0' and act.B >= 512 and
-                             max(1, BATCHES_IN_FLIGHT) * _CONCURRENT_BRANCHES >= SEQ_MIN_IN_FLIGHT)
+    seq = _seq_mode(act.B)
     if act.bounded:
         return 'seq' if seq else 'fused'
     if act.absmax is not None and act.T * act.B >= 128 and not os.environ.get('SLOIKA_B200_NO_F16'):
@@ -383,6 +388,17 @@ def _fused_gru_ok(layer, act):
 
 
 SEQ_MIN_IN_FLIGHT = 6
+
+
+def _seq_mode(B):
+    """GRU layers run as the sequences-on-lanes launch (and the layers around them speak its blocked layout): enough
+    batches in flight, and batches of at least 512 sequences (small ones -- strong scaling splits a batch over the GPUs --
+    would put a single CTA to work for 4 ms per layer: they keep the fused form).  SLOIKA_B200_GRU_SEQ=1 / 0 forces /
+    forbids it; SLOIKA_B200_FUSED_GRU=0 (no throughput forms at all) forbids it as well."""
+    env = os.environ.get('SLOIKA_B200_GRU_SEQ', '')
+    if env == '0' or os.environ.get('SLOIKA_B200_FUSED_GRU', '') == '0':
+        return False
+    return env == '1' or (B >= 512 and max(1, BATCHES_IN_FLIGHT) * _CONCURRENT_BRANCHES >= SEQ_MIN_IN_FLIGHT)
 
 
 def _blocked_empty(T, B, F, dev):
@@ -402,14 +418,19 @@ def _run_gru_seq(layer, act, form, out):
     common = (cabi.ptr(layer.iW.device(dev)), cabi.ptr(layer.sW.device(dev)), cabi.ptr(layer.sW2.device(dev)),
               cabi.ptr(layer.b.device(dev)))
     if form == 'seq_gated':
-        xb = _blocked_empty(T, B, I, dev)
         y = _padded_rows(T, B, H, dev)                       # written only if the input leaves the fp16 range
         vI = _padded_rows(T, B, 3 * H, dev)
-        launch('gru_seq', 5, lib.sloika_gru_seq_fwd_gated, cabi.ptr(act.data), act.ld, *common, cabi.ptr(yb), cabi.ptr(xb),
+        if act.blocked is not None and act._data is None:    # the convolution wrote the blocked layout
+            scratch = _padded_rows(T, B, I, dev)             # its row-major copy, made only if the range check fails
+            xptr, ldx, xblk, sptr = cabi.ptr(act.blocked), _row_stride(scratch), 1, cabi.ptr(scratch)
+        else:
+            scratch = _blocked_empty(T, B, I, dev)
+            xptr, ldx, xblk, sptr = cabi.ptr(act.data), act.ld, 0, cabi.ptr(scratch)
+        launch('gru_seq', 5, lib.sloika_gru_seq_fwd_gated, xptr, ldx, xblk, *common, cabi.ptr(yb), sptr,
                cabi.ptr(y), _row_stride(y), cabi.ptr(vI), _row_stride(vI), cabi.ptr(act.lengths), T, B, I, H,
                1 if act.reverse else 0, code_of(layer.fun), code_of(layer.gatefun),
                B * max(1, BATCHES_IN_FLIGHT) * _CONCURRENT_BRANCHES, cabi.ptr(act.absmax), _F16_INPUT_LIMIT, cabi.stream_ptr(dev))
-        for t in (xb, y, vI):
+        for t in (scratch, y, vI):
             t.record_stream(stream)
     else:
         xb = act.blocked

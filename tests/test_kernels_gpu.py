@@ -905,3 +905,27 @@ def test_softmax_logits_from_blocked_input(monkeypatch):
     assert (fused.data - plain.data).abs().max().item() < 2e-4
     assert sum(a != b for a, b in zip(p1, p2)) <= 1            # two float32 roundings of the same network: near-ties may flip
     np.testing.assert_allclose(s1, s2, rtol=1e-4, atol=5e-2)
+
+
+@pytest.mark.parametrize('C,stride,B,ragged', [(96, 5, 150, False), (32, 2, 33, True), (64, 5, 700, True)])
+def test_convolution_blocked_output(C, stride, B, ragged, monkeypatch):
+    """The raw-signal convolution writing the blocked layout (lanes = sequences, `sloika_conv1d_fwd_ex` with ldy = -1) gives
+    bit for bit the values of the row-major kernel, and the same range report."""
+    np.random.seed(C + B)
+    layer = layers.Convolution(1, C, 11, stride, init=_init(), has_bias=True, fun=act.elu)
+    T = 333
+    x = torch.from_numpy(np.random.standard_normal((T, B, 1)).astype(np.float32)).to(DEV)
+    lens = torch.from_numpy(np.random.randint(1, T + 1, size=B).astype(np.int32)).to(DEV) if ragged else None
+    monkeypatch.setenv('SLOIKA_B200_GRU_SEQ', '0')
+    row = layer.run(engine.Act(x, lens))
+    assert row.blocked is None
+    monkeypatch.setenv('SLOIKA_B200_GRU_SEQ', '1')
+    blk = layer.run(engine.Act(x, lens))
+    assert blk.blocked is not None and blk._data is None
+    torch.cuda.synchronize()
+    assert torch.equal(blk.absmax, row.absmax)
+    if lens is not None:
+        assert torch.equal(blk.lengths, row.lengths)
+    got = _from_blocked(blk.blocked.cpu().numpy(), blk.T, B, C)
+    assert np.array_equal(got, row.data.cpu().numpy())
+    assert torch.equal(blk.data, row.data)                       # and through the conversion kernel
