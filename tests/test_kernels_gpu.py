@@ -192,6 +192,35 @@ def test_birnn_parallel_writes_in_place():
     assert np.abs(got - ref).max() < 5e-5
 
 
+@pytest.mark.parametrize('seq', ['0', '1'])
+def test_birnn_through_throughput_forms(seq, monkeypatch):
+    """Parallel branches with the GRU layers forced onto the fused (seq = 0) / sequences-on-lanes (seq = 1) launch: each
+    branch writes its column slice of the shared buffer (the blocked result is converted into the slice), bounded input."""
+    monkeypatch.setenv('SLOIKA_B200_FUSED_GRU', '1')
+    monkeypatch.setenv('SLOIKA_B200_GRU_SEQ', seq)
+    np.random.seed(13)
+    init = _init()
+    net = layers.Serial([layers.birnn(layers.Gru(32, 96, init=init, has_bias=True), layers.Gru(32, 96, init=init, has_bias=True)),
+                         layers.FeedForward(192, 64, init=init, has_bias=True),
+                         layers.birnn(layers.Gru(64, 48, init=init, has_bias=True), layers.Gru(64, 80, init=init, has_bias=True))])
+    x = np.tanh(np.random.standard_normal((60, 140, 32))).astype(np.float32)
+    lengths = np.random.randint(1, 61, size=140).astype(np.int32)
+    lengths[0] = 60
+    a = engine.Act(torch.from_numpy(x).to(DEV), torch.from_numpy(lengths).to(DEV), bounded=True)
+    engine.TIMER.reset()
+    engine.TIMER.enabled = True
+    try:
+        got = net.run(a).data.cpu().numpy()
+        ran = set(engine.TIMER.totals_ms())
+    finally:
+        engine.TIMER.enabled = False
+    assert ('gru_seq' if seq == '1' else 'gru_fused') in ran
+    for b in (0, 1, 70, 139):
+        ref = _oracle(net, x[:lengths[b], b:b + 1])
+        assert np.abs(got[:lengths[b], b] - ref[:, 0]).max() < 5e-5, b
+        assert np.all(got[lengths[b]:, b] == 0)
+
+
 # ------------------------------------------------------------------ whole networks
 @pytest.mark.parametrize('name,T,B', [('raw_rgrgr', 1000, 6), ('raw_rGr', 400, 5), ('bigger_raw_gru', 300, 4),
                                       ('pretrained_like', 900, 3)])
