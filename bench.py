@@ -594,6 +594,8 @@ def run_b200_arm(args):
         "frac_of_paper_roofline": value / world / paper,
         "cpu_baseline": cpu_baseline,
         "clocks": clocks,
+        "device_memory_gb": {"reserved_peak": torch.cuda.max_memory_reserved(dev) / 1e9,
+                             "allocated_peak": torch.cuda.max_memory_allocated(dev) / 1e9},
     }
     print(json.dumps(line), flush=True)
     if world > 1:
